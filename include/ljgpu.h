@@ -1,0 +1,181 @@
+/* include/ljgpu.h - C ABI of libljgpu.so, the B200 (sm_100a) Lennard-Jones integrator.
+ *
+ * This is the drop-in boundary for ONE path of ifilot/lennard-jones-live-simulator: the per-step
+ * integrator behind class LennardJonesSimulation (src/simulator/lennardjonessimulation.h:113-155).
+ * Each entry point names the reference interface it replaces (file:line under the reference's
+ * src/simulator/).  Plain pointers and sizes only; no C++/torch types.
+ *
+ * Conventions
+ *   - every function returns an int status: LJGPU_OK (0) or a negative LJGPU_E* code; the message
+ *     for the calling thread's last failure is ljgpu_last_error();
+ *   - every array argument is a caller-owned HOST buffer of nr_particles elements, structure of
+ *     arrays, in ORIGINAL ATOM ORDER (the order of the arrays given to ljgpu_create), whatever
+ *     order the device keeps internally;
+ *   - all arithmetic is fp64; indices are uint32_t;
+ *   - one handle may be stepped by one thread while other threads call getters: calls on one
+ *     handle are serialised internally, a getter sees the state after the last completed step;
+ *   - there is no CPU fallback: without a usable CUDA device every call fails with LJGPU_ECUDA.
+ */
+#ifndef LJGPU_H
+#define LJGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LJGPU_VERSION_MAJOR 0
+#define LJGPU_VERSION_MINOR 1
+
+enum {
+    LJGPU_OK       =  0,
+    LJGPU_EINVAL   = -1,   /* bad argument / unsupported parameter combination */
+    LJGPU_ECUDA    = -2,   /* CUDA runtime failure (no device, launch error, out of memory ...) */
+    LJGPU_ENCCL    = -3,   /* NCCL failure on the slab path */
+    LJGPU_ESTATE   = -4    /* call not valid in the handle's current state */
+};
+
+/* Which force path integrates the system.  AUTO picks ALLPAIRS for nr_particles <= 8192 or when
+ * the box holds fewer than 3 cells per axis, VERLET otherwise. */
+enum {
+    LJGPU_KERNEL_AUTO     = 0,
+    LJGPU_KERNEL_ALLPAIRS = 1,  /* shared-memory tiled O(N^2), minimum image, atoms stay in caller order */
+    LJGPU_KERNEL_CELL     = 2,  /* cell-sorted atoms, 27-cell stencil evaluated every step            */
+    LJGPU_KERNEL_VERLET   = 3   /* cell-sorted atoms + device Verlet list (skin = shell), the fast path */
+};
+
+/* The ten keys of LennardJonesParameters (lennardjonesparameters.h:32-69) as MainWindow fills
+ * them (src/gui/mainwindow.cpp:67-77), read ONCE here instead of by string on every stage
+ * (lennardjonessimulation.cpp:259-266 etc.), plus the device-side choices. */
+typedef struct ljgpu_params {
+    double  cell_length;     /* cubic box edge L                                   */
+    int32_t nr_particles;    /* N                                                  */
+    int32_t force_kernel;    /* LJGPU_KERNEL_*                                     */
+    double  kT;
+    double  mass;
+    double  sigma;
+    double  rcut;
+    double  epsilon;
+    double  tau;             /* Berendsen coupling time (always on, .cpp:80,368-383) */
+    double  shell;           /* Verlet skin                                        */
+    double  stepsize;        /* informational: dt is passed to every step call     */
+    int32_t device;          /* CUDA device ordinal; -1 = the calling thread's current device */
+    int32_t reserved;
+} ljgpu_params;
+
+typedef struct ljgpu_sim ljgpu_sim;   /* opaque */
+
+/* Wall/device time spent per stage since creation or the last ljgpu_reset_timers(); filled only
+ * while profiling is enabled (ljgpu_set_profiling), measured with CUDA events on the
+ * integrator's own stream. Milliseconds and launch counts. */
+typedef struct ljgpu_timers {
+    double   ms_predict, ms_kick_drift, ms_ghost, ms_force, ms_kick2, ms_rebuild, ms_halo;
+    uint64_t n_predict, n_kick_drift, n_ghost, n_force, n_kick2, n_rebuild, n_halo;
+    uint64_t steps;            /* integrate steps completed                         */
+    uint64_t rebuilds;         /* cell re-binnings (+ list builds) so far           */
+    uint64_t kernel_launches;  /* every kernel this handle has launched             */
+} ljgpu_timers;
+
+/* ---- library -------------------------------------------------------------------------- */
+
+/* Message of the calling thread's most recent failing call ("" if none). */
+const char* ljgpu_last_error(void);
+
+/* Number of CUDA devices visible (0 if none / driver missing). Never fails. */
+int ljgpu_device_count(void);
+
+/* ---- initial state (host) ---------------------------------------------------------------- */
+
+/* LennardJonesSimulation::initialize() + get_gauss() (lennardjonessimulation.cpp:185-252):
+ * simple-cubic start lattice and Gaussian velocities drawn from a process-wide, never-reseeded
+ * std::default_random_engine + std::normal_distribution<double>(0,1), mean velocity removed.
+ * Runs on the host with the same std:: calls as the reference, so a fresh process reproduces
+ * the reference's start state bit for bit. */
+int ljgpu_host_initialize(const ljgpu_params* p, double* x, double* y, double* z,
+                          double* vx, double* vy, double* vz);
+
+/* Reseed that process-wide generator to its default-constructed state (test convenience; the
+ * reference has no such call). */
+void ljgpu_host_rng_reset(void);
+
+/* ---- lifecycle --------------------------------------------------------------------------- */
+
+/* Constructor, lennardjonessimulation.cpp:31-63: uploads the state, bins the atoms, evaluates
+ * forces and epot; ekin reads 0.0 until the first step, as in the reference. */
+int ljgpu_create(const ljgpu_params* p, const double* x, const double* y, const double* z,
+                 const double* vx, const double* vy, const double* vz, ljgpu_sim** out);
+
+void ljgpu_destroy(ljgpu_sim* s);
+
+/* Replace positions and velocities (original order) and redo what the constructor does. */
+int ljgpu_set_state(ljgpu_sim* s, const double* x, const double* y, const double* z,
+                    const double* vx, const double* vy, const double* vz);
+
+/* The reference re-reads its parameter map on every stage, so a caller may change kT, tau, mass,
+ * sigma or epsilon between steps (LennardJonesParameters::set_param, lennardjonesparameters.h:66).
+ * This call applies such a change; cell_length, nr_particles, rcut and shell must be unchanged. */
+int ljgpu_update_params(ljgpu_sim* s, const ljgpu_params* p);
+
+/* ---- stepping ---------------------------------------------------------------------------- */
+
+/* LennardJonesSimulation::integrate(step, dt), lennardjonessimulation.cpp:70-114.  Returns when
+ * the step is complete and published. */
+int ljgpu_step(ljgpu_sim* s, uint32_t step, double dt);
+
+/* n consecutive integrate() calls (step indices first .. first+n-1) without returning to the
+ * caller in between: the headless loop of ThreadIntegrate::run (threadintegrate.cpp:38-66)
+ * minus its 2000 steps/s throttle. */
+int ljgpu_step_n(ljgpu_sim* s, uint32_t first, uint32_t n, double dt);
+
+/* ---- queries (original atom order) --------------------------------------------------------- */
+
+/* get_positions_copy / get_render_x,y,z (lennardjonessimulation.h:131-143, .cpp:159-171):
+ * published positions, wrapped into [0, L] by the reference's own expression (.cpp:431-433). */
+int ljgpu_get_positions(ljgpu_sim* s, double* x, double* y, double* z);
+/* get_velocities_copy (.cpp:173-180). */
+int ljgpu_get_velocities(ljgpu_sim* s, double* vx, double* vy, double* vz);
+/* The reference's private fx,fy,fz (lennardjonessimulation.h:91) - parity probe. */
+int ljgpu_get_forces(ljgpu_sim* s, double* fx, double* fy, double* fz);
+/* get_ekin / get_epot / get_etot (lennardjonessimulation.h:146-148). */
+int ljgpu_get_energies(ljgpu_sim* s, double* ekin, double* epot, double* etot);
+/* Energies of the most recent steps, newest last: fills at most max_entries triples and returns
+ * how many in *n_out.  step_index[] are the values passed as `step`. */
+int ljgpu_get_energy_history(ljgpu_sim* s, uint32_t max_entries, uint32_t* step_index,
+                             double* ekin, double* epot, uint32_t* n_out);
+
+/* GraphWidget::set_particle_speed (graphwidget.cpp:205-233): counts[b] = number of atoms with
+ * b == min((int)(|v| / vmax * nbins), nbins-1); the GUI uses nbins = 100, vmax = 10.0
+ * (graphwidget.h:73-74). */
+int ljgpu_get_speed_histogram(ljgpu_sim* s, uint32_t nbins, double vmax, uint64_t* counts);
+/* GraphWidget::set_params (graphwidget.cpp:55-73): Maxwell-Boltzmann expectation per bin. Host. */
+int ljgpu_maxwell_boltzmann(double kT, double mass, int32_t nr_particles, uint32_t nbins,
+                            double vmax, double* expected);
+
+/* Parity probes of build_neighbor_list (lennardjonessimulation.cpp:441-551) on the published
+ * positions, bit-exact with the reference's comparisons:
+ *   cell_of_atom[i] = iz*nx*ny + iy*nx + ix with ix = min((unsigned)(x/dx), nx-1)   (:447-476)
+ *   count_of_atom[i] = #{ j != i : min-image dist2 <= cutoff^2 }  when inclusive != 0  (:518-540)
+ *                    = #{ j != i : min-image dist2 <  cutoff^2 }  when inclusive == 0  (:291-305)
+ * cutoff must not exceed rcut + shell. */
+int ljgpu_get_cell_ids(ljgpu_sim* s, uint32_t* cell_of_atom, uint32_t dims[3]);
+int ljgpu_get_neighbor_counts(ljgpu_sim* s, double cutoff, int inclusive, uint32_t* count_of_atom);
+
+/* write_to_movie_file (lennardjonessimulation.cpp:121-157): u32 N when create != 0, then one
+ * frame = 3 f64 box edges + N x 7 f64 {x,y,z,vx,vy,vz,|v|}, native endianness. */
+int ljgpu_write_movie_frame(ljgpu_sim* s, const char* path, int create);
+
+/* ---- introspection --------------------------------------------------------------------------- */
+
+int ljgpu_set_profiling(ljgpu_sim* s, int enabled);
+int ljgpu_get_timers(ljgpu_sim* s, ljgpu_timers* out);
+int ljgpu_reset_timers(ljgpu_sim* s);
+/* Force path actually in use (LJGPU_KERNEL_*), cells per axis, current list capacity per atom. */
+int ljgpu_get_layout(ljgpu_sim* s, int32_t* force_kernel, uint32_t* cells_per_axis,
+                     uint32_t* list_capacity, uint64_t* n_ghosts);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LJGPU_H */

@@ -1,0 +1,298 @@
+"""ctypes view of libljgpu.so with the method names of the reference's LennardJonesSimulation.
+
+Reference interface mirrored: /root/reference/src/simulator/lennardjonessimulation.h:113-155 and
+lennardjonesparameters.h:32-69.  There is no CPU fallback: if the CUDA library is missing or no
+device is usable the calls raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+KERNEL_AUTO, KERNEL_ALLPAIRS, KERNEL_CELL, KERNEL_VERLET = 0, 1, 2, 3
+
+# every symbol include/ljgpu.h declares
+EXPORTED_SYMBOLS = [
+    "ljgpu_last_error", "ljgpu_device_count", "ljgpu_host_initialize", "ljgpu_host_rng_reset",
+    "ljgpu_create", "ljgpu_destroy", "ljgpu_set_state", "ljgpu_update_params", "ljgpu_step",
+    "ljgpu_step_n", "ljgpu_get_positions", "ljgpu_get_velocities", "ljgpu_get_forces",
+    "ljgpu_get_energies", "ljgpu_get_energy_history", "ljgpu_get_speed_histogram",
+    "ljgpu_maxwell_boltzmann", "ljgpu_get_cell_ids", "ljgpu_get_neighbor_counts",
+    "ljgpu_write_movie_frame", "ljgpu_set_profiling", "ljgpu_get_timers", "ljgpu_reset_timers",
+    "ljgpu_get_layout",
+]
+
+
+class LJGpuError(RuntimeError):
+    pass
+
+
+class LJParams(C.Structure):
+    """struct ljgpu_params (include/ljgpu.h)."""
+    _fields_ = [
+        ("cell_length", C.c_double), ("nr_particles", C.c_int32), ("force_kernel", C.c_int32),
+        ("kT", C.c_double), ("mass", C.c_double), ("sigma", C.c_double), ("rcut", C.c_double),
+        ("epsilon", C.c_double), ("tau", C.c_double), ("shell", C.c_double), ("stepsize", C.c_double),
+        ("device", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+class LJTimers(C.Structure):
+    _fields_ = [(k, C.c_double) for k in
+                ("ms_predict", "ms_kick_drift", "ms_ghost", "ms_force", "ms_kick2", "ms_rebuild", "ms_halo")] + \
+               [(k, C.c_uint64) for k in
+                ("n_predict", "n_kick_drift", "n_ghost", "n_force", "n_kick2", "n_rebuild", "n_halo",
+                 "steps", "rebuilds", "kernel_launches")]
+
+
+_LIB = None
+
+
+def library_path():
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libljgpu.so")
+
+
+def load_library():
+    """Load libljgpu.so (built in-tree by __graft_entry__.build() / make). Raises if absent."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        raise LJGpuError(f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                         "(there is no CPU fallback)")
+    lib = C.CDLL(path)
+    dp = C.POINTER(C.c_double)
+    vp = C.c_void_p
+    lib.ljgpu_last_error.restype = C.c_char_p
+    lib.ljgpu_device_count.restype = C.c_int
+    lib.ljgpu_host_initialize.argtypes = [C.POINTER(LJParams)] + [vp] * 6
+    lib.ljgpu_create.argtypes = [C.POINTER(LJParams)] + [vp] * 6 + [C.POINTER(vp)]
+    lib.ljgpu_destroy.argtypes = [vp]
+    lib.ljgpu_destroy.restype = None
+    lib.ljgpu_set_state.argtypes = [vp] + [vp] * 6
+    lib.ljgpu_update_params.argtypes = [vp, C.POINTER(LJParams)]
+    lib.ljgpu_step.argtypes = [vp, C.c_uint32, C.c_double]
+    lib.ljgpu_step_n.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_double]
+    for name in ("ljgpu_get_positions", "ljgpu_get_velocities", "ljgpu_get_forces"):
+        getattr(lib, name).argtypes = [vp, vp, vp, vp]
+    lib.ljgpu_get_energies.argtypes = [vp, dp, dp, dp]
+    lib.ljgpu_get_energy_history.argtypes = [vp, C.c_uint32, vp, vp, vp, C.POINTER(C.c_uint32)]
+    lib.ljgpu_get_speed_histogram.argtypes = [vp, C.c_uint32, C.c_double, vp]
+    lib.ljgpu_maxwell_boltzmann.argtypes = [C.c_double, C.c_double, C.c_int32, C.c_uint32, C.c_double, vp]
+    lib.ljgpu_get_cell_ids.argtypes = [vp, vp, vp]
+    lib.ljgpu_get_neighbor_counts.argtypes = [vp, C.c_double, C.c_int, vp]
+    lib.ljgpu_write_movie_frame.argtypes = [vp, C.c_char_p, C.c_int]
+    lib.ljgpu_set_profiling.argtypes = [vp, C.c_int]
+    lib.ljgpu_get_timers.argtypes = [vp, C.POINTER(LJTimers)]
+    lib.ljgpu_reset_timers.argtypes = [vp]
+    lib.ljgpu_get_layout.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
+                                     C.POINTER(C.c_uint64)]
+    _LIB = lib
+    return lib
+
+
+def _check(lib, rc):
+    if rc != 0:
+        raise LJGpuError(f"ljgpu error {rc}: {lib.ljgpu_last_error().decode()}")
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def device_count():
+    return load_library().ljgpu_device_count()
+
+
+class LennardJonesParameters:
+    """String-keyed parameter set with the reference's ten keys and its error behaviour:
+    get_param of a missing key raises RuntimeError("Could not find parameter: <name>")
+    (lennardjonesparameters.h:52-58)."""
+    KEYS = ("cell_length", "nr_particles", "kT", "mass", "sigma", "rcut", "epsilon", "tau", "shell", "stepsize")
+
+    def __init__(self, **kw):
+        self._p = {}
+        for k, v in kw.items():
+            self.set_param(k, v)
+
+    def set_param(self, name, value):
+        self._p[name] = value
+
+    def get_param(self, name, typ=float):
+        if name not in self._p:
+            raise RuntimeError("Could not find parameter: " + name)
+        v = self._p[name]
+        if typ is int:
+            return int(round(float(v)))      # QVariant::value<int>() of a double/string rounds
+        return float(v)
+
+    @classmethod
+    def default(cls):
+        """The shipped default configuration, src/gui/mainwindow.cpp:67-77."""
+        return cls(cell_length=14.938, nr_particles=1000, kT=1.0, mass=1.0, sigma=1.0, rcut=2.5,
+                   epsilon=1.0, tau=0.5, shell=0.4, stepsize=0.001)
+
+    def to_struct(self, force_kernel=KERNEL_AUTO, device=-1):
+        g = self.get_param
+        return LJParams(g("cell_length"), g("nr_particles", int), force_kernel, g("kT"), g("mass"), g("sigma"),
+                        g("rcut"), g("epsilon"), g("tau"), g("shell"), g("stepsize"), device, 0)
+
+
+def host_rng_reset():
+    load_library().ljgpu_host_rng_reset()
+
+
+def host_initialize(params, force_kernel=KERNEL_AUTO):
+    """initialize() of the reference (lennardjonessimulation.cpp:185-246) -> six float64 arrays."""
+    lib = load_library()
+    st = params.to_struct(force_kernel) if isinstance(params, LennardJonesParameters) else params
+    n = st.nr_particles
+    arrs = [np.empty(n, dtype=np.float64) for _ in range(6)]
+    rc = lib.ljgpu_host_initialize(C.byref(st), *[_ptr(a) for a in arrs])
+    if rc != 0:
+        raise LJGpuError(f"ljgpu_host_initialize failed ({rc})")
+    return arrs
+
+
+def maxwell_boltzmann(kT, mass, n, nbins=100, vmax=10.0):
+    out = np.empty(nbins, dtype=np.float64)
+    rc = load_library().ljgpu_maxwell_boltzmann(kT, mass, n, nbins, vmax, _ptr(out))
+    if rc != 0:
+        raise LJGpuError(f"ljgpu_maxwell_boltzmann failed ({rc})")
+    return out
+
+
+class LennardJonesSimulation:
+    """Same public surface as the reference class (lennardjonessimulation.h:113-155), GPU-backed."""
+
+    def __init__(self, params, state=None, force_kernel=KERNEL_AUTO, device=-1):
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        self.params = params
+        self._struct = params.to_struct(force_kernel, device)
+        self.n = self._struct.nr_particles
+        if state is None:
+            state = host_initialize(self._struct)
+        state = [np.ascontiguousarray(a, dtype=np.float64) for a in state]
+        if len(state) != 6 or any(a.shape != (self.n,) for a in state):
+            raise ValueError("state must be six arrays of nr_particles float64")
+        _check(self._lib, self._lib.ljgpu_create(C.byref(self._struct), *[_ptr(a) for a in state], C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            self._lib.ljgpu_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- stepping ----------------------------------------------------------------------------
+    def integrate(self, step, dt):
+        _check(self._lib, self._lib.ljgpu_step(self._h, step, dt))
+
+    def integrate_n(self, first, n, dt):
+        _check(self._lib, self._lib.ljgpu_step_n(self._h, first, n, dt))
+
+    def set_state(self, state):
+        state = [np.ascontiguousarray(a, dtype=np.float64) for a in state]
+        _check(self._lib, self._lib.ljgpu_set_state(self._h, *[_ptr(a) for a in state]))
+
+    def set_param(self, name, value):
+        """LennardJonesParameters::set_param on a live simulation (kT, tau, mass, sigma, epsilon)."""
+        self.params.set_param(name, value)
+        st = self.params.to_struct(self._struct.force_kernel, self._struct.device)
+        _check(self._lib, self._lib.ljgpu_update_params(self._h, C.byref(st)))
+        self._struct = st
+
+    # -- queries -----------------------------------------------------------------------------
+    def get_params(self):
+        return self.params
+
+    def get_dims(self):
+        length = self._struct.cell_length
+        return (length, length, length)
+
+    def get_particle_count(self):
+        return self.n
+
+    def _get3(self, fn):
+        a = [np.empty(self.n, dtype=np.float64) for _ in range(3)]
+        _check(self._lib, fn(self._h, *[_ptr(x) for x in a]))
+        return a
+
+    def get_positions_soa(self):
+        return self._get3(self._lib.ljgpu_get_positions)
+
+    def get_velocities_soa(self):
+        return self._get3(self._lib.ljgpu_get_velocities)
+
+    def get_forces_soa(self):
+        return self._get3(self._lib.ljgpu_get_forces)
+
+    def get_positions_copy(self):
+        return np.stack(self.get_positions_soa(), axis=1)
+
+    def get_velocities_copy(self):
+        return np.stack(self.get_velocities_soa(), axis=1)
+
+    def get_energies(self):
+        e = [C.c_double() for _ in range(3)]
+        _check(self._lib, self._lib.ljgpu_get_energies(self._h, *[C.byref(x) for x in e]))
+        return tuple(x.value for x in e)
+
+    def get_ekin(self):
+        return self.get_energies()[0]
+
+    def get_epot(self):
+        return self.get_energies()[1]
+
+    def get_etot(self):
+        return self.get_energies()[2]
+
+    def get_energy_history(self, max_entries=4096):
+        steps = np.empty(max_entries, dtype=np.uint32)
+        ek = np.empty(max_entries, dtype=np.float64)
+        ep = np.empty(max_entries, dtype=np.float64)
+        n = C.c_uint32()
+        _check(self._lib, self._lib.ljgpu_get_energy_history(self._h, max_entries, _ptr(steps), _ptr(ek), _ptr(ep), C.byref(n)))
+        return steps[:n.value], ek[:n.value], ep[:n.value]
+
+    def get_speed_histogram(self, nbins=100, vmax=10.0):
+        out = np.zeros(nbins, dtype=np.uint64)
+        _check(self._lib, self._lib.ljgpu_get_speed_histogram(self._h, nbins, vmax, _ptr(out)))
+        return out
+
+    def get_cell_ids(self):
+        out = np.empty(self.n, dtype=np.uint32)
+        dims = (C.c_uint32 * 3)()
+        _check(self._lib, self._lib.ljgpu_get_cell_ids(self._h, _ptr(out), dims))
+        return out, tuple(dims)
+
+    def get_neighbor_counts(self, cutoff, inclusive=True):
+        out = np.empty(self.n, dtype=np.uint32)
+        _check(self._lib, self._lib.ljgpu_get_neighbor_counts(self._h, cutoff, 1 if inclusive else 0, _ptr(out)))
+        return out
+
+    def write_to_movie_file(self, path, create=False):
+        _check(self._lib, self._lib.ljgpu_write_movie_frame(self._h, os.fsencode(path), 1 if create else 0))
+
+    # -- introspection -------------------------------------------------------------------------
+    def set_profiling(self, on):
+        _check(self._lib, self._lib.ljgpu_set_profiling(self._h, 1 if on else 0))
+
+    def get_timers(self):
+        t = LJTimers()
+        _check(self._lib, self._lib.ljgpu_get_timers(self._h, C.byref(t)))
+        return {k: getattr(t, k) for k, _ in LJTimers._fields_}
+
+    def reset_timers(self):
+        _check(self._lib, self._lib.ljgpu_reset_timers(self._h))
+
+    def get_layout(self):
+        k, nc, cap, g = C.c_int32(), C.c_uint32(), C.c_uint32(), C.c_uint64()
+        _check(self._lib, self._lib.ljgpu_get_layout(self._h, C.byref(k), C.byref(nc), C.byref(cap), C.byref(g)))
+        return {"force_kernel": k.value, "cells_per_axis": nc.value, "list_capacity": cap.value, "n_ghosts": g.value}

@@ -1,0 +1,178 @@
+// lj_common.cuh - shared declarations of the sm_100a Lennard-Jones integrator (libljgpu.so).
+//
+// Reference path being replaced: LennardJonesSimulation::integrate and its stages,
+// /root/reference/src/simulator/lennardjonessimulation.cpp:70-576 (".cpp" in the comments below).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstddef>
+
+namespace ljgpu {
+
+// ---------------------------------------------------------------------------------------------
+// Exactly rounded, never-contracted fp64 arithmetic.  The reference's arithmetic is an x86-64
+// baseline build (no FMA); wherever a result feeds an integer decision (cell id, wrap, histogram
+// bin, neighbour count) or is cheap to keep identical (the HBM-bound integrator stages) we spell
+// the operations with these so nvcc cannot fuse a multiply into an add.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double xmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double xadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double xsub(double a, double b) { return __dadd_rn(a, -b); }
+__device__ __forceinline__ double xdiv(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __forceinline__ double xsqrt(double a)          { return __dsqrt_rn(a); }
+
+// x*x + y*y + z*z in the reference's association ((xx + yy) + zz), no contraction.
+__device__ __forceinline__ double xnorm2(double x, double y, double z) {
+    return xadd(xadd(xmul(x, x), xmul(y, y)), xmul(z, z));
+}
+
+// apply_boundary_conditions, .cpp:431-433:  x -= L * floor(x * invL)
+__device__ __forceinline__ double wrap_coord(double x, double L, double invL) {
+    return xsub(x, xmul(L, floor(xmul(x, invL))));
+}
+
+// One-shot minimum image, .cpp:295-302 / :523-530.
+__device__ __forceinline__ double min_image(double d, double L, double halfL) {
+    if (d >= halfL) d = xsub(d, L);
+    else if (d < -halfL) d = xadd(d, L);
+    return d;
+}
+
+// Cell coordinate along one axis, .cpp:468-474:  min((unsigned)(x / edge), nc - 1).
+// The float->unsigned conversion of a negative value is undefined in C++; the reference only
+// ever converts wrapped coordinates (>= 0).  __double2uint_rz saturates, which agrees there.
+__device__ __forceinline__ unsigned cell_coord(double x, double edge, unsigned nc) {
+    unsigned i = __double2uint_rz(xdiv(x, edge));
+    return i < nc - 1u ? i : nc - 1u;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Constants of one simulation, passed to kernels by value.
+// ---------------------------------------------------------------------------------------------
+struct LJConst {
+    double L, invL, halfL;        // box edge, 1/L, L*0.5
+    double rc2;                   // rcut*rcut                                  (.cpp:262)
+    double sigma2;                // sigma*sigma                                (.cpp:264)
+    double ecut;                  // (s2/rc2)^6 - (s2/rc2)^3                    (.cpp:270-273)
+    double prefctr;               // 24*epsilon                                 (.cpp:267)
+    double epsilon;
+    double mass;
+    double ekin0;                 // 1.5*(N-1)*kT                               (.cpp:374)
+    double dt_over_tau;           // set per step
+    double list_cut2;             // (rcut+shell)^2                             (.cpp:445)
+    double disp_thresh;           // shell*shell*0.25                           (.cpp:559-560)
+    double cell_edge;             // L / cells_per_axis                         (.cpp:455-457)
+    unsigned nc;                  // cells per axis                             (.cpp:447-453)
+    unsigned n;                   // atoms owned by this device
+};
+
+// Device-resident control block: accumulators, published energies, batch bookkeeping.
+struct StepCtrl {
+    double pred_sum;              // sum |v + a f|^2 : kinetic sum the NEXT kick1 will see
+    double ekin, epot, etot;      // published (.h:100-102)
+    double epot_sum;              // sum over ordered pairs of (s12 - s6 - ecut), last force pass
+    unsigned long long maxdisp2;  // bits of max_i |x_i - x0_i|^2 of the current step
+    unsigned int stop;            // a re-binning is due: remaining steps of the batch do nothing
+    unsigned int steps_done;      // steps completed in the current batch
+    unsigned int overflow;        // list capacity exceeded during a build
+    unsigned int max_count;       // max list length seen by the last build
+    unsigned long long hist_head; // energy history ring: entries written so far
+};
+
+constexpr int kHistCap = 4096;    // entries in the energy history ring
+struct HistEntry { double ekin, epot; unsigned int step; unsigned int pad; };
+
+constexpr int kMaxPartials = 1 << 16;   // upper bound on per-block partial sums
+
+// ---------------------------------------------------------------------------------------------
+// Deterministic block reduction (fixed shape => fixed summation order).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, o));
+    return v;
+}
+// All threads must call; result valid in thread 0.  blockDim.x multiple of 32, <= 1024.
+__device__ __forceinline__ double block_sum(double v, double* smem32) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    v = warp_sum(v);
+    if (lane == 0) smem32[w] = v;
+    __syncthreads();
+    const int nw = (blockDim.x + 31) >> 5;
+    double r = 0.0;
+    if (w == 0) {
+        r = lane < nw ? smem32[lane] : 0.0;
+        r = warp_sum(r);
+    }
+    __syncthreads();
+    return r;
+}
+__device__ __forceinline__ double block_max(double v, double* smem32) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    v = warp_max(v);
+    if (lane == 0) smem32[w] = v;
+    __syncthreads();
+    const int nw = (blockDim.x + 31) >> 5;
+    double r = 0.0;
+    if (w == 0) {
+        r = lane < nw ? smem32[lane] : 0.0;
+        r = warp_max(r);
+    }
+    __syncthreads();
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// The Lennard-Jones pair term, .cpp:307-317, for a pair already known to be inside the cutoff.
+// Returns fr (force / 24 eps / distance-vector) and adds the pair's s12 - s6 to e; the constant
+// -ecut per accepted pair is applied once per thread from the accepted-pair count.
+//   inv = 1/d2 ; s2 = sigma2*inv ; s6 = s2^3 ; s12 = s6^2 ; e += s12 - s6 ; fr = (2 s12 - s6) inv
+// The reciprocal is the hardware seed (MUFU.RCP64H) plus two Newton steps: relative error
+// <= 2^-52-ish, no slow path needed because cutoff-accepted d2 is a normal number.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double fast_rcp(double a) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    double e = fma(-a, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-a, y, 1.0);
+    y = fma(y, e, y);
+    return y;
+}
+__device__ __forceinline__ double lj_pair(double d2, double sigma2, double& e) {
+    const double inv = fast_rcp(d2);
+    const double s2 = sigma2 * inv;
+    const double s6 = s2 * s2 * s2;
+    const double t = fma(s6, s6, -s6);       // s12 - s6
+    const double u = fma(s6, s6, t);         // 2 s12 - s6
+    e += t;
+    return u * inv;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Device-wide primitives implemented in lj_sort.cu
+// ---------------------------------------------------------------------------------------------
+struct SortScratch {
+    uint32_t* keys_alt = nullptr;
+    uint32_t* vals_alt = nullptr;
+    uint32_t* hist = nullptr;       // 256 * nblocks
+    uint32_t* scan_tmp = nullptr;   // block sums for the scan (two levels)
+    size_t    cap_items = 0;
+    size_t    cap_hist = 0;
+    size_t    cap_scan = 0;
+};
+// Stable LSD radix sort of (key,value) pairs on `key_bits` low bits.  On return the sorted data is
+// in keys/vals (the alt buffers are scratch).  Returns number of kernels launched.
+int radix_sort_pairs(uint32_t* keys, uint32_t* vals, size_t n, int key_bits, SortScratch& scr,
+                     cudaStream_t st);
+// In-place exclusive prefix sum of n uint32; total written to *total_out (device pointer, may be null).
+int exclusive_scan_u32(uint32_t* data, size_t n, uint32_t* total_out, SortScratch& scr, cudaStream_t st);
+void sort_scratch_free(SortScratch& scr);
+
+} // namespace ljgpu

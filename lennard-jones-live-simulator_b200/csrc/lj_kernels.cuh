@@ -1,0 +1,670 @@
+// lj_kernels.cuh - every per-step and re-binning kernel of the integrator (included by lj_sim.cu only).
+//
+// Stage order of one step, LennardJonesSimulation::integrate
+// (/root/reference/src/simulator/lennardjonessimulation.cpp:70-98, ".cpp" below):
+//   kick1 -> Berendsen scale -> drift -> forces (on drifted, not yet wrapped positions) -> wrap
+//   -> list-rebuild check (+ rebuild) -> kick2 -> etot -> publish.
+// Here:  kick_drift_kernel (kick1 + scale + drift + displacement check, one pass over HBM)
+//        ghost_update_kernel (periodic images follow their owners; list paths only)
+//        force_*_kernel
+//        kick2_kernel (kick2 + sum v^2 + the NEXT step's kick1 kinetic sum; + wrap on the all-pairs path)
+//        step_finalize_kernel (fixed-order final reductions, energies, history, rebuild flag).
+#pragma once
+#include "lj_common.cuh"
+
+namespace ljgpu {
+
+constexpr int kBlock = 128;            // threads per block of the per-atom kernels
+constexpr int kFinalizeThreads = 256;
+
+// ---------------------------------------------------------------------------------------------
+// K0  predict: sum |v + a f|^2, the kinetic sum kick1 of the coming step will produce
+//     (.cpp:350-354 evaluated ahead of time; same operations, so the same values).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock)
+predict_kernel(unsigned n, double a,
+               const double* __restrict__ vx, const double* __restrict__ vy, const double* __restrict__ vz,
+               const double* __restrict__ fx, const double* __restrict__ fy, const double* __restrict__ fz,
+               double* __restrict__ partial_pred) {
+    __shared__ double red[32];
+    const unsigned i = blockIdx.x * kBlock + threadIdx.x;
+    double s = 0.0;
+    if (i < n) {
+        const double tx = xadd(vx[i], xmul(a, fx[i]));
+        const double ty = xadd(vy[i], xmul(a, fy[i]));
+        const double tz = xadd(vz[i], xmul(a, fz[i]));
+        s = xnorm2(tx, ty, tz);
+    }
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) partial_pred[blockIdx.x] = s;
+}
+
+__global__ void __launch_bounds__(kFinalizeThreads)
+predict_finalize_kernel(StepCtrl* __restrict__ ctrl, const double* __restrict__ partial_pred, unsigned nb) {
+    __shared__ double red[32];
+    double s = 0.0;
+    for (unsigned k = threadIdx.x; k < nb; k += kFinalizeThreads) s += partial_pred[k];
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) ctrl->pred_sum = s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2  kick1 + Berendsen + drift (+ displacement check)
+//     .cpp:336-362 (kick), :368-383 (lambda from the kick1 kinetic energy), :388-413 (drift),
+//     :557-568 (any |displacement|^2 > shell^2/4 since the last binning).
+//     Displacement is x - x0 with x0 the position at the last binning (the reference accumulates the
+//     increments instead; the two differ in the last bits only).
+// ---------------------------------------------------------------------------------------------
+template <bool TRACK_DISP>
+__global__ void __launch_bounds__(kBlock)
+kick_drift_kernel(LJConst c, double dt, double a, StepCtrl* __restrict__ ctrl,
+                  double4* __restrict__ pos,
+                  const double* __restrict__ x0, const double* __restrict__ y0, const double* __restrict__ z0,
+                  double* __restrict__ vx, double* __restrict__ vy, double* __restrict__ vz,
+                  const double* __restrict__ fx, const double* __restrict__ fy, const double* __restrict__ fz) {
+    __shared__ double red[32];
+    if (ctrl->stop) return;
+    // lambda = sqrt(1 + dt/tau * (ekin0/ekin - 1)),  ekin = 0.5*m*sum   (.cpp:354, :373-375)
+    const double ek = xmul(xmul(0.5, c.mass), ctrl->pred_sum);
+    const double lambda = xsqrt(xadd(1.0, xmul(c.dt_over_tau, xsub(xdiv(c.ekin0, ek), 1.0))));
+
+    const unsigned i = blockIdx.x * kBlock + threadIdx.x;
+    double d2 = 0.0;
+    if (i < c.n) {
+        double4 p = pos[i];
+        double ux = xadd(vx[i], xmul(a, fx[i]));
+        double uy = xadd(vy[i], xmul(a, fy[i]));
+        double uz = xadd(vz[i], xmul(a, fz[i]));
+        ux = xmul(ux, lambda); uy = xmul(uy, lambda); uz = xmul(uz, lambda);
+        p.x = xadd(p.x, xmul(ux, dt));
+        p.y = xadd(p.y, xmul(uy, dt));
+        p.z = xadd(p.z, xmul(uz, dt));
+        vx[i] = ux; vy[i] = uy; vz[i] = uz;
+        pos[i] = p;
+        if (TRACK_DISP) d2 = xnorm2(xsub(p.x, x0[i]), xsub(p.y, y0[i]), xsub(p.z, z0[i]));
+    }
+    if (TRACK_DISP) {
+        d2 = block_max(d2, red);
+        if (threadIdx.x == 0 && d2 > c.disp_thresh)
+            atomicMax(&ctrl->maxdisp2, (unsigned long long)__double_as_longlong(d2));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Ghost atoms: slot n+g mirrors atom (gsrc & mask) displaced by a whole number of box edges, so the
+// list kernels need no minimum-image logic in their inner loops (what .cpp:295-302 does per pair).
+// ---------------------------------------------------------------------------------------------
+constexpr unsigned kGhostShiftBits = 27;
+constexpr unsigned kGhostIdxMask = (1u << kGhostShiftBits) - 1u;
+
+__global__ void __launch_bounds__(kBlock)
+ghost_update_kernel(unsigned nghost, unsigned nreal, double L, const StepCtrl* __restrict__ ctrl,
+                    double4* __restrict__ pos, const uint32_t* __restrict__ gsrc) {
+    if (ctrl->stop) return;
+    const unsigned g = blockIdx.x * kBlock + threadIdx.x;
+    if (g >= nghost) return;
+    const uint32_t s = gsrc[g];
+    const unsigned code = s >> kGhostShiftBits;
+    double4 p = pos[s & kGhostIdxMask];
+    p.x += L * (double)((int)(code % 3u) - 1);
+    p.y += L * (double)((int)((code / 3u) % 3u) - 1);
+    p.z += L * (double)((int)(code / 9u) - 1);
+    pos[nreal + g] = p;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1  all-pairs force kernel (small N): calculate_forces .cpp:258-330 with the pair set taken
+//     over ALL j (the Verlet list only pre-filters it), minimum image per pair as :295-302, the
+//     cutoff decision d2 >= rcut^2 on a d2 formed exactly like :304.
+//     grid = (i tiles, j splits); each block stages its j range through shared memory; partial
+//     forces of the j splits are summed in fixed order by allpairs_reduce_kernel.
+// ---------------------------------------------------------------------------------------------
+constexpr int kApTile = 128;      // j positions staged per shared-memory tile (== kBlock)
+
+__global__ void __launch_bounds__(kBlock)
+force_allpairs_kernel(LJConst c, const StepCtrl* __restrict__ ctrl, const double4* __restrict__ pos,
+                      unsigned jchunk,
+                      double* __restrict__ pfx, double* __restrict__ pfy, double* __restrict__ pfz,
+                      double* __restrict__ partial_epot) {
+    __shared__ double sx[kApTile], sy[kApTile], sz[kApTile];
+    __shared__ double red[32];
+    if (ctrl->stop) return;
+    const unsigned i = blockIdx.x * kBlock + threadIdx.x;
+    const bool active = i < c.n;
+    double4 pi = active ? pos[i] : make_double4(0, 0, 0, 0);
+    const unsigned j0 = blockIdx.y * jchunk;
+    const unsigned j1 = min(j0 + jchunk, c.n);
+
+    double ax = 0.0, ay = 0.0, az = 0.0, e = 0.0;
+    unsigned nacc = 0;
+    for (unsigned jb = j0; jb < j1; jb += kApTile) {
+        const unsigned jl = jb + threadIdx.x;
+        __syncthreads();
+        if (jl < j1) { const double4 q = pos[jl]; sx[threadIdx.x] = q.x; sy[threadIdx.x] = q.y; sz[threadIdx.x] = q.z; }
+        __syncthreads();
+        const unsigned cnt = min((unsigned)kApTile, j1 - jb);
+        if (active) {
+#pragma unroll 4
+            for (unsigned jj = 0; jj < cnt; ++jj) {
+                const double dx = min_image(xsub(pi.x, sx[jj]), c.L, c.halfL);
+                const double dy = min_image(xsub(pi.y, sy[jj]), c.L, c.halfL);
+                const double dz = min_image(xsub(pi.z, sz[jj]), c.L, c.halfL);
+                const double d2 = xnorm2(dx, dy, dz);
+                if (d2 < c.rc2 && (jb + jj) != i) {
+                    const double fr = lj_pair(d2, c.sigma2, e);
+                    ax = fma(fr, dx, ax); ay = fma(fr, dy, ay); az = fma(fr, dz, az);
+                    ++nacc;
+                }
+            }
+        }
+    }
+    if (active) {
+        const size_t o = (size_t)blockIdx.y * c.n + i;
+        pfx[o] = ax; pfy[o] = ay; pfz[o] = az;
+    }
+    e = fma(-(double)nacc, c.ecut, e);
+    e = block_sum(e, red);
+    if (threadIdx.x == 0) partial_epot[blockIdx.y * gridDim.x + blockIdx.x] = e;
+}
+
+__global__ void __launch_bounds__(kBlock)
+allpairs_reduce_kernel(LJConst c, const StepCtrl* __restrict__ ctrl, unsigned nsplit,
+                       const double* __restrict__ pfx, const double* __restrict__ pfy, const double* __restrict__ pfz,
+                       double* __restrict__ fx, double* __restrict__ fy, double* __restrict__ fz) {
+    if (ctrl->stop) return;
+    const unsigned i = blockIdx.x * kBlock + threadIdx.x;
+    if (i >= c.n) return;
+    double ax = 0.0, ay = 0.0, az = 0.0;
+    for (unsigned s = 0; s < nsplit; ++s) {
+        const size_t o = (size_t)s * c.n + i;
+        ax += pfx[o]; ay += pfy[o]; az += pfz[o];
+    }
+    fx[i] = ax * c.prefctr; fy[i] = ay * c.prefctr; fz[i] = az * c.prefctr;     // .cpp:321-325
+}
+
+// ---------------------------------------------------------------------------------------------
+// Cell traversal shared by the list build and the cell-list force kernel: one warp per home cell,
+// lanes = home atoms, the 27 stencil cells (extended grid: ghost layer included, so no periodic
+// index wrap and no minimum image) streamed through a warp-private shared-memory tile.
+// ---------------------------------------------------------------------------------------------
+constexpr int kCellWarps = 4;
+
+struct CellGrid {
+    const uint32_t* __restrict__ cstart;     // inner cells: first slot
+    const uint32_t* __restrict__ ccount;     // inner cells: atoms
+    const uint32_t* __restrict__ estart;     // extended cells: first slot (ghost cells point past n)
+    const uint32_t* __restrict__ ecount;
+    unsigned nc;                             // inner cells per axis
+};
+
+template <class Op>
+__device__ __forceinline__ void cell_traverse(const CellGrid& g, const double4* __restrict__ pos,
+                                              double4 (*tile)[32], Op& op) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const unsigned cell = blockIdx.x * kCellWarps + w;
+    const unsigned ncell = g.nc * g.nc * g.nc;
+    if (cell >= ncell) return;
+    const unsigned ix = cell % g.nc, iy = (cell / g.nc) % g.nc, iz = cell / (g.nc * g.nc);
+    const unsigned E = g.nc + 2;
+    const unsigned hs = g.cstart[cell], hn = g.ccount[cell];
+    for (unsigned hb = 0; hb < hn; hb += 32) {
+        const unsigned i = hs + hb + lane;
+        const bool active = hb + lane < hn;
+        const double4 pi = active ? pos[i] : make_double4(1e300, 1e300, 1e300, 0);
+        op.begin(i, active);
+        for (unsigned dz = 0; dz < 3; ++dz)
+        for (unsigned dy = 0; dy < 3; ++dy) {
+            // the three x-adjacent extended cells are consecutive in memory order of the table
+            const unsigned e0 = ((iz + dz) * E + (iy + dy)) * E + ix;
+            for (unsigned dx = 0; dx < 3; ++dx) {
+                const unsigned js = g.estart[e0 + dx], jn = g.ecount[e0 + dx];
+                for (unsigned jb = 0; jb < jn; jb += 32) {
+                    __syncwarp();
+                    if (jb + lane < jn) tile[w][lane] = pos[js + jb + lane];
+                    __syncwarp();
+                    const unsigned cnt = min(32u, jn - jb);
+                    for (unsigned jj = 0; jj < cnt; ++jj) {
+                        const double4 pj = tile[w][jj];
+                        const double ddx = pi.x - pj.x, ddy = pi.y - pj.y, ddz = pi.z - pj.z;
+                        const double d2 = fma(ddz, ddz, fma(ddy, ddy, ddx * ddx));
+                        op.pair(i, js + jb + jj, ddx, ddy, ddz, d2, active);
+                    }
+                }
+            }
+        }
+        op.end(i, active);
+    }
+}
+
+// Verlet list layout: atoms are grouped in tiles of 32 consecutive slots; entry k of slot i lives at
+// nl[((i>>5)*cap + k)*32 + (i&31)], so a warp that walks its 32 lists reads 128 contiguous bytes per k.
+// Replaces the reference's flat [offsets][entries..., sentinel] vector (.cpp:543-550).
+__device__ __forceinline__ size_t nl_index(unsigned i, unsigned k, unsigned cap) {
+    return ((size_t)(i >> 5) * cap + k) * 32 + (i & 31u);
+}
+
+template <bool FILL>
+struct ListBuildOp {
+    double cut2; unsigned cap; uint32_t* nl; uint32_t* nl_count; StepCtrl* ctrl; unsigned cnt;
+    __device__ __forceinline__ void begin(unsigned, bool) { cnt = 0; }
+    __device__ __forceinline__ void pair(unsigned i, unsigned j, double, double, double, double d2, bool active) {
+        if (active && d2 <= cut2 && j != i) {
+            if (FILL && cnt < cap) nl[nl_index(i, cnt, cap)] = j;
+            ++cnt;
+        }
+    }
+    __device__ __forceinline__ void end(unsigned i, bool active) {
+        if (active) nl_count[i] = FILL ? min(cnt, cap) : cnt;
+        unsigned m = active ? cnt : 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if ((threadIdx.x & 31) == 0) {
+            atomicMax(&ctrl->max_count, m);
+            if (FILL && m > cap) atomicExch(&ctrl->overflow, 1u);
+        }
+    }
+};
+
+// build_neighbor_list, .cpp:441-551 (acceptance dist2 <= (rcut+shell)^2, :536), on the device layout.
+template <bool FILL>
+__global__ void __launch_bounds__(kCellWarps * 32)
+build_list_kernel(LJConst c, CellGrid g, const double4* __restrict__ pos, unsigned cap,
+                  uint32_t* __restrict__ nl, uint32_t* __restrict__ nl_count, StepCtrl* __restrict__ ctrl) {
+    __shared__ double4 tile[kCellWarps][32];
+    ListBuildOp<FILL> op{c.list_cut2, cap, nl, nl_count, ctrl, 0};
+    cell_traverse(g, pos, tile, op);
+}
+
+struct CellForceOp {
+    double rc2, sigma2, ecut, prefctr;
+    double* fx; double* fy; double* fz;
+    double ax, ay, az, e, etot; unsigned nacc;
+    __device__ __forceinline__ void begin(unsigned, bool) { ax = ay = az = e = 0.0; nacc = 0; }
+    __device__ __forceinline__ void pair(unsigned i, unsigned j, double dx, double dy, double dz, double d2, bool active) {
+        if (active && d2 < rc2 && j != i) {
+            const double fr = lj_pair(d2, sigma2, e);
+            ax = fma(fr, dx, ax); ay = fma(fr, dy, ay); az = fma(fr, dz, az);
+            ++nacc;
+        }
+    }
+    __device__ __forceinline__ void end(unsigned i, bool active) {
+        if (active) { fx[i] = ax * prefctr; fy[i] = ay * prefctr; fz[i] = az * prefctr; }
+        etot += fma(-(double)nacc, ecut, e);
+    }
+};
+
+// K7a cell-list force kernel: every step, all 27 stencil cells, cutoff test d2 < rcut^2 (.cpp:304-305).
+__global__ void __launch_bounds__(kCellWarps * 32)
+force_cell_kernel(LJConst c, CellGrid g, const StepCtrl* __restrict__ ctrl, const double4* __restrict__ pos,
+                  double* __restrict__ fx, double* __restrict__ fy, double* __restrict__ fz,
+                  double* __restrict__ partial_epot) {
+    __shared__ double4 tile[kCellWarps][32];
+    __shared__ double red[32];
+    if (ctrl->stop) return;
+    CellForceOp op{c.rc2, c.sigma2, c.ecut, c.prefctr, fx, fy, fz, 0, 0, 0, 0, 0.0, 0};
+    cell_traverse(g, pos, tile, op);
+    const double e = block_sum(op.etot, red);
+    if (threadIdx.x == 0) partial_epot[blockIdx.x] = e;
+}
+
+// K7b Verlet-list force kernel: one thread per atom slot, its list entries gathered as 32-byte
+// double4 sectors (served by L1/L2: neighbours of consecutive slots overlap almost completely).
+// calculate_forces, .cpp:286-319, minus the minimum image (ghost slots carry the shifted images).
+__global__ void __launch_bounds__(kBlock)
+force_verlet_kernel(LJConst c, const StepCtrl* __restrict__ ctrl, const double4* __restrict__ pos,
+                    const uint32_t* __restrict__ nl, const uint32_t* __restrict__ nl_count, unsigned cap,
+                    double* __restrict__ fx, double* __restrict__ fy, double* __restrict__ fz,
+                    double* __restrict__ partial_epot) {
+    __shared__ double red[32];
+    if (ctrl->stop) return;
+    const unsigned i = blockIdx.x * kBlock + threadIdx.x;
+    const bool active = i < c.n;
+    double ax = 0.0, ay = 0.0, az = 0.0, e = 0.0;
+    unsigned nacc = 0;
+    if (active) {
+        const double4 pi = pos[i];
+        const unsigned cnt = nl_count[i];
+        const uint32_t* __restrict__ row = nl + nl_index(i, 0, cap);
+        unsigned k = 0;
+        for (; k + 4 <= cnt; k += 4) {
+            const uint32_t j0 = row[(size_t)(k + 0) * 32], j1 = row[(size_t)(k + 1) * 32];
+            const uint32_t j2 = row[(size_t)(k + 2) * 32], j3 = row[(size_t)(k + 3) * 32];
+            const double4 p0 = pos[j0], p1 = pos[j1], p2 = pos[j2], p3 = pos[j3];
+#define LJ_ACC(P)                                                                          \
+            {                                                                              \
+                const double dx = pi.x - P.x, dy = pi.y - P.y, dz = pi.z - P.z;            \
+                const double d2 = fma(dz, dz, fma(dy, dy, dx * dx));                       \
+                if (d2 < c.rc2) {                                                          \
+                    const double fr = lj_pair(d2, c.sigma2, e);                            \
+                    ax = fma(fr, dx, ax); ay = fma(fr, dy, ay); az = fma(fr, dz, az);      \
+                    ++nacc;                                                                \
+                }                                                                          \
+            }
+            LJ_ACC(p0) LJ_ACC(p1) LJ_ACC(p2) LJ_ACC(p3)
+        }
+        for (; k < cnt; ++k) {
+            const double4 p0 = pos[row[(size_t)k * 32]];
+            LJ_ACC(p0)
+        }
+#undef LJ_ACC
+        fx[i] = ax * c.prefctr; fy[i] = ay * c.prefctr; fz[i] = az * c.prefctr;
+    }
+    e = fma(-(double)nacc, c.ecut, e);
+    e = block_sum(e, red);
+    if (threadIdx.x == 0) partial_epot[blockIdx.x] = e;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3  kick2 + kinetic sums (+ wrap on the all-pairs path)
+//     .cpp:336-362; WRAP adds apply_boundary_conditions .cpp:419-435 (a per-atom operation that the
+//     reference runs between the force pass and kick2; it touches positions only).
+// ---------------------------------------------------------------------------------------------
+template <bool WRAP>
+__global__ void __launch_bounds__(kBlock)
+kick2_kernel(LJConst c, double a, const StepCtrl* __restrict__ ctrl, double4* __restrict__ pos,
+             double* __restrict__ vx, double* __restrict__ vy, double* __restrict__ vz,
+             const double* __restrict__ fx, const double* __restrict__ fy, const double* __restrict__ fz,
+             double* __restrict__ partial_ekin, double* __restrict__ partial_pred) {
+    __shared__ double red[32];
+    if (ctrl->stop) return;
+    const unsigned i = blockIdx.x * kBlock + threadIdx.x;
+    double s1 = 0.0, s2 = 0.0;
+    if (i < c.n) {
+        const double gx = xmul(a, fx[i]), gy = xmul(a, fy[i]), gz = xmul(a, fz[i]);
+        const double ux = xadd(vx[i], gx), uy = xadd(vy[i], gy), uz = xadd(vz[i], gz);
+        vx[i] = ux; vy[i] = uy; vz[i] = uz;
+        s1 = xnorm2(ux, uy, uz);
+        s2 = xnorm2(xadd(ux, gx), xadd(uy, gy), xadd(uz, gz));
+        if (WRAP) {
+            double4 p = pos[i];
+            p.x = wrap_coord(p.x, c.L, c.invL);
+            p.y = wrap_coord(p.y, c.L, c.invL);
+            p.z = wrap_coord(p.z, c.L, c.invL);
+            pos[i] = p;
+        }
+    }
+    s1 = block_sum(s1, red);
+    s2 = block_sum(s2, red);
+    if (threadIdx.x == 0) { partial_ekin[blockIdx.x] = s1; partial_pred[blockIdx.x] = s2; }
+}
+
+// Final reductions in fixed order, energies (.cpp:95-96, :327-329, :361), history, rebuild flag.
+__global__ void __launch_bounds__(kFinalizeThreads)
+step_finalize_kernel(LJConst c, StepCtrl* __restrict__ ctrl, HistEntry* __restrict__ hist, unsigned step,
+                     const double* __restrict__ partial_epot, unsigned nb_epot,
+                     const double* __restrict__ partial_ekin, const double* __restrict__ partial_pred,
+                     unsigned nb_kick) {
+    __shared__ double red[32];
+    if (ctrl->stop) return;
+    double se = 0.0, sk = 0.0, sp = 0.0;
+    for (unsigned k = threadIdx.x; k < nb_epot; k += kFinalizeThreads) se += partial_epot[k];
+    for (unsigned k = threadIdx.x; k < nb_kick; k += kFinalizeThreads) { sk += partial_ekin[k]; sp += partial_pred[k]; }
+    se = block_sum(se, red);
+    sk = block_sum(sk, red);
+    sp = block_sum(sp, red);
+    if (threadIdx.x == 0) {
+        const double ekin = xmul(xmul(0.5, c.mass), sk);
+        const double epot = xmul(xmul(xmul(se, 4.0), c.epsilon), 0.5);
+        ctrl->epot_sum = se;
+        ctrl->pred_sum = sp;
+        ctrl->ekin = ekin; ctrl->epot = epot; ctrl->etot = xadd(ekin, epot);
+        HistEntry& h = hist[ctrl->hist_head % kHistCap];
+        h.ekin = ekin; h.epot = epot; h.step = step; h.pad = 0;
+        ctrl->hist_head += 1;
+        ctrl->steps_done += 1;
+        if (__longlong_as_double((long long)ctrl->maxdisp2) > c.disp_thresh) ctrl->stop = 1;
+        ctrl->maxdisp2 = 0ull;
+    }
+}
+
+// Constructor path: energies after the first force pass; ekin stays 0 (.cpp:57-62).
+__global__ void __launch_bounds__(kFinalizeThreads)
+init_finalize_kernel(LJConst c, StepCtrl* __restrict__ ctrl, const double* __restrict__ partial_epot, unsigned nb_epot) {
+    __shared__ double red[32];
+    double se = 0.0;
+    for (unsigned k = threadIdx.x; k < nb_epot; k += kFinalizeThreads) se += partial_epot[k];
+    se = block_sum(se, red);
+    if (threadIdx.x == 0) {
+        ctrl->epot_sum = se;
+        ctrl->epot = xmul(xmul(xmul(se, 4.0), c.epsilon), 0.5);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Re-binning kernels (K4 wrap, K5 cell id, K6 permutation after the radix sort).
+// ---------------------------------------------------------------------------------------------
+// wrap (.cpp:431-433) + cell key (.cpp:468-476) of every owned atom; unsorted wrapped copy to pos_tmp.
+__global__ void __launch_bounds__(kBlock)
+wrap_key_kernel(LJConst c, const double4* __restrict__ pos, double4* __restrict__ pos_tmp,
+                uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    const unsigned i = blockIdx.x * kBlock + threadIdx.x;
+    if (i >= c.n) return;
+    double4 p = pos[i];
+    p.x = wrap_coord(p.x, c.L, c.invL);
+    p.y = wrap_coord(p.y, c.L, c.invL);
+    p.z = wrap_coord(p.z, c.L, c.invL);
+    pos_tmp[i] = p;
+    const unsigned ix = cell_coord(p.x, c.cell_edge, c.nc);
+    const unsigned iy = cell_coord(p.y, c.cell_edge, c.nc);
+    const unsigned iz = cell_coord(p.z, c.cell_edge, c.nc);
+    keys[i] = iz * c.nc * c.nc + iy * c.nc + ix;
+    vals[i] = i;
+}
+
+__global__ void __launch_bounds__(kBlock)
+permute_kernel(unsigned n, const uint32_t* __restrict__ perm, const double4* __restrict__ pos_tmp,
+               double4* __restrict__ pos, double* __restrict__ x0, double* __restrict__ y0, double* __restrict__ z0,
+               const double* __restrict__ vxi, const double* __restrict__ vyi, const double* __restrict__ vzi,
+               const double* __restrict__ fxi, const double* __restrict__ fyi, const double* __restrict__ fzi,
+               const uint32_t* __restrict__ origi,
+               double* __restrict__ vxo, double* __restrict__ vyo, double* __restrict__ vzo,
+               double* __restrict__ fxo, double* __restrict__ fyo, double* __restrict__ fzo,
+               uint32_t* __restrict__ origo) {
+    const unsigned i = blockIdx.x * kBlock + threadIdx.x;
+    if (i >= n) return;
+    const unsigned s = perm[i];
+    const double4 p = pos_tmp[s];
+    pos[i] = p; x0[i] = p.x; y0[i] = p.y; z0[i] = p.z;
+    vxo[i] = vxi[s]; vyo[i] = vyi[s]; vzo[i] = vzi[s];
+    fxo[i] = fxi[s]; fyo[i] = fyi[s]; fzo[i] = fzi[s];
+    origo[i] = origi[s];
+}
+
+// Cell table from the sorted keys.
+__global__ void __launch_bounds__(kBlock)
+cell_bounds_kernel(unsigned n, const uint32_t* __restrict__ keys, uint32_t* __restrict__ cstart, uint32_t* __restrict__ cend) {
+    const unsigned i = blockIdx.x * kBlock + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t k = keys[i];
+    if (i == 0 || keys[i - 1] != k) cstart[k] = i;
+    if (i == n - 1 || keys[i + 1] != k) cend[k] = i + 1;
+}
+
+__global__ void __launch_bounds__(kBlock)
+cell_count_kernel(unsigned ncell, const uint32_t* __restrict__ cstart, const uint32_t* __restrict__ cend, uint32_t* __restrict__ ccount) {
+    const unsigned k = blockIdx.x * kBlock + threadIdx.x;
+    if (k < ncell) ccount[k] = cend[k] - cstart[k];
+}
+
+// Extended grid (one ghost layer per face).  Pass 1: number of ghost slots every extended cell needs.
+__device__ __forceinline__ void ext_decode(unsigned e, unsigned nc, unsigned& src, unsigned& code, bool& ghost) {
+    const unsigned E = nc + 2;
+    const unsigned ex = e % E, ey = (e / E) % E, ez = e / (E * E);
+    const unsigned ix = ex == 0 ? nc - 1 : (ex == E - 1 ? 0 : ex - 1);
+    const unsigned iy = ey == 0 ? nc - 1 : (ey == E - 1 ? 0 : ey - 1);
+    const unsigned iz = ez == 0 ? nc - 1 : (ez == E - 1 ? 0 : ez - 1);
+    const unsigned sx = ex == 0 ? 0u : (ex == E - 1 ? 2u : 1u);      // 0: image at -L, 1: none, 2: +L
+    const unsigned sy = ey == 0 ? 0u : (ey == E - 1 ? 2u : 1u);
+    const unsigned sz = ez == 0 ? 0u : (ez == E - 1 ? 2u : 1u);
+    src = iz * nc * nc + iy * nc + ix;
+    code = sx + 3u * sy + 9u * sz;
+    ghost = code != 13u;
+}
+
+__global__ void __launch_bounds__(kBlock)
+ext_count_kernel(unsigned nc, const uint32_t* __restrict__ ccount, uint32_t* __restrict__ goff) {
+    const unsigned E = nc + 2;
+    const unsigned e = blockIdx.x * kBlock + threadIdx.x;
+    if (e >= E * E * E) return;
+    unsigned src, code; bool ghost;
+    ext_decode(e, nc, src, code, ghost);
+    goff[e] = ghost ? ccount[src] : 0u;
+}
+
+// Pass 2 (after the exclusive scan of goff): extended cell table + ghost source list.
+__global__ void __launch_bounds__(kBlock)
+ext_fill_kernel(unsigned nc, unsigned nreal, const uint32_t* __restrict__ cstart, const uint32_t* __restrict__ ccount,
+                const uint32_t* __restrict__ goff, uint32_t* __restrict__ estart, uint32_t* __restrict__ ecount,
+                uint32_t* __restrict__ gsrc, unsigned gcap) {
+    const unsigned E = nc + 2;
+    const unsigned e = blockIdx.x * kBlock + threadIdx.x;
+    if (e >= E * E * E) return;
+    unsigned src, code; bool ghost;
+    ext_decode(e, nc, src, code, ghost);
+    const unsigned cnt = ccount[src];
+    ecount[e] = cnt;
+    if (!ghost) { estart[e] = cstart[src]; return; }
+    const unsigned off = goff[e];
+    estart[e] = nreal + off;
+    const unsigned s0 = cstart[src];
+    for (unsigned k = 0; k < cnt; ++k)
+        if (off + k < gcap) gsrc[off + k] = (s0 + k) | (code << kGhostShiftBits);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Query kernels (original atom order out).
+// ---------------------------------------------------------------------------------------------
+template <bool WRAP>
+__global__ void __launch_bounds__(kBlock)
+export_positions_kernel(LJConst c, const double4* __restrict__ pos, const uint32_t* __restrict__ orig,
+                        double* __restrict__ ox, double* __restrict__ oy, double* __restrict__ oz) {
+    const unsigned i = blockIdx.x * kBlock + threadIdx.x;
+    if (i >= c.n) return;
+    const double4 p = pos[i];
+    const unsigned o = orig[i];
+    ox[o] = WRAP ? wrap_coord(p.x, c.L, c.invL) : p.x;
+    oy[o] = WRAP ? wrap_coord(p.y, c.L, c.invL) : p.y;
+    oz[o] = WRAP ? wrap_coord(p.z, c.L, c.invL) : p.z;
+}
+
+__global__ void __launch_bounds__(kBlock)
+export_soa_kernel(unsigned n, const double* __restrict__ a, const double* __restrict__ b, const double* __restrict__ cc,
+                  const uint32_t* __restrict__ orig, double* __restrict__ ox, double* __restrict__ oy, double* __restrict__ oz) {
+    const unsigned i = blockIdx.x * kBlock + threadIdx.x;
+    if (i >= n) return;
+    const unsigned o = orig[i];
+    ox[o] = a[i]; oy[o] = b[i]; oz[o] = cc[i];
+}
+
+__global__ void __launch_bounds__(kBlock)
+import_state_kernel(unsigned n, const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
+                    double4* __restrict__ pos, uint32_t* __restrict__ orig) {
+    const unsigned i = blockIdx.x * kBlock + threadIdx.x;
+    if (i >= n) return;
+    pos[i] = make_double4(x[i], y[i], z[i], 0.0);
+    orig[i] = i;
+}
+
+// K8  speed histogram, graphwidget.cpp:225-230: bin = min((int)(|v| / vmax * nbins), nbins-1),
+//     |v| = sqrt(x*x + y*y + z*z) (glm::length).  Shared-memory integer atomics, then one global
+//     atomic per non-empty bin per block.
+constexpr int kMaxBins = 1024;
+__global__ void __launch_bounds__(256)
+speed_histogram_kernel(unsigned n, const double* __restrict__ vx, const double* __restrict__ vy, const double* __restrict__ vz,
+                       unsigned nbins, double vmax, unsigned long long* __restrict__ counts) {
+    __shared__ unsigned int h[kMaxBins];
+    for (unsigned b = threadIdx.x; b < nbins; b += blockDim.x) h[b] = 0;
+    __syncthreads();
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const double speed = xsqrt(xnorm2(vx[i], vy[i], vz[i]));
+        int bin = __double2int_rz(xmul(xdiv(speed, vmax), (double)nbins));
+        bin = min(bin, (int)nbins - 1);
+        bin = max(bin, 0);
+        atomicAdd(&h[bin], 1u);
+    }
+    __syncthreads();
+    for (unsigned b = threadIdx.x; b < nbins; b += blockDim.x)
+        if (h[b]) atomicAdd(&counts[b], (unsigned long long)h[b]);
+}
+
+// Cell-id probe on the published (wrapped) positions, .cpp:447-476, original order out.
+template <bool WRAP>
+__global__ void __launch_bounds__(kBlock)
+cell_id_probe_kernel(LJConst c, const double4* __restrict__ pos, const uint32_t* __restrict__ orig, uint32_t* __restrict__ out) {
+    const unsigned i = blockIdx.x * kBlock + threadIdx.x;
+    if (i >= c.n) return;
+    double4 p = pos[i];
+    if (WRAP) { p.x = wrap_coord(p.x, c.L, c.invL); p.y = wrap_coord(p.y, c.L, c.invL); p.z = wrap_coord(p.z, c.L, c.invL); }
+    const unsigned ix = cell_coord(p.x, c.cell_edge, c.nc);
+    const unsigned iy = cell_coord(p.y, c.cell_edge, c.nc);
+    const unsigned iz = cell_coord(p.z, c.cell_edge, c.nc);
+    out[orig[i]] = iz * c.nc * c.nc + iy * c.nc + ix;
+}
+
+// Neighbour-count probe, bit-exact with the reference's comparisons: min-image distance formed as
+// .cpp:519-534 and accepted by dist2 <= cut2 (inclusive, :536) or d2 < cut2 (strict, :304-305).
+// Variant A: all pairs through shared memory (any layout).
+__global__ void __launch_bounds__(kBlock)
+count_allpairs_kernel(LJConst c, const double4* __restrict__ pos, const uint32_t* __restrict__ orig,
+                      double cut2, int inclusive, uint32_t* __restrict__ out) {
+    __shared__ double sx[kApTile], sy[kApTile], sz[kApTile];
+    const unsigned i = blockIdx.x * kBlock + threadIdx.x;
+    const bool active = i < c.n;
+    const double4 pi = active ? pos[i] : make_double4(0, 0, 0, 0);
+    unsigned cnt = 0;
+    for (unsigned jb = 0; jb < c.n; jb += kApTile) {
+        __syncthreads();
+        if (jb + threadIdx.x < c.n) { const double4 q = pos[jb + threadIdx.x]; sx[threadIdx.x] = q.x; sy[threadIdx.x] = q.y; sz[threadIdx.x] = q.z; }
+        __syncthreads();
+        const unsigned m = min((unsigned)kApTile, c.n - jb);
+        if (active)
+            for (unsigned jj = 0; jj < m; ++jj) {
+                const double dx = min_image(xsub(pi.x, sx[jj]), c.L, c.halfL);
+                const double dy = min_image(xsub(pi.y, sy[jj]), c.L, c.halfL);
+                const double dz = min_image(xsub(pi.z, sz[jj]), c.L, c.halfL);
+                const double d2 = xnorm2(dx, dy, dz);
+                const bool in = inclusive ? (d2 <= cut2) : (d2 < cut2);
+                if (in && (jb + jj) != i) ++cnt;
+            }
+    }
+    if (active) out[orig[i]] = cnt;
+}
+
+// Variant B: over the inner cell table right after a re-binning (positions wrapped and cell-sorted),
+// 27-cell periodic stencil exactly as .cpp:488-516, one warp per home cell.
+__global__ void __launch_bounds__(kCellWarps * 32)
+count_cells_kernel(LJConst c, const uint32_t* __restrict__ cstart, const uint32_t* __restrict__ ccount,
+                   const double4* __restrict__ pos, const uint32_t* __restrict__ orig,
+                   double cut2, int inclusive, uint32_t* __restrict__ out) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const unsigned cell = blockIdx.x * kCellWarps + w;
+    const unsigned nc = c.nc;
+    if (cell >= nc * nc * nc) return;
+    const unsigned ix = cell % nc, iy = (cell / nc) % nc, iz = cell / (nc * nc);
+    const unsigned xs[3] = { ix == 0 ? nc - 1 : ix - 1, ix, ix == nc - 1 ? 0 : ix + 1 };
+    const unsigned ys[3] = { iy == 0 ? nc - 1 : iy - 1, iy, iy == nc - 1 ? 0 : iy + 1 };
+    const unsigned zs[3] = { iz == 0 ? nc - 1 : iz - 1, iz, iz == nc - 1 ? 0 : iz + 1 };
+    const unsigned hs = cstart[cell], hn = ccount[cell];
+    for (unsigned hb = 0; hb < hn; hb += 32) {
+        const unsigned i = hs + hb + lane;
+        const bool active = hb + lane < hn;
+        const double4 pi = active ? pos[i] : make_double4(0, 0, 0, 0);
+        unsigned cnt = 0;
+        for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) for (int d = 0; d < 3; ++d) {
+            const unsigned cid = zs[d] * nc * nc + ys[b] * nc + xs[a];
+            const unsigned js = cstart[cid], jn = ccount[cid];
+            for (unsigned jj = 0; jj < jn; ++jj) {
+                const double4 pj = pos[js + jj];
+                const double dx = min_image(xsub(pi.x, pj.x), c.L, c.halfL);
+                const double dy = min_image(xsub(pi.y, pj.y), c.L, c.halfL);
+                const double dz = min_image(xsub(pi.z, pj.z), c.L, c.halfL);
+                const double d2 = xnorm2(dx, dy, dz);
+                const bool in = inclusive ? (d2 <= cut2) : (d2 < cut2);
+                if (active && in && (js + jj) != i) ++cnt;
+            }
+        }
+        if (active) out[orig[i]] = cnt;
+    }
+}
+
+} // namespace ljgpu

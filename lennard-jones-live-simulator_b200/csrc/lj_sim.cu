@@ -1,0 +1,723 @@
+// lj_sim.cu - host orchestration of the sm_100a Lennard-Jones integrator and its C ABI (include/ljgpu.h).
+//
+// Path replaced: class LennardJonesSimulation, /root/reference/src/simulator/lennardjonessimulation.{h,cpp}
+// (".cpp"/".h" below).  No CPU fallback: every entry point fails with LJGPU_ECUDA when there is no device.
+#include "lj_kernels.cuh"
+#include "../../include/ljgpu.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+using namespace ljgpu;
+
+namespace {
+
+thread_local std::string g_err;
+
+struct LjError : std::runtime_error {
+    int code;
+    LjError(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            throw LjError(LJGPU_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e__) +       \
+                                           " (" __FILE__ ":" + std::to_string(__LINE__) + ")");    \
+    } while (0)
+
+inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+enum Stage { ST_PREDICT = 0, ST_KICK_DRIFT, ST_GHOST, ST_FORCE, ST_KICK2, ST_REBUILD, ST_HALO, ST_COUNT };
+
+template <class T>
+void dfree(T*& p) { if (p) { cudaFree(p); p = nullptr; } }
+
+} // namespace
+
+struct ljgpu_sim {
+    std::mutex mu;
+    ljgpu_params p{};
+    int mode = 0;
+    int device = 0;
+    cudaStream_t st = nullptr;
+    LJConst c{};
+    unsigned n = 0, nc = 0, ncell = 0, necell = 0;
+
+    // state, device order (cell-sorted on the list paths, caller order on the all-pairs path)
+    double4* pos = nullptr; double4* pos_tmp = nullptr; size_t pos_cap = 0;
+    double* x0[3] = {nullptr, nullptr, nullptr};
+    double* v[3] = {nullptr, nullptr, nullptr};
+    double* f[3] = {nullptr, nullptr, nullptr};
+    double* v_alt[3] = {nullptr, nullptr, nullptr};
+    double* f_alt[3] = {nullptr, nullptr, nullptr};
+    uint32_t* orig = nullptr; uint32_t* orig_alt = nullptr;
+
+    // binning
+    uint32_t *keys = nullptr, *vals = nullptr;
+    uint32_t *cstart = nullptr, *cend = nullptr, *ccount = nullptr;
+    uint32_t *estart = nullptr, *ecount = nullptr, *goff = nullptr;
+    uint32_t* gsrc = nullptr; size_t gcap = 0; unsigned nghost = 0;
+    uint32_t* d_total = nullptr;
+    SortScratch scr;
+
+    // Verlet list
+    uint32_t* nl = nullptr; uint32_t* nl_count = nullptr; unsigned cap = 0; size_t nl_alloc = 0;
+
+    // reductions
+    double *partial_epot = nullptr, *partial_ekin = nullptr, *partial_pred = nullptr;
+    unsigned nb_atoms = 0, nb_force = 0;
+    double* apf[3] = {nullptr, nullptr, nullptr}; unsigned nsplit = 1, jchunk = 0;
+
+    StepCtrl* ctrl = nullptr; StepCtrl* h_ctrl = nullptr;
+    HistEntry* hist = nullptr;
+
+    // staging for queries
+    double* out3 = nullptr; uint32_t* out_u32 = nullptr; unsigned long long* hist_counts = nullptr;
+
+    // stepping bookkeeping
+    bool pred_valid = false; double pred_dt = 0.0;
+    unsigned since_rebuild = 0, last_interval = 16;
+    bool dirty_since_rebuild = false;
+
+    // profiling
+    bool prof = false;
+    struct Pending { int stage; cudaEvent_t a, b; };
+    std::vector<Pending> pending;
+    std::vector<cudaEvent_t> pool;
+    cudaEvent_t cur_a = nullptr;
+    double ms[ST_COUNT] = {0};
+    uint64_t cnt[ST_COUNT] = {0};
+    uint64_t steps = 0, rebuilds = 0, launches = 0;
+
+    ~ljgpu_sim();
+
+    // ---- helpers ------------------------------------------------------------------------------
+    cudaEvent_t get_event() {
+        if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+        cudaEvent_t e; CK(cudaEventCreate(&e)); return e;
+    }
+    void stage_begin() { if (prof) { cur_a = get_event(); CK(cudaEventRecord(cur_a, st)); } }
+    void stage_end(int stage) {
+        cnt[stage]++;
+        if (prof) {
+            cudaEvent_t b = get_event();
+            CK(cudaEventRecord(b, st));
+            pending.push_back({stage, cur_a, b});
+            cur_a = nullptr;
+        }
+    }
+    void resolve_pending() {      // stream must be idle
+        for (auto& q : pending) {
+            float t = 0.f;
+            if (cudaEventElapsedTime(&t, q.a, q.b) == cudaSuccess) ms[q.stage] += t;
+            pool.push_back(q.a); pool.push_back(q.b);
+        }
+        pending.clear();
+    }
+    void sync() { CK(cudaStreamSynchronize(st)); resolve_pending(); }
+    void check_launch(const char* what) {
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) throw LjError(LJGPU_ECUDA, std::string(what) + " launch: " + cudaGetErrorString(e));
+        ++launches;
+    }
+
+    bool list_mode() const { return mode != LJGPU_KERNEL_ALLPAIRS; }
+
+    void setup_constants();
+    void allocate();
+    void upload_state(const double* x, const double* y, const double* z,
+                      const double* vx, const double* vy, const double* vz);
+    void rebuild();
+    void build_list();
+    void launch_force(bool guarded);
+    void initial_forces();
+    void launch_predict(double dt);
+    void enqueue_step(unsigned step, double dt);
+    void run_steps(unsigned first, unsigned nsteps, double dt);
+    void fetch_ctrl() {
+        CK(cudaMemcpyAsync(h_ctrl, ctrl, sizeof(StepCtrl), cudaMemcpyDeviceToHost, st));
+        sync();
+    }
+    void export3(int what, double* a, double* b, double* cc);
+};
+
+ljgpu_sim::~ljgpu_sim() {
+    cudaSetDevice(device);
+    if (st) cudaStreamSynchronize(st);
+    dfree(pos); dfree(pos_tmp);
+    for (int k = 0; k < 3; ++k) { dfree(x0[k]); dfree(v[k]); dfree(f[k]); dfree(v_alt[k]); dfree(f_alt[k]); dfree(apf[k]); }
+    dfree(orig); dfree(orig_alt); dfree(keys); dfree(vals);
+    dfree(cstart); dfree(cend); dfree(ccount); dfree(estart); dfree(ecount); dfree(goff); dfree(gsrc); dfree(d_total);
+    dfree(nl); dfree(nl_count);
+    dfree(partial_epot); dfree(partial_ekin); dfree(partial_pred);
+    dfree(ctrl); dfree(hist); dfree(out3); dfree(out_u32); dfree(hist_counts);
+    if (h_ctrl) cudaFreeHost(h_ctrl);
+    sort_scratch_free(scr);
+    for (auto& q : pending) { cudaEventDestroy(q.a); cudaEventDestroy(q.b); }
+    for (auto e : pool) cudaEventDestroy(e);
+    if (st) cudaStreamDestroy(st);
+}
+
+void ljgpu_sim::setup_constants() {
+    // Every expression below is the host-side scalar set-up of the cited reference lines.
+    const double L = p.cell_length;
+    c.L = L; c.invL = 1.0 / L; c.halfL = L * 0.5;                       // .cpp:424-426, :295
+    c.rc2 = p.rcut * p.rcut;                                            // .cpp:262
+    c.sigma2 = p.sigma * p.sigma;                                       // .cpp:264
+    const double sr2 = c.sigma2 / c.rc2, sr6 = sr2 * sr2 * sr2, sr12 = sr6 * sr6;
+    c.ecut = sr12 - sr6;                                                // .cpp:270-273
+    c.prefctr = 24.0 * p.epsilon;                                       // .cpp:267
+    c.epsilon = p.epsilon;
+    c.mass = p.mass;
+    c.ekin0 = 1.5 * (double)((size_t)p.nr_particles - 1) * p.kT;        // .cpp:374
+    const double csc = p.rcut + p.shell;                                // .cpp:443-445
+    c.list_cut2 = csc * csc;
+    c.disp_thresh = p.shell * p.shell * 0.25;                           // .cpp:559-560
+    unsigned ncells = (unsigned)(L / csc);                              // .cpp:447-453
+    ncells = std::max(1u, ncells);
+    c.nc = ncells;
+    c.cell_edge = L / (double)ncells;                                   // .cpp:455-457
+    c.n = (unsigned)p.nr_particles;
+    c.dt_over_tau = 0.0;
+    nc = ncells; ncell = nc * nc * nc; necell = (nc + 2) * (nc + 2) * (nc + 2);
+}
+
+void ljgpu_sim::allocate() {
+    const size_t N = n;
+    nb_atoms = cdiv(N, kBlock);
+    // ghost estimate: ghost-layer cells over inner cells, 50 % slack
+    size_t gest = 0;
+    if (list_mode()) {
+        const double ratio = (double)(necell - ncell) / (double)ncell;
+        gest = (size_t)(ratio * (double)N * 1.5) + 4096;
+    }
+    pos_cap = N + gest; gcap = gest;
+    CK(cudaMalloc(&pos, pos_cap * sizeof(double4)));
+    CK(cudaMemset(pos, 0, pos_cap * sizeof(double4)));
+    for (int k = 0; k < 3; ++k) {
+        CK(cudaMalloc(&v[k], N * 8)); CK(cudaMalloc(&f[k], N * 8));
+        CK(cudaMemset(f[k], 0, N * 8));
+    }
+    CK(cudaMalloc(&orig, N * 4));
+    CK(cudaMalloc(&ctrl, sizeof(StepCtrl))); CK(cudaMemset(ctrl, 0, sizeof(StepCtrl)));
+    CK(cudaMallocHost(&h_ctrl, sizeof(StepCtrl))); std::memset(h_ctrl, 0, sizeof(StepCtrl));
+    CK(cudaMalloc(&hist, sizeof(HistEntry) * kHistCap)); CK(cudaMemset(hist, 0, sizeof(HistEntry) * kHistCap));
+    CK(cudaMalloc(&out3, 3 * N * 8));
+    CK(cudaMalloc(&out_u32, N * 4));
+    CK(cudaMalloc(&hist_counts, kMaxBins * sizeof(unsigned long long)));
+    CK(cudaMalloc(&partial_ekin, (size_t)nb_atoms * 8));
+    CK(cudaMalloc(&partial_pred, (size_t)nb_atoms * 8));
+
+    if (list_mode()) {
+        CK(cudaMalloc(&pos_tmp, N * sizeof(double4)));
+        for (int k = 0; k < 3; ++k) {
+            CK(cudaMalloc(&x0[k], N * 8)); CK(cudaMalloc(&v_alt[k], N * 8)); CK(cudaMalloc(&f_alt[k], N * 8));
+        }
+        CK(cudaMalloc(&orig_alt, N * 4));
+        CK(cudaMalloc(&keys, N * 4)); CK(cudaMalloc(&vals, N * 4));
+        CK(cudaMalloc(&cstart, (size_t)ncell * 4)); CK(cudaMalloc(&cend, (size_t)ncell * 4)); CK(cudaMalloc(&ccount, (size_t)ncell * 4));
+        CK(cudaMalloc(&estart, (size_t)necell * 4)); CK(cudaMalloc(&ecount, (size_t)necell * 4)); CK(cudaMalloc(&goff, (size_t)necell * 4));
+        CK(cudaMalloc(&gsrc, std::max<size_t>(gcap, 1) * 4));
+        CK(cudaMalloc(&d_total, 4));
+        CK(cudaMalloc(&nl_count, N * 4));
+        nb_force = mode == LJGPU_KERNEL_VERLET ? nb_atoms : cdiv(ncell, kCellWarps);
+    } else {
+        // j splits: enough blocks to fill 148 SMs a few times over, each split at least 64 atoms wide
+        const unsigned want = std::max(1u, (4u * 148u + nb_atoms - 1) / nb_atoms);
+        nsplit = std::max(1u, std::min(want, (unsigned)((N + 63) / 64)));
+        jchunk = cdiv(N, nsplit);
+        nsplit = cdiv(N, jchunk);
+        for (int k = 0; k < 3; ++k) CK(cudaMalloc(&apf[k], (size_t)nsplit * N * 8));
+        nb_force = nb_atoms * nsplit;
+    }
+    CK(cudaMalloc(&partial_epot, (size_t)std::max(nb_force, 1u) * 8));
+}
+
+void ljgpu_sim::upload_state(const double* x, const double* y, const double* z,
+                             const double* vx, const double* vy, const double* vz) {
+    const size_t N = n, B = N * 8;
+    CK(cudaMemcpyAsync(out3, x, B, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(out3 + N, y, B, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(out3 + 2 * N, z, B, cudaMemcpyHostToDevice, st));
+    import_state_kernel<<<nb_atoms, kBlock, 0, st>>>(n, out3, out3 + N, out3 + 2 * N, pos, orig);
+    check_launch("import_state");
+    CK(cudaMemcpyAsync(v[0], vx, B, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(v[1], vy, B, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(v[2], vz, B, cudaMemcpyHostToDevice, st));
+    for (int k = 0; k < 3; ++k) CK(cudaMemsetAsync(f[k], 0, B, st));
+    CK(cudaMemsetAsync(ctrl, 0, sizeof(StepCtrl), st));
+    pred_valid = false;
+    since_rebuild = 0;
+}
+
+// Re-binning: wrap (.cpp:419-435), cell keys (.cpp:467-478), stable radix sort, permutation of the
+// whole state, cell table, ghost layer, and on the Verlet path the list itself (.cpp:480-550).
+void ljgpu_sim::rebuild() {
+    stage_begin();
+    CK(cudaMemsetAsync(&ctrl->stop, 0, sizeof(unsigned), st));
+    CK(cudaMemsetAsync(&ctrl->maxdisp2, 0, sizeof(unsigned long long), st));
+
+    wrap_key_kernel<<<nb_atoms, kBlock, 0, st>>>(c, pos, pos_tmp, keys, vals);
+    check_launch("wrap_key");
+    int bits = 1; while ((1ull << bits) < (unsigned long long)ncell) ++bits;
+    launches += radix_sort_pairs(keys, vals, n, bits, scr, st);
+    permute_kernel<<<nb_atoms, kBlock, 0, st>>>(n, vals, pos_tmp, pos, x0[0], x0[1], x0[2],
+                                                v[0], v[1], v[2], f[0], f[1], f[2], orig,
+                                                v_alt[0], v_alt[1], v_alt[2], f_alt[0], f_alt[1], f_alt[2], orig_alt);
+    check_launch("permute");
+    for (int k = 0; k < 3; ++k) { std::swap(v[k], v_alt[k]); std::swap(f[k], f_alt[k]); }
+    std::swap(orig, orig_alt);
+
+    CK(cudaMemsetAsync(cstart, 0, (size_t)ncell * 4, st));
+    CK(cudaMemsetAsync(cend, 0, (size_t)ncell * 4, st));
+    cell_bounds_kernel<<<nb_atoms, kBlock, 0, st>>>(n, keys, cstart, cend);
+    check_launch("cell_bounds");
+    cell_count_kernel<<<cdiv(ncell, kBlock), kBlock, 0, st>>>(ncell, cstart, cend, ccount);
+    check_launch("cell_count");
+
+    ext_count_kernel<<<cdiv(necell, kBlock), kBlock, 0, st>>>(nc, ccount, goff);
+    check_launch("ext_count");
+    launches += exclusive_scan_u32(goff, necell, d_total, scr, st);
+    uint32_t G = 0;
+    CK(cudaMemcpyAsync(&G, d_total, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (G > gcap || (size_t)n + G > pos_cap) {
+        const size_t ng = (size_t)G + G / 4 + 4096;
+        dfree(gsrc);
+        CK(cudaMalloc(&gsrc, ng * 4));
+        gcap = ng;
+        double4* np = nullptr;
+        CK(cudaMalloc(&np, ((size_t)n + ng) * sizeof(double4)));
+        CK(cudaMemcpy(np, pos, (size_t)n * sizeof(double4), cudaMemcpyDeviceToDevice));
+        dfree(pos);
+        pos = np; pos_cap = (size_t)n + ng;
+    }
+    if ((size_t)n + G >= (1ull << kGhostShiftBits))
+        throw LjError(LJGPU_EINVAL, "too many atoms + ghosts for the 27-bit ghost source index");
+    nghost = G;
+    ext_fill_kernel<<<cdiv(necell, kBlock), kBlock, 0, st>>>(nc, n, cstart, ccount, goff, estart, ecount, gsrc, (unsigned)gcap);
+    check_launch("ext_fill");
+    if (nghost) {
+        ghost_update_kernel<<<cdiv(nghost, kBlock), kBlock, 0, st>>>(nghost, n, c.L, ctrl, pos, gsrc);
+        check_launch("ghost_update");
+    }
+    if (mode == LJGPU_KERNEL_VERLET) build_list();
+    stage_end(ST_REBUILD);
+    ++rebuilds;
+    if (since_rebuild > 0) last_interval = since_rebuild;
+    since_rebuild = 0;
+    dirty_since_rebuild = false;
+}
+
+void ljgpu_sim::build_list() {
+    CellGrid g{cstart, ccount, estart, ecount, nc};
+    const unsigned nbc = cdiv(ncell, kCellWarps);
+    const unsigned ntiles = cdiv(n, 32);
+    for (int attempt = 0; attempt < 4; ++attempt) {
+        CK(cudaMemsetAsync(&ctrl->max_count, 0, sizeof(unsigned), st));
+        CK(cudaMemsetAsync(&ctrl->overflow, 0, sizeof(unsigned), st));
+        if (cap == 0) {
+            build_list_kernel<false><<<nbc, kCellWarps * 32, 0, st>>>(c, g, pos, 0, nullptr, nl_count, ctrl);
+            check_launch("build_list<count>");
+            fetch_ctrl();
+            cap = ((h_ctrl->max_count + 8 + 3) / 4) * 4;
+        }
+        const size_t need = (size_t)ntiles * cap * 32;
+        if (need > nl_alloc) {
+            dfree(nl);
+            CK(cudaMalloc(&nl, need * 4));
+            nl_alloc = need;
+        }
+        build_list_kernel<true><<<nbc, kCellWarps * 32, 0, st>>>(c, g, pos, cap, nl, nl_count, ctrl);
+        check_launch("build_list<fill>");
+        fetch_ctrl();
+        if (!h_ctrl->overflow) return;
+        cap = ((h_ctrl->max_count + 8 + 3) / 4) * 4;       // grow and refill
+    }
+    throw LjError(LJGPU_ESTATE, "neighbour list capacity did not converge");
+}
+
+void ljgpu_sim::launch_force(bool timed) {
+    if (timed) stage_begin();
+    if (mode == LJGPU_KERNEL_ALLPAIRS) {
+        dim3 grid(nb_atoms, nsplit);
+        force_allpairs_kernel<<<grid, kBlock, 0, st>>>(c, ctrl, pos, jchunk, apf[0], apf[1], apf[2], partial_epot);
+        check_launch("force_allpairs");
+        allpairs_reduce_kernel<<<nb_atoms, kBlock, 0, st>>>(c, ctrl, nsplit, apf[0], apf[1], apf[2], f[0], f[1], f[2]);
+        check_launch("allpairs_reduce");
+    } else if (mode == LJGPU_KERNEL_CELL) {
+        CellGrid g{cstart, ccount, estart, ecount, nc};
+        force_cell_kernel<<<nb_force, kCellWarps * 32, 0, st>>>(c, g, ctrl, pos, f[0], f[1], f[2], partial_epot);
+        check_launch("force_cell");
+    } else {
+        force_verlet_kernel<<<nb_force, kBlock, 0, st>>>(c, ctrl, pos, nl, nl_count, cap, f[0], f[1], f[2], partial_epot);
+        check_launch("force_verlet");
+    }
+    if (timed) stage_end(ST_FORCE);
+}
+
+// Constructor tail, .cpp:57-62: list, forces, publish; ekin stays 0.
+void ljgpu_sim::initial_forces() {
+    if (list_mode()) rebuild();
+    launch_force(false);
+    init_finalize_kernel<<<1, kFinalizeThreads, 0, st>>>(c, ctrl, partial_epot, nb_force);
+    check_launch("init_finalize");
+    sync();
+}
+
+void ljgpu_sim::launch_predict(double dt) {
+    const double a = 0.5 * dt / p.mass;                                  // .cpp:339
+    stage_begin();
+    predict_kernel<<<nb_atoms, kBlock, 0, st>>>(n, a, v[0], v[1], v[2], f[0], f[1], f[2], partial_pred);
+    check_launch("predict");
+    predict_finalize_kernel<<<1, kFinalizeThreads, 0, st>>>(ctrl, partial_pred, nb_atoms);
+    check_launch("predict_finalize");
+    stage_end(ST_PREDICT);
+    pred_valid = true; pred_dt = dt;
+}
+
+void ljgpu_sim::enqueue_step(unsigned step, double dt) {
+    const double a = 0.5 * dt / p.mass;                                  // .cpp:339
+    c.dt_over_tau = dt / p.tau;                                          // .cpp:375
+    stage_begin();
+    if (list_mode())
+        kick_drift_kernel<true><<<nb_atoms, kBlock, 0, st>>>(c, dt, a, ctrl, pos, x0[0], x0[1], x0[2],
+                                                             v[0], v[1], v[2], f[0], f[1], f[2]);
+    else
+        kick_drift_kernel<false><<<nb_atoms, kBlock, 0, st>>>(c, dt, a, ctrl, pos, nullptr, nullptr, nullptr,
+                                                              v[0], v[1], v[2], f[0], f[1], f[2]);
+    check_launch("kick_drift");
+    stage_end(ST_KICK_DRIFT);
+    if (list_mode() && nghost) {
+        stage_begin();
+        ghost_update_kernel<<<cdiv(nghost, kBlock), kBlock, 0, st>>>(nghost, n, c.L, ctrl, pos, gsrc);
+        check_launch("ghost_update");
+        stage_end(ST_GHOST);
+    }
+    launch_force(true);
+    stage_begin();
+    if (list_mode())
+        kick2_kernel<false><<<nb_atoms, kBlock, 0, st>>>(c, a, ctrl, pos, v[0], v[1], v[2], f[0], f[1], f[2], partial_ekin, partial_pred);
+    else
+        kick2_kernel<true><<<nb_atoms, kBlock, 0, st>>>(c, a, ctrl, pos, v[0], v[1], v[2], f[0], f[1], f[2], partial_ekin, partial_pred);
+    check_launch("kick2");
+    step_finalize_kernel<<<1, kFinalizeThreads, 0, st>>>(c, ctrl, hist, step, partial_epot, nb_force,
+                                                         partial_ekin, partial_pred, nb_atoms);
+    check_launch("step_finalize");
+    stage_end(ST_KICK2);
+}
+
+// n integrate() calls.  Steps are enqueued in batches without host round trips; once a step finds a
+// displacement beyond shell/2 (.cpp:557-568) the device raises `stop`, the rest of the batch turns
+// into no-ops, and the host re-bins (.cpp:89-91) before continuing.
+void ljgpu_sim::run_steps(unsigned first, unsigned nsteps, double dt) {
+    unsigned step = first, remaining = nsteps;
+    while (remaining) {
+        if (!pred_valid || pred_dt != dt) launch_predict(dt);
+        unsigned batch;
+        if (!list_mode()) batch = std::min(remaining, 512u);
+        else if (since_rebuild < last_interval) batch = std::max(1u, ((last_interval - since_rebuild) * 3u) / 4u);
+        else batch = 2;
+        batch = std::min(std::min(batch, remaining), 256u);
+        CK(cudaMemsetAsync(&ctrl->steps_done, 0, sizeof(unsigned), st));
+        for (unsigned k = 0; k < batch; ++k) enqueue_step(step + k, dt);
+        fetch_ctrl();
+        const unsigned done = h_ctrl->steps_done;
+        step += done; remaining -= done; steps += done; since_rebuild += done;
+        if (done) dirty_since_rebuild = true;
+        if (h_ctrl->stop) rebuild();
+        else if (done != batch) throw LjError(LJGPU_ESTATE, "step batch ended early without a rebuild request");
+    }
+}
+
+void ljgpu_sim::export3(int what, double* a, double* b, double* cc) {
+    const size_t N = n;
+    if (what == 0) {
+        if (list_mode()) export_positions_kernel<true><<<nb_atoms, kBlock, 0, st>>>(c, pos, orig, out3, out3 + N, out3 + 2 * N);
+        else export_positions_kernel<false><<<nb_atoms, kBlock, 0, st>>>(c, pos, orig, out3, out3 + N, out3 + 2 * N);
+    } else {
+        double** src = what == 1 ? v : f;
+        export_soa_kernel<<<nb_atoms, kBlock, 0, st>>>(n, src[0], src[1], src[2], orig, out3, out3 + N, out3 + 2 * N);
+    }
+    check_launch("export");
+    CK(cudaMemcpyAsync(a, out3, N * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(b, out3 + N, N * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(cc, out3 + 2 * N, N * 8, cudaMemcpyDeviceToHost, st));
+    sync();
+}
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+namespace {
+
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+template <class F>
+int guarded(F&& fn) {
+    try { fn(); g_err.clear(); return LJGPU_OK; }
+    catch (const LjError& e) { return fail(e.code, e.what()); }
+    catch (const std::exception& e) { return fail(LJGPU_ECUDA, e.what()); }
+}
+
+template <class F>
+int with_sim(ljgpu_sim* s, F&& fn) {
+    if (!s) return fail(LJGPU_EINVAL, "null simulation handle");
+    return guarded([&] {
+        std::lock_guard<std::mutex> lk(s->mu);
+        CK(cudaSetDevice(s->device));
+        fn();
+    });
+}
+
+void validate(const ljgpu_params& p, int& mode) {
+    auto bad = [](const std::string& m) { throw LjError(LJGPU_EINVAL, m); };
+    if (p.nr_particles < 2) bad("nr_particles must be at least 2");
+    if (!(p.cell_length > 0) || !(p.mass > 0) || !(p.sigma > 0) || !(p.rcut > 0) || !(p.shell >= 0) || !(p.tau != 0))
+        bad("cell_length, mass, sigma, rcut must be positive, shell non-negative, tau non-zero");
+    const unsigned ncells = std::max(1u, (unsigned)(p.cell_length / (p.rcut + p.shell)));
+    if (ncells < 3)
+        bad("cell_length / (rcut + shell) < 3: the reference's 27-cell stencil revisits cells there and "
+            "double-counts pairs (lennardjonessimulation.cpp:496-516); such boxes are not supported");
+    mode = p.force_kernel;
+    if (mode == LJGPU_KERNEL_AUTO) mode = p.nr_particles <= 8192 ? LJGPU_KERNEL_ALLPAIRS : LJGPU_KERNEL_VERLET;
+    if (mode < LJGPU_KERNEL_ALLPAIRS || mode > LJGPU_KERNEL_VERLET) bad("unknown force_kernel");
+    if (mode == LJGPU_KERNEL_ALLPAIRS && p.nr_particles > (1 << 20)) bad("all-pairs path is limited to 2^20 atoms");
+}
+
+} // namespace
+
+extern "C" {
+
+const char* ljgpu_last_error(void) { return g_err.c_str(); }
+
+int ljgpu_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int ljgpu_create(const ljgpu_params* p, const double* x, const double* y, const double* z,
+                 const double* vx, const double* vy, const double* vz, ljgpu_sim** out) {
+    if (!p || !x || !y || !z || !vx || !vy || !vz || !out) return fail(LJGPU_EINVAL, "null argument");
+    *out = nullptr;
+    ljgpu_sim* s = nullptr;
+    int rc = guarded([&] {
+        int mode = 0;
+        validate(*p, mode);
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+            cudaGetLastError();
+            throw LjError(LJGPU_ECUDA, "no CUDA device available (libljgpu has no CPU fallback)");
+        }
+        int dev = p->device;
+        if (dev < 0) CK(cudaGetDevice(&dev));
+        if (dev >= ndev) throw LjError(LJGPU_EINVAL, "device ordinal out of range");
+        CK(cudaSetDevice(dev));
+        s = new ljgpu_sim;
+        s->p = *p; s->mode = mode; s->device = dev; s->n = (unsigned)p->nr_particles;
+        CK(cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking));
+        s->setup_constants();
+        s->allocate();
+        s->upload_state(x, y, z, vx, vy, vz);
+        s->initial_forces();
+    });
+    if (rc != LJGPU_OK) { delete s; return rc; }
+    *out = s;
+    return LJGPU_OK;
+}
+
+void ljgpu_destroy(ljgpu_sim* s) { delete s; }
+
+int ljgpu_set_state(ljgpu_sim* s, const double* x, const double* y, const double* z,
+                    const double* vx, const double* vy, const double* vz) {
+    if (!x || !y || !z || !vx || !vy || !vz) return fail(LJGPU_EINVAL, "null argument");
+    return with_sim(s, [&] { s->upload_state(x, y, z, vx, vy, vz); s->initial_forces(); });
+}
+
+int ljgpu_update_params(ljgpu_sim* s, const ljgpu_params* p) {
+    if (!p) return fail(LJGPU_EINVAL, "null argument");
+    return with_sim(s, [&] {
+        if (p->cell_length != s->p.cell_length || p->nr_particles != s->p.nr_particles ||
+            p->rcut != s->p.rcut || p->shell != s->p.shell)
+            throw LjError(LJGPU_EINVAL, "cell_length, nr_particles, rcut and shell cannot change on a live simulation");
+        if (!(p->mass > 0) || !(p->sigma > 0) || !(p->tau != 0)) throw LjError(LJGPU_EINVAL, "bad parameter value");
+        const bool force_changed = p->sigma != s->p.sigma || p->epsilon != s->p.epsilon;
+        const int keep_kernel = s->p.force_kernel, keep_dev = s->p.device;
+        s->p = *p; s->p.force_kernel = keep_kernel; s->p.device = keep_dev;
+        const double dto = s->c.dt_over_tau;
+        s->setup_constants();
+        s->c.dt_over_tau = dto;
+        s->pred_valid = false;                         // mass enters the kick factor
+        if (force_changed) {                           // forces of the current positions under the new potential
+            s->launch_force(false);
+            init_finalize_kernel<<<1, kFinalizeThreads, 0, s->st>>>(s->c, s->ctrl, s->partial_epot, s->nb_force);
+            s->check_launch("init_finalize");
+            s->sync();
+        }
+    });
+}
+
+int ljgpu_step(ljgpu_sim* s, uint32_t step, double dt) {
+    return with_sim(s, [&] { s->run_steps(step, 1, dt); });
+}
+
+int ljgpu_step_n(ljgpu_sim* s, uint32_t first, uint32_t n, double dt) {
+    return with_sim(s, [&] { s->run_steps(first, n, dt); });
+}
+
+int ljgpu_get_positions(ljgpu_sim* s, double* x, double* y, double* z) {
+    if (!x || !y || !z) return fail(LJGPU_EINVAL, "null argument");
+    return with_sim(s, [&] { s->export3(0, x, y, z); });
+}
+int ljgpu_get_velocities(ljgpu_sim* s, double* x, double* y, double* z) {
+    if (!x || !y || !z) return fail(LJGPU_EINVAL, "null argument");
+    return with_sim(s, [&] { s->export3(1, x, y, z); });
+}
+int ljgpu_get_forces(ljgpu_sim* s, double* x, double* y, double* z) {
+    if (!x || !y || !z) return fail(LJGPU_EINVAL, "null argument");
+    return with_sim(s, [&] { s->export3(2, x, y, z); });
+}
+
+int ljgpu_get_energies(ljgpu_sim* s, double* ekin, double* epot, double* etot) {
+    return with_sim(s, [&] {
+        s->fetch_ctrl();
+        if (ekin) *ekin = s->h_ctrl->ekin;
+        if (epot) *epot = s->h_ctrl->epot;
+        if (etot) *etot = s->h_ctrl->etot;
+    });
+}
+
+int ljgpu_get_energy_history(ljgpu_sim* s, uint32_t max_entries, uint32_t* step_index,
+                             double* ekin, double* epot, uint32_t* n_out) {
+    if (!n_out) return fail(LJGPU_EINVAL, "null argument");
+    return with_sim(s, [&] {
+        s->fetch_ctrl();
+        std::vector<HistEntry> h(kHistCap);
+        CK(cudaMemcpyAsync(h.data(), s->hist, sizeof(HistEntry) * kHistCap, cudaMemcpyDeviceToHost, s->st));
+        s->sync();
+        const unsigned long long head = s->h_ctrl->hist_head;
+        const unsigned long long avail = std::min<unsigned long long>(head, kHistCap);
+        const unsigned long long take = std::min<unsigned long long>(avail, max_entries);
+        for (unsigned long long k = 0; k < take; ++k) {
+            const HistEntry& e = h[(head - take + k) % kHistCap];
+            if (step_index) step_index[k] = e.step;
+            if (ekin) ekin[k] = e.ekin;
+            if (epot) epot[k] = e.epot;
+        }
+        *n_out = (uint32_t)take;
+    });
+}
+
+int ljgpu_get_speed_histogram(ljgpu_sim* s, uint32_t nbins, double vmax, uint64_t* counts) {
+    if (!counts) return fail(LJGPU_EINVAL, "null argument");
+    if (nbins == 0 || nbins > (uint32_t)kMaxBins || !(vmax > 0)) return fail(LJGPU_EINVAL, "nbins must be 1..1024 and vmax positive");
+    return with_sim(s, [&] {
+        CK(cudaMemsetAsync(s->hist_counts, 0, nbins * sizeof(unsigned long long), s->st));
+        const unsigned blocks = std::min(cdiv(s->n, 256), 148u * 8u);
+        speed_histogram_kernel<<<blocks, 256, 0, s->st>>>(s->n, s->v[0], s->v[1], s->v[2], nbins, vmax, s->hist_counts);
+        s->check_launch("speed_histogram");
+        static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "");
+        CK(cudaMemcpyAsync(counts, s->hist_counts, nbins * sizeof(uint64_t), cudaMemcpyDeviceToHost, s->st));
+        s->sync();
+    });
+}
+
+int ljgpu_get_cell_ids(ljgpu_sim* s, uint32_t* cell_of_atom, uint32_t dims[3]) {
+    if (!cell_of_atom) return fail(LJGPU_EINVAL, "null argument");
+    return with_sim(s, [&] {
+        if (s->list_mode()) cell_id_probe_kernel<true><<<s->nb_atoms, kBlock, 0, s->st>>>(s->c, s->pos, s->orig, s->out_u32);
+        else cell_id_probe_kernel<false><<<s->nb_atoms, kBlock, 0, s->st>>>(s->c, s->pos, s->orig, s->out_u32);
+        s->check_launch("cell_id_probe");
+        CK(cudaMemcpyAsync(cell_of_atom, s->out_u32, (size_t)s->n * 4, cudaMemcpyDeviceToHost, s->st));
+        s->sync();
+        if (dims) dims[0] = dims[1] = dims[2] = s->nc;
+    });
+}
+
+int ljgpu_get_neighbor_counts(ljgpu_sim* s, double cutoff, int inclusive, uint32_t* count_of_atom) {
+    if (!count_of_atom) return fail(LJGPU_EINVAL, "null argument");
+    return with_sim(s, [&] {
+        if (!(cutoff > 0) || cutoff > s->p.rcut + s->p.shell)
+            throw LjError(LJGPU_EINVAL, "cutoff must be in (0, rcut + shell]");
+        const double cut2 = cutoff * cutoff;
+        if (s->list_mode()) {
+            if (s->dirty_since_rebuild) s->rebuild();       // positions wrapped + cell-sorted again
+            count_cells_kernel<<<cdiv(s->ncell, kCellWarps), kCellWarps * 32, 0, s->st>>>(
+                s->c, s->cstart, s->ccount, s->pos, s->orig, cut2, inclusive, s->out_u32);
+        } else {
+            count_allpairs_kernel<<<s->nb_atoms, kBlock, 0, s->st>>>(s->c, s->pos, s->orig, cut2, inclusive, s->out_u32);
+        }
+        s->check_launch("neighbor_count");
+        CK(cudaMemcpyAsync(count_of_atom, s->out_u32, (size_t)s->n * 4, cudaMemcpyDeviceToHost, s->st));
+        s->sync();
+    });
+}
+
+int ljgpu_write_movie_frame(ljgpu_sim* s, const char* path, int create) {
+    if (!path) return fail(LJGPU_EINVAL, "null argument");
+    return with_sim(s, [&] {
+        const size_t N = s->n;
+        std::vector<double> buf(6 * N);
+        s->export3(0, &buf[0], &buf[N], &buf[2 * N]);
+        s->export3(1, &buf[3 * N], &buf[4 * N], &buf[5 * N]);
+        FILE* fp = std::fopen(path, create ? "wb" : "ab");                 // .cpp:131-138
+        if (!fp) throw LjError(LJGPU_EINVAL, std::string("cannot open ") + path);
+        if (create) { const uint32_t n32 = (uint32_t)N; std::fwrite(&n32, sizeof n32, 1, fp); }
+        const double dims[3] = {s->p.cell_length, s->p.cell_length, s->p.cell_length};
+        std::fwrite(dims, sizeof(double), 3, fp);                           // .cpp:141-143
+        std::vector<double> rec(7 * N);
+        for (size_t i = 0; i < N; ++i) {                                    // .cpp:145-154
+            double* r = &rec[7 * i];
+            r[0] = buf[i]; r[1] = buf[N + i]; r[2] = buf[2 * N + i];
+            r[3] = buf[3 * N + i]; r[4] = buf[4 * N + i]; r[5] = buf[5 * N + i];
+            r[6] = std::sqrt(r[3] * r[3] + r[4] * r[4] + r[5] * r[5]);
+        }
+        std::fwrite(rec.data(), sizeof(double), rec.size(), fp);
+        std::fclose(fp);
+    });
+}
+
+int ljgpu_set_profiling(ljgpu_sim* s, int enabled) {
+    return with_sim(s, [&] { s->sync(); s->prof = enabled != 0; });
+}
+
+int ljgpu_get_timers(ljgpu_sim* s, ljgpu_timers* out) {
+    if (!out) return fail(LJGPU_EINVAL, "null argument");
+    return with_sim(s, [&] {
+        s->sync();
+        out->ms_predict = s->ms[ST_PREDICT]; out->ms_kick_drift = s->ms[ST_KICK_DRIFT]; out->ms_ghost = s->ms[ST_GHOST];
+        out->ms_force = s->ms[ST_FORCE]; out->ms_kick2 = s->ms[ST_KICK2]; out->ms_rebuild = s->ms[ST_REBUILD]; out->ms_halo = s->ms[ST_HALO];
+        out->n_predict = s->cnt[ST_PREDICT]; out->n_kick_drift = s->cnt[ST_KICK_DRIFT]; out->n_ghost = s->cnt[ST_GHOST];
+        out->n_force = s->cnt[ST_FORCE]; out->n_kick2 = s->cnt[ST_KICK2]; out->n_rebuild = s->cnt[ST_REBUILD]; out->n_halo = s->cnt[ST_HALO];
+        out->steps = s->steps; out->rebuilds = s->rebuilds; out->kernel_launches = s->launches;
+    });
+}
+
+int ljgpu_reset_timers(ljgpu_sim* s) {
+    return with_sim(s, [&] {
+        s->sync();
+        for (int k = 0; k < ST_COUNT; ++k) { s->ms[k] = 0; s->cnt[k] = 0; }
+        s->steps = 0; s->rebuilds = 0; s->launches = 0;
+    });
+}
+
+int ljgpu_get_layout(ljgpu_sim* s, int32_t* force_kernel, uint32_t* cells_per_axis,
+                     uint32_t* list_capacity, uint64_t* n_ghosts) {
+    return with_sim(s, [&] {
+        if (force_kernel) *force_kernel = s->mode;
+        if (cells_per_axis) *cells_per_axis = s->nc;
+        if (list_capacity) *list_capacity = s->cap;
+        if (n_ghosts) *n_ghosts = s->nghost;
+    });
+}
+
+} // extern "C"

@@ -1,0 +1,209 @@
+"""GPU parity tests: the CUDA integrator (through the C ABI) against the CPU oracle on the same
+seeded inputs.  Tolerances follow BASELINE.json's north_star: integer outputs bit-exact; forces and
+energies within 1e-12 relative over 10-step windows."""
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-12
+DT = 0.001
+
+
+def rel(a, b):
+    return abs(a - b) / max(abs(b), 1e-300)
+
+
+def make_pair(lj, cfg, kernel, state=None):
+    """Oracle + GPU simulation started from the same state (the oracle's initialize())."""
+    o = ol.Oracle(cfg, state=state)
+    st = o.state()
+    params = lj.LennardJonesParameters(**cfg)
+    g = lj.LennardJonesSimulation(params, st, force_kernel=kernel)
+    return o, g
+
+
+def check_step(o, g, tol=TOL, what=""):
+    ek, ep, et = g.get_energies()
+    oek, oep, oet = o.energies()
+    assert rel(ep, oep) < tol, f"{what} epot {ep} vs {oep}"
+    if oek != 0.0:
+        assert rel(ek, oek) < tol, f"{what} ekin {ek} vs {oek}"
+        assert abs(et - oet) < tol * (abs(oek) + abs(oep)), f"{what} etot {et} vs {oet}"
+    else:
+        assert ek == 0.0
+    err = ol.force_rel_error(g.get_forces_soa(), o.forces())
+    assert err.max() < tol, f"{what} force rel err {err.max()}"
+
+
+CASES = [
+    ("default-allpairs", ol.DEFAULT, 1),
+    ("default-cell", ol.DEFAULT, 2),
+    ("default-verlet", ol.DEFAULT, 3),
+    ("n4096-allpairs", ol.config(4096), 1),
+    ("n4096-cell", ol.config(4096), 2),
+    ("n4096-verlet", ol.config(4096), 3),
+    ("n3000-ragged-verlet", ol.config(3000, rho=0.6), 3),     # not a cube: lattice with empty sites
+    ("triple-point-verlet", ol.config(4096, rho=0.84, kT=0.72), 3),
+]
+
+
+@pytest.mark.parametrize("name,cfg,kernel", CASES, ids=[c[0] for c in CASES])
+def test_ten_step_window(lj, name, cfg, kernel):
+    o, g = make_pair(lj, cfg, kernel)
+    assert g.get_layout()["force_kernel"] == kernel
+    check_step(o, g, what=f"{name} step 0")
+    for s in range(1, 11):
+        o.integrate(s, DT)
+        g.integrate(s, DT)
+        check_step(o, g, what=f"{name} step {s}")
+    # state after the window
+    L = cfg["cell_length"]
+    for a, b in zip(g.get_velocities_soa(), o.velocities()):
+        assert np.max(np.abs(a - b)) < 1e-12
+    for a, b in zip(g.get_positions_soa(), o.positions()):
+        d = np.abs(a - b)
+        d = np.minimum(d, L - d)          # an atom sitting on a face may be reported on either side
+        assert d.max() < 1e-12
+
+
+@pytest.mark.parametrize("kernel", [2, 3])
+def test_n65536_window(lj, kernel):
+    cfg = ol.config(65536)
+    o, g = make_pair(lj, cfg, kernel)
+    check_step(o, g, what="n65536 step 0")
+    for s in range(1, 11):
+        o.integrate(s, DT)
+        g.integrate(s, DT)
+        check_step(o, g, what=f"n65536 step {s}")
+
+
+def equilibrated_state(cfg, steps):
+    o = ol.Oracle(cfg)
+    o.run(1, steps, DT)
+    return o
+
+
+@pytest.mark.parametrize("kernel", [1, 2, 3])
+def test_window_from_equilibrated_liquid(lj, kernel):
+    """Start from a melted configuration (400 oracle steps incl. several list rebuilds) and compare a
+    10-step window; then step across rebuilds with batched stepping."""
+    cfg = ol.config(4096)
+    o = equilibrated_state(cfg, 400)
+    assert o.rebuild_count() > 3
+    o2, g = make_pair(lj, cfg, kernel, state=o.state())
+    check_step(o2, g, what="equil step 0")
+    for s in range(1, 11):
+        o2.integrate(s, DT)
+        g.integrate(s, DT)
+        check_step(o2, g, what=f"equil step {s}")
+    # 150 more steps in one batched call (crosses rebuilds on the list paths); chaos amplifies
+    # rounding differences, so the tolerance is looser here
+    o2.run(11, 150, DT)
+    g.integrate_n(11, 150, DT)
+    ek, ep, _ = g.get_energies()
+    oek, oep, _ = o2.energies()
+    assert rel(ek, oek) < 1e-8 and rel(ep, oep) < 1e-8
+    if kernel != 1:
+        assert g.get_timers()["rebuilds"] >= 2
+
+
+def test_step_n_equals_repeated_step(lj):
+    cfg = ol.config(4096)
+    o = equilibrated_state(cfg, 200)
+    st = o.state()
+    params = lj.LennardJonesParameters(**cfg)
+    a = lj.LennardJonesSimulation(params, st, force_kernel=3)
+    b = lj.LennardJonesSimulation(params, st, force_kernel=3)
+    for s in range(1, 121):
+        a.integrate(s, DT)
+    b.integrate_n(1, 120, DT)
+    assert a.get_energies() == b.get_energies()
+    for u, v in zip(a.get_positions_soa() + a.get_velocities_soa(), b.get_positions_soa() + b.get_velocities_soa()):
+        assert np.array_equal(u, v)
+    steps, ek, ep = b.get_energy_history(120)
+    assert list(steps) == list(range(1, 121))
+    assert ek[-1] == b.get_ekin() and ep[-1] == b.get_epot()
+
+
+@pytest.mark.parametrize("kernel", [1, 2, 3])
+def test_cell_ids_and_neighbor_counts_bit_exact(lj, kernel):
+    cfg = ol.config(4096)
+    o, g = make_pair(lj, cfg, kernel)
+    # start lattice
+    ocell, odims = o.cell_ids()
+    gcell, gdims = g.get_cell_ids()
+    assert gdims == odims
+    assert np.array_equal(gcell, ocell)
+    assert np.array_equal(g.get_neighbor_counts(cfg["rcut"] + cfg["shell"], True), o.neighbor_counts())
+    assert np.array_equal(g.get_neighbor_counts(cfg["rcut"], False), o.incutoff_counts())
+    # melted: feed the oracle's state after 300 steps to both
+    o.run(1, 300, DT)
+    st = o.state()
+    o2 = ol.Oracle(cfg, state=st)
+    g.set_state(st)
+    ocell, _ = o2.cell_ids()
+    gcell, _ = g.get_cell_ids()
+    assert np.array_equal(gcell, ocell)
+    assert np.array_equal(g.get_neighbor_counts(cfg["rcut"] + cfg["shell"], True), o2.neighbor_counts())
+    assert np.array_equal(g.get_neighbor_counts(cfg["rcut"], False), o2.incutoff_counts())
+    # and after stepping the GPU itself: compare with the oracle's formulas on the GPU's positions
+    g.integrate_n(1, 25, DT)
+    x, y, z = g.get_positions_soa()
+    gcell, _ = g.get_cell_ids()
+    ocell, _ = ol.oracle_cell_ids_of(cfg, x, y, z)
+    assert np.array_equal(gcell, ocell)
+    want = ol.oracle_pair_counts(cfg["cell_length"], x, y, z, cfg["rcut"] + cfg["shell"])
+    assert np.array_equal(g.get_neighbor_counts(cfg["rcut"] + cfg["shell"], True), want)
+
+
+def test_speed_histogram_bit_exact(lj):
+    cfg = ol.config(4096)
+    o, g = make_pair(lj, cfg, 3)
+    g.integrate_n(1, 50, DT)
+    vx, vy, vz = g.get_velocities_soa()
+    want = ol.oracle_speed_histogram(vx, vy, vz, 100, 10.0)
+    got = g.get_speed_histogram(100, 10.0)
+    assert got.sum() == cfg["nr_particles"]
+    assert np.array_equal(got, want)
+    # a narrow range exercises the last-bin clamp
+    assert np.array_equal(g.get_speed_histogram(16, 1.5), ol.oracle_speed_histogram(vx, vy, vz, 16, 1.5))
+
+
+def test_changing_dt_and_tau_between_steps(lj):
+    """dt is an argument of every integrate() call and tau is re-read every step by the reference."""
+    cfg = ol.config(4096)
+    o, g = make_pair(lj, cfg, 3)
+    dts = [0.001, 0.002, 0.0005, 0.001, 0.001]
+    for s, dt in enumerate(dts, start=1):
+        if s == 3:
+            o.set_tau(1e300)
+            g.set_param("tau", 1e300)
+        o.integrate(s, dt)
+        g.integrate(s, dt)
+        check_step(o, g, what=f"dt/tau step {s}")
+
+
+def test_momentum_is_conserved(lj):
+    cfg = ol.config(4096)
+    _, g = make_pair(lj, cfg, 3)
+    g.integrate_n(1, 200, DT)
+    v = g.get_velocities_copy()
+    assert np.abs(v.sum(axis=0)).max() < 1e-9
+
+
+def test_rejects_small_boxes_and_bad_arguments(lj):
+    cfg = dict(ol.DEFAULT, cell_length=8.0, nr_particles=100)
+    params = lj.LennardJonesParameters(**cfg)
+    with pytest.raises(lj.LJGpuError):
+        lj.LennardJonesSimulation(params)
+    cfg = ol.config(4096)
+    _, g = make_pair(lj, cfg, 3)
+    with pytest.raises(lj.LJGpuError):
+        g.get_neighbor_counts(10.0)
+    with pytest.raises(lj.LJGpuError):
+        g.get_speed_histogram(0, 10.0)
+    with pytest.raises(lj.LJGpuError):
+        g.set_param("cell_length", 20.0)
