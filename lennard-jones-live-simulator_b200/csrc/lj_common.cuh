@@ -60,6 +60,7 @@ struct LJConst {
     double mass;
     double ekin0;                 // 1.5*(N-1)*kT                               (.cpp:374)
     double dt_over_tau;           // set per step
+    double far2;                  // a hair under (L/2)^2: raw d2 below this => no axis needs the minimum image
     double list_cut2;             // (rcut+shell)^2                             (.cpp:445)
     double disp_thresh;           // shell*shell*0.25                           (.cpp:559-560)
     double cell_edge;             // L / cells_per_axis                         (.cpp:455-457)
@@ -72,7 +73,7 @@ struct StepCtrl {
     double pred_sum;              // sum |v + a f|^2 : kinetic sum the NEXT kick1 will see
     double ekin, epot, etot;      // published (.h:100-102)
     double epot_sum;              // sum over ordered pairs of (s12 - s6 - ecut), last force pass
-    unsigned long long maxdisp2;  // bits of max_i |x_i - x0_i|^2 of the current step
+    unsigned long long maxdisp2;  // bits of max_i |dij_i|^2 of the current step (when above the threshold)
     unsigned int stop;            // a re-binning is due: remaining steps of the batch do nothing
     unsigned int steps_done;      // steps completed in the current batch
     unsigned int overflow;        // list capacity exceeded during a build

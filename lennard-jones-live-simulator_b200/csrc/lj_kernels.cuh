@@ -4,11 +4,15 @@
 // (/root/reference/src/simulator/lennardjonessimulation.cpp:70-98, ".cpp" below):
 //   kick1 -> Berendsen scale -> drift -> forces (on drifted, not yet wrapped positions) -> wrap
 //   -> list-rebuild check (+ rebuild) -> kick2 -> etot -> publish.
-// Here:  kick_drift_kernel (kick1 + scale + drift + displacement check, one pass over HBM)
-//        ghost_update_kernel (periodic images follow their owners; list paths only)
-//        force_*_kernel
-//        kick2_kernel (kick2 + sum v^2 + the NEXT step's kick1 kinetic sum; + wrap on the all-pairs path)
+// Here:  kick_drift_kernel (the PREVIOUS step's wrap applied lazily, kick1 + scale + drift + displacement
+//                           accumulation and check: one pass over HBM)
+//        force_*_kernel    (on the drifted, not yet wrapped positions, as the reference)
+//        kick2_kernel      (kick2 + sum v^2 + the NEXT step's kick1 kinetic sum)
 //        step_finalize_kernel (fixed-order final reductions, energies, history, rebuild flag).
+// Stored positions are the reference's positions BEFORE its wrap of the current step; the wrap
+// (x - L*floor(x/L), .cpp:431-433) is applied wherever the reference would read a wrapped value: at the
+// top of the next drift, in the re-binning, and in every query.  Values are bit-identical to wrapping
+// eagerly and it saves one read+write of the positions per step.
 #pragma once
 #include "lj_common.cuh"
 
@@ -49,17 +53,15 @@ predict_finalize_kernel(StepCtrl* __restrict__ ctrl, const double* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------------
-// K2  kick1 + Berendsen + drift (+ displacement check)
-//     .cpp:336-362 (kick), :368-383 (lambda from the kick1 kinetic energy), :388-413 (drift),
-//     :557-568 (any |displacement|^2 > shell^2/4 since the last binning).
-//     Displacement is x - x0 with x0 the position at the last binning (the reference accumulates the
-//     increments instead; the two differ in the last bits only).
+// K2  (lazy wrap) + kick1 + Berendsen + drift + displacement accumulation and check
+//     .cpp:431-433 (wrap of the previous step), :336-362 (kick), :368-383 (lambda from the kick1 kinetic
+//     energy), :388-413 (drift, dij += inc), :557-568 (any |dij|^2 > shell^2/4).
 // ---------------------------------------------------------------------------------------------
 template <bool TRACK_DISP>
 __global__ void __launch_bounds__(kBlock)
 kick_drift_kernel(LJConst c, double dt, double a, StepCtrl* __restrict__ ctrl,
                   double4* __restrict__ pos,
-                  const double* __restrict__ x0, const double* __restrict__ y0, const double* __restrict__ z0,
+                  double* __restrict__ dijx, double* __restrict__ dijy, double* __restrict__ dijz,
                   double* __restrict__ vx, double* __restrict__ vy, double* __restrict__ vz,
                   const double* __restrict__ fx, const double* __restrict__ fy, const double* __restrict__ fz) {
     __shared__ double red[32];
@@ -72,16 +74,22 @@ kick_drift_kernel(LJConst c, double dt, double a, StepCtrl* __restrict__ ctrl,
     double d2 = 0.0;
     if (i < c.n) {
         double4 p = pos[i];
+        p.x = wrap_coord(p.x, c.L, c.invL);
+        p.y = wrap_coord(p.y, c.L, c.invL);
+        p.z = wrap_coord(p.z, c.L, c.invL);
         double ux = xadd(vx[i], xmul(a, fx[i]));
         double uy = xadd(vy[i], xmul(a, fy[i]));
         double uz = xadd(vz[i], xmul(a, fz[i]));
         ux = xmul(ux, lambda); uy = xmul(uy, lambda); uz = xmul(uz, lambda);
-        p.x = xadd(p.x, xmul(ux, dt));
-        p.y = xadd(p.y, xmul(uy, dt));
-        p.z = xadd(p.z, xmul(uz, dt));
+        const double incx = xmul(ux, dt), incy = xmul(uy, dt), incz = xmul(uz, dt);
+        p.x = xadd(p.x, incx); p.y = xadd(p.y, incy); p.z = xadd(p.z, incz);
         vx[i] = ux; vy[i] = uy; vz[i] = uz;
         pos[i] = p;
-        if (TRACK_DISP) d2 = xnorm2(xsub(p.x, x0[i]), xsub(p.y, y0[i]), xsub(p.z, z0[i]));
+        if (TRACK_DISP) {
+            const double ax = xadd(dijx[i], incx), ay = xadd(dijy[i], incy), az = xadd(dijz[i], incz);
+            dijx[i] = ax; dijy[i] = ay; dijz[i] = az;
+            d2 = xnorm2(ax, ay, az);
+        }
     }
     if (TRACK_DISP) {
         d2 = block_max(d2, red);
@@ -91,25 +99,13 @@ kick_drift_kernel(LJConst c, double dt, double a, StepCtrl* __restrict__ ctrl,
 }
 
 // ---------------------------------------------------------------------------------------------
-// Ghost atoms: slot n+g mirrors atom (gsrc & mask) displaced by a whole number of box edges, so the
-// list kernels need no minimum-image logic in their inner loops (what .cpp:295-302 does per pair).
+// Minimum image without paying for it on every pair.  The reference shifts an axis only when
+// |d| >= L/2 (.cpp:295-302); then the raw d2 is at least L^2/4, far beyond any cutoff in use
+// (L >= 3 (rcut+shell)).  So: raw d2 below `far2` (a hair under L^2/4) => no axis shifts and the raw
+// difference IS the reference's; otherwise redo the pair with the reference's exact comparisons.
 // ---------------------------------------------------------------------------------------------
-constexpr unsigned kGhostShiftBits = 27;
-constexpr unsigned kGhostIdxMask = (1u << kGhostShiftBits) - 1u;
-
-__global__ void __launch_bounds__(kBlock)
-ghost_update_kernel(unsigned nghost, unsigned nreal, double L, const StepCtrl* __restrict__ ctrl,
-                    double4* __restrict__ pos, const uint32_t* __restrict__ gsrc) {
-    if (ctrl->stop) return;
-    const unsigned g = blockIdx.x * kBlock + threadIdx.x;
-    if (g >= nghost) return;
-    const uint32_t s = gsrc[g];
-    const unsigned code = s >> kGhostShiftBits;
-    double4 p = pos[s & kGhostIdxMask];
-    p.x += L * (double)((int)(code % 3u) - 1);
-    p.y += L * (double)((int)((code / 3u) % 3u) - 1);
-    p.z += L * (double)((int)(code / 9u) - 1);
-    pos[nreal + g] = p;
+__device__ __forceinline__ bool maybe_wrapped(double d2raw, int far2_hi) {
+    return __double2hiint(d2raw) >= far2_hi;          // integer compare on the high word: no fp64 issue slot
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -183,52 +179,57 @@ allpairs_reduce_kernel(LJConst c, const StepCtrl* __restrict__ ctrl, unsigned ns
 }
 
 // ---------------------------------------------------------------------------------------------
-// Cell traversal shared by the list build and the cell-list force kernel: one warp per home cell,
-// lanes = home atoms, the 27 stencil cells (extended grid: ghost layer included, so no periodic
-// index wrap and no minimum image) streamed through a warp-private shared-memory tile.
+// Cell traversal shared by the list build, the neighbour-count probe and the cell-list force kernel:
+// one warp per home cell, lanes = home atoms, the 27 periodic stencil cells of .cpp:488-516 streamed
+// through a warp-private shared-memory tile.  Distances are formed exactly as the reference forms them
+// (no contraction), so acceptance decisions are bit-identical.
 // ---------------------------------------------------------------------------------------------
 constexpr int kCellWarps = 4;
 
 struct CellGrid {
-    const uint32_t* __restrict__ cstart;     // inner cells: first slot
-    const uint32_t* __restrict__ ccount;     // inner cells: atoms
-    const uint32_t* __restrict__ estart;     // extended cells: first slot (ghost cells point past n)
-    const uint32_t* __restrict__ ecount;
-    unsigned nc;                             // inner cells per axis
+    const uint32_t* __restrict__ cstart;     // first slot of every cell
+    const uint32_t* __restrict__ ccount;     // atoms per cell
+    unsigned nc;                             // cells per axis
 };
 
 template <class Op>
-__device__ __forceinline__ void cell_traverse(const CellGrid& g, const double4* __restrict__ pos,
+__device__ __forceinline__ void cell_traverse(const LJConst& c, const CellGrid& g, const double4* __restrict__ pos,
                                               double4 (*tile)[32], Op& op) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const unsigned cell = blockIdx.x * kCellWarps + w;
-    const unsigned ncell = g.nc * g.nc * g.nc;
-    if (cell >= ncell) return;
-    const unsigned ix = cell % g.nc, iy = (cell / g.nc) % g.nc, iz = cell / (g.nc * g.nc);
-    const unsigned E = g.nc + 2;
+    const unsigned nc = g.nc;
+    if (cell >= nc * nc * nc) return;
+    const unsigned ix = cell % nc, iy = (cell / nc) % nc, iz = cell / (nc * nc);
+    const int far2_hi = __double2hiint(c.far2);
     const unsigned hs = g.cstart[cell], hn = g.ccount[cell];
     for (unsigned hb = 0; hb < hn; hb += 32) {
         const unsigned i = hs + hb + lane;
         const bool active = hb + lane < hn;
-        const double4 pi = active ? pos[i] : make_double4(1e300, 1e300, 1e300, 0);
+        const double4 pi = active ? pos[i] : make_double4(0, 0, 0, 0);
         op.begin(i, active);
-        for (unsigned dz = 0; dz < 3; ++dz)
-        for (unsigned dy = 0; dy < 3; ++dy) {
-            // the three x-adjacent extended cells are consecutive in memory order of the table
-            const unsigned e0 = ((iz + dz) * E + (iy + dy)) * E + ix;
-            for (unsigned dx = 0; dx < 3; ++dx) {
-                const unsigned js = g.estart[e0 + dx], jn = g.ecount[e0 + dx];
-                for (unsigned jb = 0; jb < jn; jb += 32) {
-                    __syncwarp();
-                    if (jb + lane < jn) tile[w][lane] = pos[js + jb + lane];
-                    __syncwarp();
-                    const unsigned cnt = min(32u, jn - jb);
-                    for (unsigned jj = 0; jj < cnt; ++jj) {
-                        const double4 pj = tile[w][jj];
-                        const double ddx = pi.x - pj.x, ddy = pi.y - pj.y, ddz = pi.z - pj.z;
-                        const double d2 = fma(ddz, ddz, fma(ddy, ddy, ddx * ddx));
-                        op.pair(i, js + jb + jj, ddx, ddy, ddz, d2, active);
+#pragma unroll 1
+        for (int s = 0; s < 27; ++s) {
+            // stencil cell with periodic wrap of the cell coordinates (.cpp:496-516)
+            const int ox = s % 3 - 1, oy = (s / 3) % 3 - 1, oz = s / 9 - 1;
+            const unsigned cx = (ix + nc + ox) % nc, cy = (iy + nc + oy) % nc, cz = (iz + nc + oz) % nc;
+            const unsigned cid = cz * nc * nc + cy * nc + cx;
+            const unsigned js = g.cstart[cid], jn = g.ccount[cid];
+            for (unsigned jb = 0; jb < jn; jb += 32) {
+                __syncwarp();
+                if (jb + lane < jn) tile[w][lane] = pos[js + jb + lane];
+                __syncwarp();
+                const unsigned cnt = min(32u, jn - jb);
+                for (unsigned jj = 0; jj < cnt; ++jj) {
+                    const double4 pj = tile[w][jj];
+                    double ddx = xsub(pi.x, pj.x), ddy = xsub(pi.y, pj.y), ddz = xsub(pi.z, pj.z);
+                    double d2 = xnorm2(ddx, ddy, ddz);
+                    if (maybe_wrapped(d2, far2_hi)) {
+                        ddx = min_image(ddx, c.L, c.halfL);
+                        ddy = min_image(ddy, c.L, c.halfL);
+                        ddz = min_image(ddz, c.L, c.halfL);
+                        d2 = xnorm2(ddx, ddy, ddz);
                     }
+                    op.pair(i, js + jb + jj, ddx, ddy, ddz, d2, active);
                 }
             }
         }
@@ -243,36 +244,42 @@ __device__ __forceinline__ size_t nl_index(unsigned i, unsigned k, unsigned cap)
     return ((size_t)(i >> 5) * cap + k) * 32 + (i & 31u);
 }
 
-template <bool FILL>
-struct ListBuildOp {
-    double cut2; unsigned cap; uint32_t* nl; uint32_t* nl_count; StepCtrl* ctrl; unsigned cnt;
+// MODE 0: count only (inclusive), 1: fill the list (inclusive), 2: probe with caller cutoff / strictness
+template <int MODE>
+struct ListOp {
+    double cut2; int inclusive; unsigned cap; uint32_t* nl; uint32_t* out_count; const uint32_t* orig;
+    StepCtrl* ctrl; unsigned cnt;
     __device__ __forceinline__ void begin(unsigned, bool) { cnt = 0; }
     __device__ __forceinline__ void pair(unsigned i, unsigned j, double, double, double, double d2, bool active) {
-        if (active && d2 <= cut2 && j != i) {
-            if (FILL && cnt < cap) nl[nl_index(i, cnt, cap)] = j;
+        const bool in = (MODE == 2 && !inclusive) ? (d2 < cut2) : (d2 <= cut2);
+        if (active && in && j != i) {
+            if (MODE == 1 && cnt < cap) nl[nl_index(i, cnt, cap)] = j;
             ++cnt;
         }
     }
     __device__ __forceinline__ void end(unsigned i, bool active) {
-        if (active) nl_count[i] = FILL ? min(cnt, cap) : cnt;
+        if (MODE == 2) { if (active) out_count[orig[i]] = cnt; return; }
+        if (active) out_count[i] = MODE == 1 ? min(cnt, cap) : cnt;
         unsigned m = active ? cnt : 0u;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
         if ((threadIdx.x & 31) == 0) {
             atomicMax(&ctrl->max_count, m);
-            if (FILL && m > cap) atomicExch(&ctrl->overflow, 1u);
+            if (MODE == 1 && m > cap) atomicExch(&ctrl->overflow, 1u);
         }
     }
 };
 
-// build_neighbor_list, .cpp:441-551 (acceptance dist2 <= (rcut+shell)^2, :536), on the device layout.
-template <bool FILL>
+// build_neighbor_list, .cpp:441-551 (acceptance dist2 <= (rcut+shell)^2, :536), on the device layout;
+// MODE 2 is the parity probe of include/ljgpu.h (ljgpu_get_neighbor_counts).
+template <int MODE>
 __global__ void __launch_bounds__(kCellWarps * 32)
-build_list_kernel(LJConst c, CellGrid g, const double4* __restrict__ pos, unsigned cap,
-                  uint32_t* __restrict__ nl, uint32_t* __restrict__ nl_count, StepCtrl* __restrict__ ctrl) {
+list_kernel(LJConst c, CellGrid g, const double4* __restrict__ pos, double cut2, int inclusive, unsigned cap,
+            uint32_t* __restrict__ nl, uint32_t* __restrict__ out_count, const uint32_t* __restrict__ orig,
+            StepCtrl* __restrict__ ctrl) {
     __shared__ double4 tile[kCellWarps][32];
-    ListBuildOp<FILL> op{c.list_cut2, cap, nl, nl_count, ctrl, 0};
-    cell_traverse(g, pos, tile, op);
+    ListOp<MODE> op{cut2, inclusive, cap, nl, out_count, orig, ctrl, 0};
+    cell_traverse(c, g, pos, tile, op);
 }
 
 struct CellForceOp {
@@ -302,14 +309,14 @@ force_cell_kernel(LJConst c, CellGrid g, const StepCtrl* __restrict__ ctrl, cons
     __shared__ double red[32];
     if (ctrl->stop) return;
     CellForceOp op{c.rc2, c.sigma2, c.ecut, c.prefctr, fx, fy, fz, 0, 0, 0, 0, 0.0, 0};
-    cell_traverse(g, pos, tile, op);
+    cell_traverse(c, g, pos, tile, op);
     const double e = block_sum(op.etot, red);
     if (threadIdx.x == 0) partial_epot[blockIdx.x] = e;
 }
 
 // K7b Verlet-list force kernel: one thread per atom slot, its list entries gathered as 32-byte
 // double4 sectors (served by L1/L2: neighbours of consecutive slots overlap almost completely).
-// calculate_forces, .cpp:286-319, minus the minimum image (ghost slots carry the shifted images).
+// calculate_forces, .cpp:286-319.
 __global__ void __launch_bounds__(kBlock)
 force_verlet_kernel(LJConst c, const StepCtrl* __restrict__ ctrl, const double4* __restrict__ pos,
                     const uint32_t* __restrict__ nl, const uint32_t* __restrict__ nl_count, unsigned cap,
@@ -319,6 +326,7 @@ force_verlet_kernel(LJConst c, const StepCtrl* __restrict__ ctrl, const double4*
     if (ctrl->stop) return;
     const unsigned i = blockIdx.x * kBlock + threadIdx.x;
     const bool active = i < c.n;
+    const int far2_hi = __double2hiint(c.far2);
     double ax = 0.0, ay = 0.0, az = 0.0, e = 0.0;
     unsigned nacc = 0;
     if (active) {
@@ -326,20 +334,25 @@ force_verlet_kernel(LJConst c, const StepCtrl* __restrict__ ctrl, const double4*
         const unsigned cnt = nl_count[i];
         const uint32_t* __restrict__ row = nl + nl_index(i, 0, cap);
         unsigned k = 0;
+#define LJ_ACC(P)                                                                          \
+        {                                                                                  \
+            double dx = pi.x - P.x, dy = pi.y - P.y, dz = pi.z - P.z;                      \
+            double d2 = fma(dz, dz, fma(dy, dy, dx * dx));                                 \
+            if (maybe_wrapped(d2, far2_hi)) {                                              \
+                dx = min_image(dx, c.L, c.halfL); dy = min_image(dy, c.L, c.halfL);        \
+                dz = min_image(dz, c.L, c.halfL);                                          \
+                d2 = fma(dz, dz, fma(dy, dy, dx * dx));                                    \
+            }                                                                              \
+            if (d2 < c.rc2) {                                                              \
+                const double fr = lj_pair(d2, c.sigma2, e);                                \
+                ax = fma(fr, dx, ax); ay = fma(fr, dy, ay); az = fma(fr, dz, az);          \
+                ++nacc;                                                                    \
+            }                                                                              \
+        }
         for (; k + 4 <= cnt; k += 4) {
             const uint32_t j0 = row[(size_t)(k + 0) * 32], j1 = row[(size_t)(k + 1) * 32];
             const uint32_t j2 = row[(size_t)(k + 2) * 32], j3 = row[(size_t)(k + 3) * 32];
             const double4 p0 = pos[j0], p1 = pos[j1], p2 = pos[j2], p3 = pos[j3];
-#define LJ_ACC(P)                                                                          \
-            {                                                                              \
-                const double dx = pi.x - P.x, dy = pi.y - P.y, dz = pi.z - P.z;            \
-                const double d2 = fma(dz, dz, fma(dy, dy, dx * dx));                       \
-                if (d2 < c.rc2) {                                                          \
-                    const double fr = lj_pair(d2, c.sigma2, e);                            \
-                    ax = fma(fr, dx, ax); ay = fma(fr, dy, ay); az = fma(fr, dz, az);      \
-                    ++nacc;                                                                \
-                }                                                                          \
-            }
             LJ_ACC(p0) LJ_ACC(p1) LJ_ACC(p2) LJ_ACC(p3)
         }
         for (; k < cnt; ++k) {
@@ -355,13 +368,12 @@ force_verlet_kernel(LJConst c, const StepCtrl* __restrict__ ctrl, const double4*
 }
 
 // ---------------------------------------------------------------------------------------------
-// K3  kick2 + kinetic sums (+ wrap on the all-pairs path)
-//     .cpp:336-362; WRAP adds apply_boundary_conditions .cpp:419-435 (a per-atom operation that the
-//     reference runs between the force pass and kick2; it touches positions only).
+// K3  kick2 + kinetic sums, .cpp:336-362.  Also forms sum |v' + a f|^2, which is exactly the kinetic sum
+//     the next step's kick1 will produce (same forces, same operations), so the thermostat factor of
+//     the next step is known without another pass.
 // ---------------------------------------------------------------------------------------------
-template <bool WRAP>
 __global__ void __launch_bounds__(kBlock)
-kick2_kernel(LJConst c, double a, const StepCtrl* __restrict__ ctrl, double4* __restrict__ pos,
+kick2_kernel(LJConst c, double a, const StepCtrl* __restrict__ ctrl,
              double* __restrict__ vx, double* __restrict__ vy, double* __restrict__ vz,
              const double* __restrict__ fx, const double* __restrict__ fy, const double* __restrict__ fz,
              double* __restrict__ partial_ekin, double* __restrict__ partial_pred) {
@@ -375,13 +387,6 @@ kick2_kernel(LJConst c, double a, const StepCtrl* __restrict__ ctrl, double4* __
         vx[i] = ux; vy[i] = uy; vz[i] = uz;
         s1 = xnorm2(ux, uy, uz);
         s2 = xnorm2(xadd(ux, gx), xadd(uy, gy), xadd(uz, gz));
-        if (WRAP) {
-            double4 p = pos[i];
-            p.x = wrap_coord(p.x, c.L, c.invL);
-            p.y = wrap_coord(p.y, c.L, c.invL);
-            p.z = wrap_coord(p.z, c.L, c.invL);
-            pos[i] = p;
-        }
     }
     s1 = block_sum(s1, red);
     s2 = block_sum(s2, red);
@@ -453,7 +458,7 @@ wrap_key_kernel(LJConst c, const double4* __restrict__ pos, double4* __restrict_
 
 __global__ void __launch_bounds__(kBlock)
 permute_kernel(unsigned n, const uint32_t* __restrict__ perm, const double4* __restrict__ pos_tmp,
-               double4* __restrict__ pos, double* __restrict__ x0, double* __restrict__ y0, double* __restrict__ z0,
+               double4* __restrict__ pos,
                const double* __restrict__ vxi, const double* __restrict__ vyi, const double* __restrict__ vzi,
                const double* __restrict__ fxi, const double* __restrict__ fyi, const double* __restrict__ fzi,
                const uint32_t* __restrict__ origi,
@@ -463,8 +468,7 @@ permute_kernel(unsigned n, const uint32_t* __restrict__ perm, const double4* __r
     const unsigned i = blockIdx.x * kBlock + threadIdx.x;
     if (i >= n) return;
     const unsigned s = perm[i];
-    const double4 p = pos_tmp[s];
-    pos[i] = p; x0[i] = p.x; y0[i] = p.y; z0[i] = p.z;
+    pos[i] = pos_tmp[s];
     vxo[i] = vxi[s]; vyo[i] = vyi[s]; vzo[i] = vzi[s];
     fxo[i] = fxi[s]; fyo[i] = fyi[s]; fzo[i] = fzi[s];
     origo[i] = origi[s];
@@ -486,55 +490,9 @@ cell_count_kernel(unsigned ncell, const uint32_t* __restrict__ cstart, const uin
     if (k < ncell) ccount[k] = cend[k] - cstart[k];
 }
 
-// Extended grid (one ghost layer per face).  Pass 1: number of ghost slots every extended cell needs.
-__device__ __forceinline__ void ext_decode(unsigned e, unsigned nc, unsigned& src, unsigned& code, bool& ghost) {
-    const unsigned E = nc + 2;
-    const unsigned ex = e % E, ey = (e / E) % E, ez = e / (E * E);
-    const unsigned ix = ex == 0 ? nc - 1 : (ex == E - 1 ? 0 : ex - 1);
-    const unsigned iy = ey == 0 ? nc - 1 : (ey == E - 1 ? 0 : ey - 1);
-    const unsigned iz = ez == 0 ? nc - 1 : (ez == E - 1 ? 0 : ez - 1);
-    const unsigned sx = ex == 0 ? 0u : (ex == E - 1 ? 2u : 1u);      // 0: image at -L, 1: none, 2: +L
-    const unsigned sy = ey == 0 ? 0u : (ey == E - 1 ? 2u : 1u);
-    const unsigned sz = ez == 0 ? 0u : (ez == E - 1 ? 2u : 1u);
-    src = iz * nc * nc + iy * nc + ix;
-    code = sx + 3u * sy + 9u * sz;
-    ghost = code != 13u;
-}
-
-__global__ void __launch_bounds__(kBlock)
-ext_count_kernel(unsigned nc, const uint32_t* __restrict__ ccount, uint32_t* __restrict__ goff) {
-    const unsigned E = nc + 2;
-    const unsigned e = blockIdx.x * kBlock + threadIdx.x;
-    if (e >= E * E * E) return;
-    unsigned src, code; bool ghost;
-    ext_decode(e, nc, src, code, ghost);
-    goff[e] = ghost ? ccount[src] : 0u;
-}
-
-// Pass 2 (after the exclusive scan of goff): extended cell table + ghost source list.
-__global__ void __launch_bounds__(kBlock)
-ext_fill_kernel(unsigned nc, unsigned nreal, const uint32_t* __restrict__ cstart, const uint32_t* __restrict__ ccount,
-                const uint32_t* __restrict__ goff, uint32_t* __restrict__ estart, uint32_t* __restrict__ ecount,
-                uint32_t* __restrict__ gsrc, unsigned gcap) {
-    const unsigned E = nc + 2;
-    const unsigned e = blockIdx.x * kBlock + threadIdx.x;
-    if (e >= E * E * E) return;
-    unsigned src, code; bool ghost;
-    ext_decode(e, nc, src, code, ghost);
-    const unsigned cnt = ccount[src];
-    ecount[e] = cnt;
-    if (!ghost) { estart[e] = cstart[src]; return; }
-    const unsigned off = goff[e];
-    estart[e] = nreal + off;
-    const unsigned s0 = cstart[src];
-    for (unsigned k = 0; k < cnt; ++k)
-        if (off + k < gcap) gsrc[off + k] = (s0 + k) | (code << kGhostShiftBits);
-}
-
 // ---------------------------------------------------------------------------------------------
 // Query kernels (original atom order out).
 // ---------------------------------------------------------------------------------------------
-template <bool WRAP>
 __global__ void __launch_bounds__(kBlock)
 export_positions_kernel(LJConst c, const double4* __restrict__ pos, const uint32_t* __restrict__ orig,
                         double* __restrict__ ox, double* __restrict__ oy, double* __restrict__ oz) {
@@ -542,9 +500,9 @@ export_positions_kernel(LJConst c, const double4* __restrict__ pos, const uint32
     if (i >= c.n) return;
     const double4 p = pos[i];
     const unsigned o = orig[i];
-    ox[o] = WRAP ? wrap_coord(p.x, c.L, c.invL) : p.x;
-    oy[o] = WRAP ? wrap_coord(p.y, c.L, c.invL) : p.y;
-    oz[o] = WRAP ? wrap_coord(p.z, c.L, c.invL) : p.z;
+    ox[o] = wrap_coord(p.x, c.L, c.invL);
+    oy[o] = wrap_coord(p.y, c.L, c.invL);
+    oz[o] = wrap_coord(p.z, c.L, c.invL);
 }
 
 __global__ void __launch_bounds__(kBlock)
@@ -588,33 +546,36 @@ speed_histogram_kernel(unsigned n, const double* __restrict__ vx, const double* 
 }
 
 // Cell-id probe on the published (wrapped) positions, .cpp:447-476, original order out.
-template <bool WRAP>
 __global__ void __launch_bounds__(kBlock)
 cell_id_probe_kernel(LJConst c, const double4* __restrict__ pos, const uint32_t* __restrict__ orig, uint32_t* __restrict__ out) {
     const unsigned i = blockIdx.x * kBlock + threadIdx.x;
     if (i >= c.n) return;
-    double4 p = pos[i];
-    if (WRAP) { p.x = wrap_coord(p.x, c.L, c.invL); p.y = wrap_coord(p.y, c.L, c.invL); p.z = wrap_coord(p.z, c.L, c.invL); }
-    const unsigned ix = cell_coord(p.x, c.cell_edge, c.nc);
-    const unsigned iy = cell_coord(p.y, c.cell_edge, c.nc);
-    const unsigned iz = cell_coord(p.z, c.cell_edge, c.nc);
+    const double4 p = pos[i];
+    const unsigned ix = cell_coord(wrap_coord(p.x, c.L, c.invL), c.cell_edge, c.nc);
+    const unsigned iy = cell_coord(wrap_coord(p.y, c.L, c.invL), c.cell_edge, c.nc);
+    const unsigned iz = cell_coord(wrap_coord(p.z, c.L, c.invL), c.cell_edge, c.nc);
     out[orig[i]] = iz * c.nc * c.nc + iy * c.nc + ix;
 }
 
-// Neighbour-count probe, bit-exact with the reference's comparisons: min-image distance formed as
-// .cpp:519-534 and accepted by dist2 <= cut2 (inclusive, :536) or d2 < cut2 (strict, :304-305).
-// Variant A: all pairs through shared memory (any layout).
+// Neighbour-count probe on the all-pairs layout (no cell table): every j through shared memory,
+// published (wrapped) positions, the reference's comparisons (.cpp:519-536 / :291-305).
 __global__ void __launch_bounds__(kBlock)
 count_allpairs_kernel(LJConst c, const double4* __restrict__ pos, const uint32_t* __restrict__ orig,
                       double cut2, int inclusive, uint32_t* __restrict__ out) {
     __shared__ double sx[kApTile], sy[kApTile], sz[kApTile];
     const unsigned i = blockIdx.x * kBlock + threadIdx.x;
     const bool active = i < c.n;
-    const double4 pi = active ? pos[i] : make_double4(0, 0, 0, 0);
+    double4 pi = active ? pos[i] : make_double4(0, 0, 0, 0);
+    pi.x = wrap_coord(pi.x, c.L, c.invL); pi.y = wrap_coord(pi.y, c.L, c.invL); pi.z = wrap_coord(pi.z, c.L, c.invL);
     unsigned cnt = 0;
     for (unsigned jb = 0; jb < c.n; jb += kApTile) {
         __syncthreads();
-        if (jb + threadIdx.x < c.n) { const double4 q = pos[jb + threadIdx.x]; sx[threadIdx.x] = q.x; sy[threadIdx.x] = q.y; sz[threadIdx.x] = q.z; }
+        if (jb + threadIdx.x < c.n) {
+            const double4 q = pos[jb + threadIdx.x];
+            sx[threadIdx.x] = wrap_coord(q.x, c.L, c.invL);
+            sy[threadIdx.x] = wrap_coord(q.y, c.L, c.invL);
+            sz[threadIdx.x] = wrap_coord(q.z, c.L, c.invL);
+        }
         __syncthreads();
         const unsigned m = min((unsigned)kApTile, c.n - jb);
         if (active)
@@ -628,43 +589,6 @@ count_allpairs_kernel(LJConst c, const double4* __restrict__ pos, const uint32_t
             }
     }
     if (active) out[orig[i]] = cnt;
-}
-
-// Variant B: over the inner cell table right after a re-binning (positions wrapped and cell-sorted),
-// 27-cell periodic stencil exactly as .cpp:488-516, one warp per home cell.
-__global__ void __launch_bounds__(kCellWarps * 32)
-count_cells_kernel(LJConst c, const uint32_t* __restrict__ cstart, const uint32_t* __restrict__ ccount,
-                   const double4* __restrict__ pos, const uint32_t* __restrict__ orig,
-                   double cut2, int inclusive, uint32_t* __restrict__ out) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const unsigned cell = blockIdx.x * kCellWarps + w;
-    const unsigned nc = c.nc;
-    if (cell >= nc * nc * nc) return;
-    const unsigned ix = cell % nc, iy = (cell / nc) % nc, iz = cell / (nc * nc);
-    const unsigned xs[3] = { ix == 0 ? nc - 1 : ix - 1, ix, ix == nc - 1 ? 0 : ix + 1 };
-    const unsigned ys[3] = { iy == 0 ? nc - 1 : iy - 1, iy, iy == nc - 1 ? 0 : iy + 1 };
-    const unsigned zs[3] = { iz == 0 ? nc - 1 : iz - 1, iz, iz == nc - 1 ? 0 : iz + 1 };
-    const unsigned hs = cstart[cell], hn = ccount[cell];
-    for (unsigned hb = 0; hb < hn; hb += 32) {
-        const unsigned i = hs + hb + lane;
-        const bool active = hb + lane < hn;
-        const double4 pi = active ? pos[i] : make_double4(0, 0, 0, 0);
-        unsigned cnt = 0;
-        for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) for (int d = 0; d < 3; ++d) {
-            const unsigned cid = zs[d] * nc * nc + ys[b] * nc + xs[a];
-            const unsigned js = cstart[cid], jn = ccount[cid];
-            for (unsigned jj = 0; jj < jn; ++jj) {
-                const double4 pj = pos[js + jj];
-                const double dx = min_image(xsub(pi.x, pj.x), c.L, c.halfL);
-                const double dy = min_image(xsub(pi.y, pj.y), c.L, c.halfL);
-                const double dz = min_image(xsub(pi.z, pj.z), c.L, c.halfL);
-                const double d2 = xnorm2(dx, dy, dz);
-                const bool in = inclusive ? (d2 <= cut2) : (d2 < cut2);
-                if (active && in && (js + jj) != i) ++cnt;
-            }
-        }
-        if (active) out[orig[i]] = cnt;
-    }
 }
 
 } // namespace ljgpu

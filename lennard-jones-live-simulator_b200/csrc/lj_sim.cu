@@ -49,11 +49,11 @@ struct ljgpu_sim {
     int device = 0;
     cudaStream_t st = nullptr;
     LJConst c{};
-    unsigned n = 0, nc = 0, ncell = 0, necell = 0;
+    unsigned n = 0, nc = 0, ncell = 0;
 
     // state, device order (cell-sorted on the list paths, caller order on the all-pairs path)
-    double4* pos = nullptr; double4* pos_tmp = nullptr; size_t pos_cap = 0;
-    double* x0[3] = {nullptr, nullptr, nullptr};
+    double4* pos = nullptr; double4* pos_tmp = nullptr;
+    double* dij[3] = {nullptr, nullptr, nullptr};      // accumulated displacement since the last binning (.h:94)
     double* v[3] = {nullptr, nullptr, nullptr};
     double* f[3] = {nullptr, nullptr, nullptr};
     double* v_alt[3] = {nullptr, nullptr, nullptr};
@@ -63,9 +63,6 @@ struct ljgpu_sim {
     // binning
     uint32_t *keys = nullptr, *vals = nullptr;
     uint32_t *cstart = nullptr, *cend = nullptr, *ccount = nullptr;
-    uint32_t *estart = nullptr, *ecount = nullptr, *goff = nullptr;
-    uint32_t* gsrc = nullptr; size_t gcap = 0; unsigned nghost = 0;
-    uint32_t* d_total = nullptr;
     SortScratch scr;
 
     // Verlet list
@@ -153,9 +150,9 @@ ljgpu_sim::~ljgpu_sim() {
     cudaSetDevice(device);
     if (st) cudaStreamSynchronize(st);
     dfree(pos); dfree(pos_tmp);
-    for (int k = 0; k < 3; ++k) { dfree(x0[k]); dfree(v[k]); dfree(f[k]); dfree(v_alt[k]); dfree(f_alt[k]); dfree(apf[k]); }
+    for (int k = 0; k < 3; ++k) { dfree(dij[k]); dfree(v[k]); dfree(f[k]); dfree(v_alt[k]); dfree(f_alt[k]); dfree(apf[k]); }
     dfree(orig); dfree(orig_alt); dfree(keys); dfree(vals);
-    dfree(cstart); dfree(cend); dfree(ccount); dfree(estart); dfree(ecount); dfree(goff); dfree(gsrc); dfree(d_total);
+    dfree(cstart); dfree(cend); dfree(ccount);
     dfree(nl); dfree(nl_count);
     dfree(partial_epot); dfree(partial_ekin); dfree(partial_pred);
     dfree(ctrl); dfree(hist); dfree(out3); dfree(out_u32); dfree(hist_counts);
@@ -170,6 +167,7 @@ void ljgpu_sim::setup_constants() {
     // Every expression below is the host-side scalar set-up of the cited reference lines.
     const double L = p.cell_length;
     c.L = L; c.invL = 1.0 / L; c.halfL = L * 0.5;                       // .cpp:424-426, :295
+    c.far2 = c.halfL * c.halfL * (1.0 - 1e-9);
     c.rc2 = p.rcut * p.rcut;                                            // .cpp:262
     c.sigma2 = p.sigma * p.sigma;                                       // .cpp:264
     const double sr2 = c.sigma2 / c.rc2, sr6 = sr2 * sr2 * sr2, sr12 = sr6 * sr6;
@@ -187,21 +185,14 @@ void ljgpu_sim::setup_constants() {
     c.cell_edge = L / (double)ncells;                                   // .cpp:455-457
     c.n = (unsigned)p.nr_particles;
     c.dt_over_tau = 0.0;
-    nc = ncells; ncell = nc * nc * nc; necell = (nc + 2) * (nc + 2) * (nc + 2);
+    nc = ncells; ncell = nc * nc * nc;
 }
 
 void ljgpu_sim::allocate() {
     const size_t N = n;
     nb_atoms = cdiv(N, kBlock);
-    // ghost estimate: ghost-layer cells over inner cells, 50 % slack
-    size_t gest = 0;
-    if (list_mode()) {
-        const double ratio = (double)(necell - ncell) / (double)ncell;
-        gest = (size_t)(ratio * (double)N * 1.5) + 4096;
-    }
-    pos_cap = N + gest; gcap = gest;
-    CK(cudaMalloc(&pos, pos_cap * sizeof(double4)));
-    CK(cudaMemset(pos, 0, pos_cap * sizeof(double4)));
+    CK(cudaMalloc(&pos, N * sizeof(double4)));
+    CK(cudaMemset(pos, 0, N * sizeof(double4)));
     for (int k = 0; k < 3; ++k) {
         CK(cudaMalloc(&v[k], N * 8)); CK(cudaMalloc(&f[k], N * 8));
         CK(cudaMemset(f[k], 0, N * 8));
@@ -219,14 +210,11 @@ void ljgpu_sim::allocate() {
     if (list_mode()) {
         CK(cudaMalloc(&pos_tmp, N * sizeof(double4)));
         for (int k = 0; k < 3; ++k) {
-            CK(cudaMalloc(&x0[k], N * 8)); CK(cudaMalloc(&v_alt[k], N * 8)); CK(cudaMalloc(&f_alt[k], N * 8));
+            CK(cudaMalloc(&dij[k], N * 8)); CK(cudaMalloc(&v_alt[k], N * 8)); CK(cudaMalloc(&f_alt[k], N * 8));
         }
         CK(cudaMalloc(&orig_alt, N * 4));
         CK(cudaMalloc(&keys, N * 4)); CK(cudaMalloc(&vals, N * 4));
         CK(cudaMalloc(&cstart, (size_t)ncell * 4)); CK(cudaMalloc(&cend, (size_t)ncell * 4)); CK(cudaMalloc(&ccount, (size_t)ncell * 4));
-        CK(cudaMalloc(&estart, (size_t)necell * 4)); CK(cudaMalloc(&ecount, (size_t)necell * 4)); CK(cudaMalloc(&goff, (size_t)necell * 4));
-        CK(cudaMalloc(&gsrc, std::max<size_t>(gcap, 1) * 4));
-        CK(cudaMalloc(&d_total, 4));
         CK(cudaMalloc(&nl_count, N * 4));
         nb_force = mode == LJGPU_KERNEL_VERLET ? nb_atoms : cdiv(ncell, kCellWarps);
     } else {
@@ -259,7 +247,7 @@ void ljgpu_sim::upload_state(const double* x, const double* y, const double* z,
 }
 
 // Re-binning: wrap (.cpp:419-435), cell keys (.cpp:467-478), stable radix sort, permutation of the
-// whole state, cell table, ghost layer, and on the Verlet path the list itself (.cpp:480-550).
+// whole state, cell table, dij = 0 (.cpp:484-486), and on the Verlet path the list itself (.cpp:480-550).
 void ljgpu_sim::rebuild() {
     stage_begin();
     CK(cudaMemsetAsync(&ctrl->stop, 0, sizeof(unsigned), st));
@@ -269,12 +257,13 @@ void ljgpu_sim::rebuild() {
     check_launch("wrap_key");
     int bits = 1; while ((1ull << bits) < (unsigned long long)ncell) ++bits;
     launches += radix_sort_pairs(keys, vals, n, bits, scr, st);
-    permute_kernel<<<nb_atoms, kBlock, 0, st>>>(n, vals, pos_tmp, pos, x0[0], x0[1], x0[2],
+    permute_kernel<<<nb_atoms, kBlock, 0, st>>>(n, vals, pos_tmp, pos,
                                                 v[0], v[1], v[2], f[0], f[1], f[2], orig,
                                                 v_alt[0], v_alt[1], v_alt[2], f_alt[0], f_alt[1], f_alt[2], orig_alt);
     check_launch("permute");
     for (int k = 0; k < 3; ++k) { std::swap(v[k], v_alt[k]); std::swap(f[k], f_alt[k]); }
     std::swap(orig, orig_alt);
+    for (int k = 0; k < 3; ++k) CK(cudaMemsetAsync(dij[k], 0, (size_t)n * 8, st));
 
     CK(cudaMemsetAsync(cstart, 0, (size_t)ncell * 4, st));
     CK(cudaMemsetAsync(cend, 0, (size_t)ncell * 4, st));
@@ -283,32 +272,6 @@ void ljgpu_sim::rebuild() {
     cell_count_kernel<<<cdiv(ncell, kBlock), kBlock, 0, st>>>(ncell, cstart, cend, ccount);
     check_launch("cell_count");
 
-    ext_count_kernel<<<cdiv(necell, kBlock), kBlock, 0, st>>>(nc, ccount, goff);
-    check_launch("ext_count");
-    launches += exclusive_scan_u32(goff, necell, d_total, scr, st);
-    uint32_t G = 0;
-    CK(cudaMemcpyAsync(&G, d_total, 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    if (G > gcap || (size_t)n + G > pos_cap) {
-        const size_t ng = (size_t)G + G / 4 + 4096;
-        dfree(gsrc);
-        CK(cudaMalloc(&gsrc, ng * 4));
-        gcap = ng;
-        double4* np = nullptr;
-        CK(cudaMalloc(&np, ((size_t)n + ng) * sizeof(double4)));
-        CK(cudaMemcpy(np, pos, (size_t)n * sizeof(double4), cudaMemcpyDeviceToDevice));
-        dfree(pos);
-        pos = np; pos_cap = (size_t)n + ng;
-    }
-    if ((size_t)n + G >= (1ull << kGhostShiftBits))
-        throw LjError(LJGPU_EINVAL, "too many atoms + ghosts for the 27-bit ghost source index");
-    nghost = G;
-    ext_fill_kernel<<<cdiv(necell, kBlock), kBlock, 0, st>>>(nc, n, cstart, ccount, goff, estart, ecount, gsrc, (unsigned)gcap);
-    check_launch("ext_fill");
-    if (nghost) {
-        ghost_update_kernel<<<cdiv(nghost, kBlock), kBlock, 0, st>>>(nghost, n, c.L, ctrl, pos, gsrc);
-        check_launch("ghost_update");
-    }
     if (mode == LJGPU_KERNEL_VERLET) build_list();
     stage_end(ST_REBUILD);
     ++rebuilds;
@@ -318,15 +281,15 @@ void ljgpu_sim::rebuild() {
 }
 
 void ljgpu_sim::build_list() {
-    CellGrid g{cstart, ccount, estart, ecount, nc};
+    CellGrid g{cstart, ccount, nc};
     const unsigned nbc = cdiv(ncell, kCellWarps);
     const unsigned ntiles = cdiv(n, 32);
     for (int attempt = 0; attempt < 4; ++attempt) {
         CK(cudaMemsetAsync(&ctrl->max_count, 0, sizeof(unsigned), st));
         CK(cudaMemsetAsync(&ctrl->overflow, 0, sizeof(unsigned), st));
         if (cap == 0) {
-            build_list_kernel<false><<<nbc, kCellWarps * 32, 0, st>>>(c, g, pos, 0, nullptr, nl_count, ctrl);
-            check_launch("build_list<count>");
+            list_kernel<0><<<nbc, kCellWarps * 32, 0, st>>>(c, g, pos, c.list_cut2, 1, 0, nullptr, nl_count, orig, ctrl);
+            check_launch("list_kernel<count>");
             fetch_ctrl();
             cap = ((h_ctrl->max_count + 8 + 3) / 4) * 4;
         }
@@ -336,8 +299,8 @@ void ljgpu_sim::build_list() {
             CK(cudaMalloc(&nl, need * 4));
             nl_alloc = need;
         }
-        build_list_kernel<true><<<nbc, kCellWarps * 32, 0, st>>>(c, g, pos, cap, nl, nl_count, ctrl);
-        check_launch("build_list<fill>");
+        list_kernel<1><<<nbc, kCellWarps * 32, 0, st>>>(c, g, pos, c.list_cut2, 1, cap, nl, nl_count, orig, ctrl);
+        check_launch("list_kernel<fill>");
         fetch_ctrl();
         if (!h_ctrl->overflow) return;
         cap = ((h_ctrl->max_count + 8 + 3) / 4) * 4;       // grow and refill
@@ -354,7 +317,7 @@ void ljgpu_sim::launch_force(bool timed) {
         allpairs_reduce_kernel<<<nb_atoms, kBlock, 0, st>>>(c, ctrl, nsplit, apf[0], apf[1], apf[2], f[0], f[1], f[2]);
         check_launch("allpairs_reduce");
     } else if (mode == LJGPU_KERNEL_CELL) {
-        CellGrid g{cstart, ccount, estart, ecount, nc};
+        CellGrid g{cstart, ccount, nc};
         force_cell_kernel<<<nb_force, kCellWarps * 32, 0, st>>>(c, g, ctrl, pos, f[0], f[1], f[2], partial_epot);
         check_launch("force_cell");
     } else {
@@ -389,25 +352,16 @@ void ljgpu_sim::enqueue_step(unsigned step, double dt) {
     c.dt_over_tau = dt / p.tau;                                          // .cpp:375
     stage_begin();
     if (list_mode())
-        kick_drift_kernel<true><<<nb_atoms, kBlock, 0, st>>>(c, dt, a, ctrl, pos, x0[0], x0[1], x0[2],
+        kick_drift_kernel<true><<<nb_atoms, kBlock, 0, st>>>(c, dt, a, ctrl, pos, dij[0], dij[1], dij[2],
                                                              v[0], v[1], v[2], f[0], f[1], f[2]);
     else
         kick_drift_kernel<false><<<nb_atoms, kBlock, 0, st>>>(c, dt, a, ctrl, pos, nullptr, nullptr, nullptr,
                                                               v[0], v[1], v[2], f[0], f[1], f[2]);
     check_launch("kick_drift");
     stage_end(ST_KICK_DRIFT);
-    if (list_mode() && nghost) {
-        stage_begin();
-        ghost_update_kernel<<<cdiv(nghost, kBlock), kBlock, 0, st>>>(nghost, n, c.L, ctrl, pos, gsrc);
-        check_launch("ghost_update");
-        stage_end(ST_GHOST);
-    }
     launch_force(true);
     stage_begin();
-    if (list_mode())
-        kick2_kernel<false><<<nb_atoms, kBlock, 0, st>>>(c, a, ctrl, pos, v[0], v[1], v[2], f[0], f[1], f[2], partial_ekin, partial_pred);
-    else
-        kick2_kernel<true><<<nb_atoms, kBlock, 0, st>>>(c, a, ctrl, pos, v[0], v[1], v[2], f[0], f[1], f[2], partial_ekin, partial_pred);
+    kick2_kernel<<<nb_atoms, kBlock, 0, st>>>(c, a, ctrl, v[0], v[1], v[2], f[0], f[1], f[2], partial_ekin, partial_pred);
     check_launch("kick2");
     step_finalize_kernel<<<1, kFinalizeThreads, 0, st>>>(c, ctrl, hist, step, partial_epot, nb_force,
                                                          partial_ekin, partial_pred, nb_atoms);
@@ -441,8 +395,7 @@ void ljgpu_sim::run_steps(unsigned first, unsigned nsteps, double dt) {
 void ljgpu_sim::export3(int what, double* a, double* b, double* cc) {
     const size_t N = n;
     if (what == 0) {
-        if (list_mode()) export_positions_kernel<true><<<nb_atoms, kBlock, 0, st>>>(c, pos, orig, out3, out3 + N, out3 + 2 * N);
-        else export_positions_kernel<false><<<nb_atoms, kBlock, 0, st>>>(c, pos, orig, out3, out3 + N, out3 + 2 * N);
+        export_positions_kernel<<<nb_atoms, kBlock, 0, st>>>(c, pos, orig, out3, out3 + N, out3 + 2 * N);
     } else {
         double** src = what == 1 ? v : f;
         export_soa_kernel<<<nb_atoms, kBlock, 0, st>>>(n, src[0], src[1], src[2], orig, out3, out3 + N, out3 + 2 * N);
@@ -634,8 +587,7 @@ int ljgpu_get_speed_histogram(ljgpu_sim* s, uint32_t nbins, double vmax, uint64_
 int ljgpu_get_cell_ids(ljgpu_sim* s, uint32_t* cell_of_atom, uint32_t dims[3]) {
     if (!cell_of_atom) return fail(LJGPU_EINVAL, "null argument");
     return with_sim(s, [&] {
-        if (s->list_mode()) cell_id_probe_kernel<true><<<s->nb_atoms, kBlock, 0, s->st>>>(s->c, s->pos, s->orig, s->out_u32);
-        else cell_id_probe_kernel<false><<<s->nb_atoms, kBlock, 0, s->st>>>(s->c, s->pos, s->orig, s->out_u32);
+        cell_id_probe_kernel<<<s->nb_atoms, kBlock, 0, s->st>>>(s->c, s->pos, s->orig, s->out_u32);
         s->check_launch("cell_id_probe");
         CK(cudaMemcpyAsync(cell_of_atom, s->out_u32, (size_t)s->n * 4, cudaMemcpyDeviceToHost, s->st));
         s->sync();
@@ -651,8 +603,9 @@ int ljgpu_get_neighbor_counts(ljgpu_sim* s, double cutoff, int inclusive, uint32
         const double cut2 = cutoff * cutoff;
         if (s->list_mode()) {
             if (s->dirty_since_rebuild) s->rebuild();       // positions wrapped + cell-sorted again
-            count_cells_kernel<<<cdiv(s->ncell, kCellWarps), kCellWarps * 32, 0, s->st>>>(
-                s->c, s->cstart, s->ccount, s->pos, s->orig, cut2, inclusive, s->out_u32);
+            CellGrid g{s->cstart, s->ccount, s->nc};
+            list_kernel<2><<<cdiv(s->ncell, kCellWarps), kCellWarps * 32, 0, s->st>>>(
+                s->c, g, s->pos, cut2, inclusive, 0, nullptr, s->out_u32, s->orig, s->ctrl);
         } else {
             count_allpairs_kernel<<<s->nb_atoms, kBlock, 0, s->st>>>(s->c, s->pos, s->orig, cut2, inclusive, s->out_u32);
         }
@@ -716,7 +669,7 @@ int ljgpu_get_layout(ljgpu_sim* s, int32_t* force_kernel, uint32_t* cells_per_ax
         if (force_kernel) *force_kernel = s->mode;
         if (cells_per_axis) *cells_per_axis = s->nc;
         if (list_capacity) *list_capacity = s->cap;
-        if (n_ghosts) *n_ghosts = s->nghost;
+        if (n_ghosts) *n_ghosts = 0;      // no ghost atoms in this layout: periodic images are resolved per pair
     });
 }
 

@@ -426,6 +426,59 @@ void ljo_incutoff_counts(const ljo_sim* s, unsigned* counts) {
     }
 }
 
+/* Per-atom sum over accepted list entries of |f_ij| (same pair expressions as forces()): the
+ * scale against which a rounding-level force difference has to be judged when the net force
+ * nearly cancels (perfect start lattice). Not a reference quantity - a test yardstick. */
+void ljo_force_abs_sums(const ljo_sim* s, double* out) {
+    const double L = s->L, rcutsq = s->p.rcut * s->p.rcut, sigmasq = s->p.sigma * s->p.sigma;
+    const double prefctr = 24.0 * s->p.epsilon;
+    for (int i = 0; i < s->n; i++) {
+        double acc = 0.0;
+        for (uint64_t q = s->nl_off[i]; q < s->nl_off[i + 1]; q++) {
+            const unsigned j = s->nl[q];
+            const double ddx = min_image(s->x[i] - s->x[j], L);
+            const double ddy = min_image(s->y[i] - s->y[j], L);
+            const double ddz = min_image(s->z[i] - s->z[j], L);
+            const double d2 = ddx * ddx + ddy * ddy + ddz * ddz;
+            if (d2 >= rcutsq) continue;
+            const double invd2 = 1.0 / d2;
+            const double s2 = sigmasq * invd2;
+            const double s6 = s2 * s2 * s2;
+            const double s12 = s6 * s6;
+            const double fr = (2.0 * s12 - s6) * invd2;
+            acc += fabs(fr) * sqrt(d2);
+        }
+        out[i] = prefctr * acc;
+    }
+}
+
+/* Test yardstick: the potential energy of the current positions over the current list with every
+ * pair term formed as in forces() but accumulated in long double.  The reference adds ~N*55 terms
+ * into ONE double in list order (.cpp:284-312); on the perfect start lattice identical terms
+ * repeat and the rounding errors of that running sum do not average out, so its own deviation
+ * from the exact sum can exceed 1e-12 relative.  This value measures that deviation. */
+double ljo_epot_long_double(const ljo_sim* s) {
+    const double L = s->L, rcutsq = s->p.rcut * s->p.rcut, sigmasq = s->p.sigma * s->p.sigma;
+    const double sr2 = sigmasq / rcutsq, sr6 = sr2 * sr2 * sr2, sr12 = sr6 * sr6;
+    const double epot_cutoff = sr12 - sr6;
+    long double sum = 0.0L;
+    for (int i = 0; i < s->n; i++) {
+        for (uint64_t q = s->nl_off[i]; q < s->nl_off[i + 1]; q++) {
+            const unsigned j = s->nl[q];
+            const double ddx = min_image(s->x[i] - s->x[j], L);
+            const double ddy = min_image(s->y[i] - s->y[j], L);
+            const double ddz = min_image(s->z[i] - s->z[j], L);
+            const double d2 = ddx * ddx + ddy * ddy + ddz * ddz;
+            if (d2 >= rcutsq) continue;
+            const long double invd2 = 1.0L / (long double)d2;
+            const long double s2 = (long double)sigmasq * invd2;
+            const long double s6 = s2 * s2 * s2;
+            sum += s6 * s6 - s6 - (long double)epot_cutoff;
+        }
+    }
+    return (double)(sum * 4.0L * (long double)s->p.epsilon * 0.5L);
+}
+
 void ljo_cell_ids_of(const ljo_params* p, int n, const double* x, const double* y, const double* z,
                      unsigned* cell, unsigned* dims3) {
     unsigned nc; double edge;

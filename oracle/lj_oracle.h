@@ -61,6 +61,10 @@ void ljo_neighbor_counts(const ljo_sim* s, unsigned* counts);
 unsigned ljo_neighbors_of(const ljo_sim* s, unsigned i, unsigned* out, unsigned cap);
 void ljo_incutoff_counts(const ljo_sim* s, unsigned* counts);
 void ljo_cell_ids(const ljo_sim* s, unsigned* cell, unsigned* dims3);
+/* Test yardstick: per-atom sum of |f_ij| over the accepted pairs. */
+void ljo_force_abs_sums(const ljo_sim* s, double* out);
+/* Test yardstick: epot of the current positions/list accumulated in long double. */
+double ljo_epot_long_double(const ljo_sim* s);
 
 /* Stateless helpers on caller arrays. */
 void ljo_cell_ids_of(const ljo_params* p, int n, const double* x, const double* y, const double* z,

@@ -26,15 +26,25 @@ def make_pair(lj, cfg, kernel, state=None):
 
 
 def check_step(o, g, tol=TOL, what=""):
+    """Energies and forces of the GPU against the oracle at `tol` relative.
+
+    epot: the reference accumulates its ~55 N pair terms into one double in list order; on the
+    perfect start lattice (identical terms repeating) that running sum is itself off from the exact
+    sum by more than 1e-12 relative (measured here with a long-double re-summation of the oracle's
+    own pair terms).  The GPU's tree reduction does not share that error, so the bound is
+    tol + twice the oracle's own measured deviation, and the GPU must be within tol of the exact sum."""
     ek, ep, et = g.get_energies()
     oek, oep, oet = o.energies()
-    assert rel(ep, oep) < tol, f"{what} epot {ep} vs {oep}"
+    exact = o.epot_long_double()
+    own = abs(oep - exact)
+    assert abs(ep - exact) < tol * abs(exact), f"{what} epot {ep} vs exact {exact}"
+    assert abs(ep - oep) < tol * abs(oep) + 2.0 * own, f"{what} epot {ep} vs {oep} (oracle's own summation error {own})"
     if oek != 0.0:
         assert rel(ek, oek) < tol, f"{what} ekin {ek} vs {oek}"
-        assert abs(et - oet) < tol * (abs(oek) + abs(oep)), f"{what} etot {et} vs {oet}"
+        assert abs(et - oet) < tol * (abs(oek) + abs(oep)) + 2.0 * own, f"{what} etot {et} vs {oet}"
     else:
         assert ek == 0.0
-    err = ol.force_rel_error(g.get_forces_soa(), o.forces())
+    err = ol.force_rel_error(g.get_forces_soa(), o.forces(), o.force_abs_sums())
     assert err.max() < tol, f"{what} force rel err {err.max()}"
 
 
