@@ -129,6 +129,10 @@ int ljgpu_step(ljgpu_sim* s, uint32_t step, double dt);
  * minus its 2000 steps/s throttle. */
 int ljgpu_step_n(ljgpu_sim* s, uint32_t first, uint32_t n, double dt);
 
+/* ljgpu_step_n, additionally reporting the device time of the n steps (re-binning included) measured
+ * with CUDA events recorded on the integrator's own stream around the whole batch. */
+int ljgpu_step_n_timed(ljgpu_sim* s, uint32_t first, uint32_t n, double dt, double* device_ms);
+
 /* ---- queries (original atom order) --------------------------------------------------------- */
 
 /* get_positions_copy / get_render_x,y,z (lennardjonessimulation.h:131-143, .cpp:159-171):
@@ -174,6 +178,14 @@ int ljgpu_reset_timers(ljgpu_sim* s);
 /* Force path actually in use (LJGPU_KERNEL_*), cells per axis, current list capacity per atom. */
 int ljgpu_get_layout(ljgpu_sim* s, int32_t* force_kernel, uint32_t* cells_per_axis,
                      uint32_t* list_capacity, uint64_t* n_ghosts);
+
+/* Mean and maximum Verlet-list length per atom of the current list (0 on the other paths). */
+int ljgpu_get_list_stats(ljgpu_sim* s, double* mean_length, uint32_t* max_length);
+
+/* Page-locked host memory for query buffers (cudaMallocHost / cudaFreeHost): copies into such a
+ * buffer are true DMA; any other host pointer works too, only slower. */
+int ljgpu_alloc_host(size_t bytes, void** out);
+int ljgpu_free_host(void* p);
 
 #ifdef __cplusplus
 }

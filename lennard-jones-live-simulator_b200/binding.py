@@ -19,7 +19,7 @@ EXPORTED_SYMBOLS = [
     "ljgpu_get_energies", "ljgpu_get_energy_history", "ljgpu_get_speed_histogram",
     "ljgpu_maxwell_boltzmann", "ljgpu_get_cell_ids", "ljgpu_get_neighbor_counts",
     "ljgpu_write_movie_frame", "ljgpu_set_profiling", "ljgpu_get_timers", "ljgpu_reset_timers",
-    "ljgpu_get_layout",
+    "ljgpu_get_layout", "ljgpu_step_n_timed", "ljgpu_get_list_stats", "ljgpu_alloc_host", "ljgpu_free_host",
 ]
 
 
@@ -88,6 +88,10 @@ def load_library():
     lib.ljgpu_reset_timers.argtypes = [vp]
     lib.ljgpu_get_layout.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
                                      C.POINTER(C.c_uint64)]
+    lib.ljgpu_step_n_timed.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_double, dp]
+    lib.ljgpu_get_list_stats.argtypes = [vp, dp, C.POINTER(C.c_uint32)]
+    lib.ljgpu_alloc_host.argtypes = [C.c_size_t, C.POINTER(vp)]
+    lib.ljgpu_free_host.argtypes = [vp]
     _LIB = lib
     return lib
 
@@ -197,6 +201,12 @@ class LennardJonesSimulation:
     def integrate_n(self, first, n, dt):
         _check(self._lib, self._lib.ljgpu_step_n(self._h, first, n, dt))
 
+    def integrate_n_timed(self, first, n, dt):
+        """integrate_n + device milliseconds (CUDA events on the integrator's stream)."""
+        ms = C.c_double()
+        _check(self._lib, self._lib.ljgpu_step_n_timed(self._h, first, n, dt, C.byref(ms)))
+        return ms.value
+
     def set_state(self, state):
         state = [np.ascontiguousarray(a, dtype=np.float64) for a in state]
         _check(self._lib, self._lib.ljgpu_set_state(self._h, *[_ptr(a) for a in state]))
@@ -226,6 +236,15 @@ class LennardJonesSimulation:
 
     def get_positions_soa(self):
         return self._get3(self._lib.ljgpu_get_positions)
+
+    def get_positions_into(self, px, py, pz):
+        """Positions into caller buffers given as raw addresses (e.g. pinned memory)."""
+        _check(self._lib, self._lib.ljgpu_get_positions(self._h, px, py, pz))
+
+    def get_list_stats(self):
+        m, mx = C.c_double(), C.c_uint32()
+        _check(self._lib, self._lib.ljgpu_get_list_stats(self._h, C.byref(m), C.byref(mx)))
+        return m.value, mx.value
 
     def get_velocities_soa(self):
         return self._get3(self._lib.ljgpu_get_velocities)

@@ -157,6 +157,27 @@ __device__ __forceinline__ double lj_pair(double d2, double sigma2, double& e) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// One position = one 32-byte sector.  sm_100 has 256-bit global loads/stores (SASS LDG.E.ENL2.256 /
+// STG.E.ENL2.256); a plain double4 access is split into two 128-bit halves, which doubles the L1
+// sector traffic of the gather in the Verlet force kernel.  cudaMalloc'ed double4 arrays are
+// 32-byte aligned element by element.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double4 ld_pos(const double4* p) {
+    double4 r;
+    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+    return r;
+}
+// read-only path (positions are not written by the kernel that uses this)
+__device__ __forceinline__ double4 ld_pos_nc(const double4* p) {
+    double4 r;
+    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_pos(double4* p, const double4& v) {
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" :: "l"(p), "d"(v.x), "d"(v.y), "d"(v.z), "d"(v.w) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
 // Device-wide primitives implemented in lj_sort.cu
 // ---------------------------------------------------------------------------------------------
 struct SortScratch {

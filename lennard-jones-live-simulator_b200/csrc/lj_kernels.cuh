@@ -19,7 +19,7 @@
 namespace ljgpu {
 
 constexpr int kBlock = 128;            // threads per block of the per-atom kernels
-constexpr int kFinalizeThreads = 256;
+constexpr int kFinalizeThreads = 1024;
 
 // ---------------------------------------------------------------------------------------------
 // K0  predict: sum |v + a f|^2, the kinetic sum kick1 of the coming step will produce
@@ -43,11 +43,22 @@ predict_kernel(unsigned n, double a,
     if (threadIdx.x == 0) partial_pred[blockIdx.x] = s;
 }
 
+// Fixed-order partial sum of one thread of a finalize block: four independent accumulators so the
+// loads overlap; the order depends only on the launch shape, so results are reproducible run to run.
+__device__ __forceinline__ double strided_sum(const double* __restrict__ p, unsigned n) {
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    unsigned k = threadIdx.x;
+    for (; k + 3 * kFinalizeThreads < n; k += 4 * kFinalizeThreads) {
+        a0 += p[k]; a1 += p[k + kFinalizeThreads]; a2 += p[k + 2 * kFinalizeThreads]; a3 += p[k + 3 * kFinalizeThreads];
+    }
+    for (; k < n; k += kFinalizeThreads) a0 += p[k];
+    return (a0 + a1) + (a2 + a3);
+}
+
 __global__ void __launch_bounds__(kFinalizeThreads)
 predict_finalize_kernel(StepCtrl* __restrict__ ctrl, const double* __restrict__ partial_pred, unsigned nb) {
     __shared__ double red[32];
-    double s = 0.0;
-    for (unsigned k = threadIdx.x; k < nb; k += kFinalizeThreads) s += partial_pred[k];
+    double s = strided_sum(partial_pred, nb);
     s = block_sum(s, red);
     if (threadIdx.x == 0) ctrl->pred_sum = s;
 }
@@ -73,7 +84,7 @@ kick_drift_kernel(LJConst c, double dt, double a, StepCtrl* __restrict__ ctrl,
     const unsigned i = blockIdx.x * kBlock + threadIdx.x;
     double d2 = 0.0;
     if (i < c.n) {
-        double4 p = pos[i];
+        double4 p = ld_pos(pos + i);
         p.x = wrap_coord(p.x, c.L, c.invL);
         p.y = wrap_coord(p.y, c.L, c.invL);
         p.z = wrap_coord(p.z, c.L, c.invL);
@@ -84,7 +95,7 @@ kick_drift_kernel(LJConst c, double dt, double a, StepCtrl* __restrict__ ctrl,
         const double incx = xmul(ux, dt), incy = xmul(uy, dt), incz = xmul(uz, dt);
         p.x = xadd(p.x, incx); p.y = xadd(p.y, incy); p.z = xadd(p.z, incz);
         vx[i] = ux; vy[i] = uy; vz[i] = uz;
-        pos[i] = p;
+        st_pos(pos + i, p);
         if (TRACK_DISP) {
             const double ax = xadd(dijx[i], incx), ay = xadd(dijy[i], incy), az = xadd(dijz[i], incz);
             dijx[i] = ax; dijy[i] = ay; dijz[i] = az;
@@ -192,7 +203,10 @@ struct CellGrid {
     unsigned nc;                             // cells per axis
 };
 
-template <class Op>
+// EXACT: distances formed without contraction (bit-exact acceptance, used by the parity probe);
+// otherwise fused multiply-adds (the list / cell force do not need bit-exact acceptance: the list
+// keeps a skin, the force tolerance is 1e-12).
+template <bool EXACT, class Op>
 __device__ __forceinline__ void cell_traverse(const LJConst& c, const CellGrid& g, const double4* __restrict__ pos,
                                               double4 (*tile)[32], Op& op) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -205,7 +219,7 @@ __device__ __forceinline__ void cell_traverse(const LJConst& c, const CellGrid& 
     for (unsigned hb = 0; hb < hn; hb += 32) {
         const unsigned i = hs + hb + lane;
         const bool active = hb + lane < hn;
-        const double4 pi = active ? pos[i] : make_double4(0, 0, 0, 0);
+        const double4 pi = active ? ld_pos_nc(pos + i) : make_double4(0, 0, 0, 0);
         op.begin(i, active);
 #pragma unroll 1
         for (int s = 0; s < 27; ++s) {
@@ -216,18 +230,18 @@ __device__ __forceinline__ void cell_traverse(const LJConst& c, const CellGrid& 
             const unsigned js = g.cstart[cid], jn = g.ccount[cid];
             for (unsigned jb = 0; jb < jn; jb += 32) {
                 __syncwarp();
-                if (jb + lane < jn) tile[w][lane] = pos[js + jb + lane];
+                if (jb + lane < jn) tile[w][lane] = ld_pos_nc(pos + js + jb + lane);
                 __syncwarp();
                 const unsigned cnt = min(32u, jn - jb);
                 for (unsigned jj = 0; jj < cnt; ++jj) {
                     const double4 pj = tile[w][jj];
                     double ddx = xsub(pi.x, pj.x), ddy = xsub(pi.y, pj.y), ddz = xsub(pi.z, pj.z);
-                    double d2 = xnorm2(ddx, ddy, ddz);
+                    double d2 = EXACT ? xnorm2(ddx, ddy, ddz) : fma(ddz, ddz, fma(ddy, ddy, ddx * ddx));
                     if (maybe_wrapped(d2, far2_hi)) {
                         ddx = min_image(ddx, c.L, c.halfL);
                         ddy = min_image(ddy, c.L, c.halfL);
                         ddz = min_image(ddz, c.L, c.halfL);
-                        d2 = xnorm2(ddx, ddy, ddz);
+                        d2 = EXACT ? xnorm2(ddx, ddy, ddz) : fma(ddz, ddz, fma(ddy, ddy, ddx * ddx));
                     }
                     op.pair(i, js + jb + jj, ddx, ddy, ddz, d2, active);
                 }
@@ -279,7 +293,7 @@ list_kernel(LJConst c, CellGrid g, const double4* __restrict__ pos, double cut2,
             StepCtrl* __restrict__ ctrl) {
     __shared__ double4 tile[kCellWarps][32];
     ListOp<MODE> op{cut2, inclusive, cap, nl, out_count, orig, ctrl, 0};
-    cell_traverse(c, g, pos, tile, op);
+    cell_traverse<MODE == 2>(c, g, pos, tile, op);
 }
 
 struct CellForceOp {
@@ -309,7 +323,7 @@ force_cell_kernel(LJConst c, CellGrid g, const StepCtrl* __restrict__ ctrl, cons
     __shared__ double red[32];
     if (ctrl->stop) return;
     CellForceOp op{c.rc2, c.sigma2, c.ecut, c.prefctr, fx, fy, fz, 0, 0, 0, 0, 0.0, 0};
-    cell_traverse(c, g, pos, tile, op);
+    cell_traverse<false>(c, g, pos, tile, op);
     const double e = block_sum(op.etot, red);
     if (threadIdx.x == 0) partial_epot[blockIdx.x] = e;
 }
@@ -330,7 +344,7 @@ force_verlet_kernel(LJConst c, const StepCtrl* __restrict__ ctrl, const double4*
     double ax = 0.0, ay = 0.0, az = 0.0, e = 0.0;
     unsigned nacc = 0;
     if (active) {
-        const double4 pi = pos[i];
+        const double4 pi = ld_pos_nc(pos + i);
         const unsigned cnt = nl_count[i];
         const uint32_t* __restrict__ row = nl + nl_index(i, 0, cap);
         unsigned k = 0;
@@ -352,11 +366,11 @@ force_verlet_kernel(LJConst c, const StepCtrl* __restrict__ ctrl, const double4*
         for (; k + 4 <= cnt; k += 4) {
             const uint32_t j0 = row[(size_t)(k + 0) * 32], j1 = row[(size_t)(k + 1) * 32];
             const uint32_t j2 = row[(size_t)(k + 2) * 32], j3 = row[(size_t)(k + 3) * 32];
-            const double4 p0 = pos[j0], p1 = pos[j1], p2 = pos[j2], p3 = pos[j3];
+            const double4 p0 = ld_pos_nc(pos + j0), p1 = ld_pos_nc(pos + j1), p2 = ld_pos_nc(pos + j2), p3 = ld_pos_nc(pos + j3);
             LJ_ACC(p0) LJ_ACC(p1) LJ_ACC(p2) LJ_ACC(p3)
         }
         for (; k < cnt; ++k) {
-            const double4 p0 = pos[row[(size_t)k * 32]];
+            const double4 p0 = ld_pos_nc(pos + row[(size_t)k * 32]);
             LJ_ACC(p0)
         }
 #undef LJ_ACC
@@ -401,9 +415,7 @@ step_finalize_kernel(LJConst c, StepCtrl* __restrict__ ctrl, HistEntry* __restri
                      unsigned nb_kick) {
     __shared__ double red[32];
     if (ctrl->stop) return;
-    double se = 0.0, sk = 0.0, sp = 0.0;
-    for (unsigned k = threadIdx.x; k < nb_epot; k += kFinalizeThreads) se += partial_epot[k];
-    for (unsigned k = threadIdx.x; k < nb_kick; k += kFinalizeThreads) { sk += partial_ekin[k]; sp += partial_pred[k]; }
+    double se = strided_sum(partial_epot, nb_epot), sk = strided_sum(partial_ekin, nb_kick), sp = strided_sum(partial_pred, nb_kick);
     se = block_sum(se, red);
     sk = block_sum(sk, red);
     sp = block_sum(sp, red);
@@ -426,8 +438,7 @@ step_finalize_kernel(LJConst c, StepCtrl* __restrict__ ctrl, HistEntry* __restri
 __global__ void __launch_bounds__(kFinalizeThreads)
 init_finalize_kernel(LJConst c, StepCtrl* __restrict__ ctrl, const double* __restrict__ partial_epot, unsigned nb_epot) {
     __shared__ double red[32];
-    double se = 0.0;
-    for (unsigned k = threadIdx.x; k < nb_epot; k += kFinalizeThreads) se += partial_epot[k];
+    double se = strided_sum(partial_epot, nb_epot);
     se = block_sum(se, red);
     if (threadIdx.x == 0) {
         ctrl->epot_sum = se;

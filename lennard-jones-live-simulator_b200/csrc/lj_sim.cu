@@ -527,6 +527,22 @@ int ljgpu_step_n(ljgpu_sim* s, uint32_t first, uint32_t n, double dt) {
     return with_sim(s, [&] { s->run_steps(first, n, dt); });
 }
 
+int ljgpu_step_n_timed(ljgpu_sim* s, uint32_t first, uint32_t n, double dt, double* device_ms) {
+    if (!device_ms) return fail(LJGPU_EINVAL, "null argument");
+    return with_sim(s, [&] {
+        cudaEvent_t a, b;
+        CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+        CK(cudaEventRecord(a, s->st));
+        s->run_steps(first, n, dt);
+        CK(cudaEventRecord(b, s->st));
+        CK(cudaEventSynchronize(b));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, a, b));
+        cudaEventDestroy(a); cudaEventDestroy(b);
+        *device_ms = ms;
+    });
+}
+
 int ljgpu_get_positions(ljgpu_sim* s, double* x, double* y, double* z) {
     if (!x || !y || !z) return fail(LJGPU_EINVAL, "null argument");
     return with_sim(s, [&] { s->export3(0, x, y, z); });
@@ -671,6 +687,31 @@ int ljgpu_get_layout(ljgpu_sim* s, int32_t* force_kernel, uint32_t* cells_per_ax
         if (list_capacity) *list_capacity = s->cap;
         if (n_ghosts) *n_ghosts = 0;      // no ghost atoms in this layout: periodic images are resolved per pair
     });
+}
+
+int ljgpu_get_list_stats(ljgpu_sim* s, double* mean_length, uint32_t* max_length) {
+    return with_sim(s, [&] {
+        double mean = 0.0; uint32_t mx = 0;
+        if (s->mode == LJGPU_KERNEL_VERLET && s->nl_count) {
+            std::vector<uint32_t> h(s->n);
+            CK(cudaMemcpyAsync(h.data(), s->nl_count, (size_t)s->n * 4, cudaMemcpyDeviceToHost, s->st));
+            s->sync();
+            unsigned long long tot = 0;
+            for (uint32_t c : h) { tot += c; mx = std::max(mx, c); }
+            mean = (double)tot / (double)s->n;
+        }
+        if (mean_length) *mean_length = mean;
+        if (max_length) *max_length = mx;
+    });
+}
+
+int ljgpu_alloc_host(size_t bytes, void** out) {
+    if (!out) return fail(LJGPU_EINVAL, "null argument");
+    return guarded([&] { CK(cudaMallocHost(out, bytes ? bytes : 1)); });
+}
+
+int ljgpu_free_host(void* p) {
+    return guarded([&] { if (p) CK(cudaFreeHost(p)); });
 }
 
 } // extern "C"
