@@ -49,7 +49,8 @@ _LIB = None
 
 
 def library_path():
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libljgpu.so")
+    """In-tree libljgpu.so; LJGPU_LIBRARY overrides it (developer experiments with build variants)."""
+    return os.environ.get("LJGPU_LIBRARY") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libljgpu.so")
 
 
 def load_library():

@@ -190,7 +190,7 @@ allpairs_reduce_kernel(LJConst c, const StepCtrl* __restrict__ ctrl, unsigned ns
 }
 
 // ---------------------------------------------------------------------------------------------
-// Cell traversal shared by the list build, the neighbour-count probe and the cell-list force kernel:
+// Cell traversal of the neighbour-count probe (the hot kernels use the tiles of lj_tile.cuh):
 // one warp per home cell, lanes = home atoms, the 27 periodic stencil cells of .cpp:488-516 streamed
 // through a warp-private shared-memory tile.  Distances are formed exactly as the reference forms them
 // (no contraction), so acceptance decisions are bit-identical.
@@ -251,134 +251,25 @@ __device__ __forceinline__ void cell_traverse(const LJConst& c, const CellGrid& 
     }
 }
 
-// Verlet list layout: atoms are grouped in tiles of 32 consecutive slots; entry k of slot i lives at
-// nl[((i>>5)*cap + k)*32 + (i&31)], so a warp that walks its 32 lists reads 128 contiguous bytes per k.
-// Replaces the reference's flat [offsets][entries..., sentinel] vector (.cpp:543-550).
-__device__ __forceinline__ size_t nl_index(unsigned i, unsigned k, unsigned cap) {
-    return ((size_t)(i >> 5) * cap + k) * 32 + (i & 31u);
-}
-
-// MODE 0: count only (inclusive), 1: fill the list (inclusive), 2: probe with caller cutoff / strictness
-template <int MODE>
-struct ListOp {
-    double cut2; int inclusive; unsigned cap; uint32_t* nl; uint32_t* out_count; const uint32_t* orig;
-    StepCtrl* ctrl; unsigned cnt;
+// Neighbour-count parity probe of include/ljgpu.h (ljgpu_get_neighbor_counts): the acceptance test of
+// build_neighbor_list (.cpp:518-540, inclusive) or of the force loop (.cpp:291-305, strict) with a
+// caller-supplied cutoff, bit-exact, original atom order out.
+struct CountOp {
+    double cut2; int inclusive; uint32_t* out_count; const uint32_t* orig; unsigned cnt;
     __device__ __forceinline__ void begin(unsigned, bool) { cnt = 0; }
     __device__ __forceinline__ void pair(unsigned i, unsigned j, double, double, double, double d2, bool active) {
-        const bool in = (MODE == 2 && !inclusive) ? (d2 < cut2) : (d2 <= cut2);
-        if (active && in && j != i) {
-            if (MODE == 1 && cnt < cap) nl[nl_index(i, cnt, cap)] = j;
-            ++cnt;
-        }
+        const bool in = inclusive ? (d2 <= cut2) : (d2 < cut2);
+        if (active && in && j != i) ++cnt;
     }
-    __device__ __forceinline__ void end(unsigned i, bool active) {
-        if (MODE == 2) { if (active) out_count[orig[i]] = cnt; return; }
-        if (active) out_count[i] = MODE == 1 ? min(cnt, cap) : cnt;
-        unsigned m = active ? cnt : 0u;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-        if ((threadIdx.x & 31) == 0) {
-            atomicMax(&ctrl->max_count, m);
-            if (MODE == 1 && m > cap) atomicExch(&ctrl->overflow, 1u);
-        }
-    }
+    __device__ __forceinline__ void end(unsigned i, bool active) { if (active) out_count[orig[i]] = cnt; }
 };
 
-// build_neighbor_list, .cpp:441-551 (acceptance dist2 <= (rcut+shell)^2, :536), on the device layout;
-// MODE 2 is the parity probe of include/ljgpu.h (ljgpu_get_neighbor_counts).
-template <int MODE>
 __global__ void __launch_bounds__(kCellWarps * 32)
-list_kernel(LJConst c, CellGrid g, const double4* __restrict__ pos, double cut2, int inclusive, unsigned cap,
-            uint32_t* __restrict__ nl, uint32_t* __restrict__ out_count, const uint32_t* __restrict__ orig,
-            StepCtrl* __restrict__ ctrl) {
+count_cells_kernel(LJConst c, CellGrid g, const double4* __restrict__ pos, double cut2, int inclusive,
+                   uint32_t* __restrict__ out_count, const uint32_t* __restrict__ orig) {
     __shared__ double4 tile[kCellWarps][32];
-    ListOp<MODE> op{cut2, inclusive, cap, nl, out_count, orig, ctrl, 0};
-    cell_traverse<MODE == 2>(c, g, pos, tile, op);
-}
-
-struct CellForceOp {
-    double rc2, sigma2, ecut, prefctr;
-    double* fx; double* fy; double* fz;
-    double ax, ay, az, e, etot; unsigned nacc;
-    __device__ __forceinline__ void begin(unsigned, bool) { ax = ay = az = e = 0.0; nacc = 0; }
-    __device__ __forceinline__ void pair(unsigned i, unsigned j, double dx, double dy, double dz, double d2, bool active) {
-        if (active && d2 < rc2 && j != i) {
-            const double fr = lj_pair(d2, sigma2, e);
-            ax = fma(fr, dx, ax); ay = fma(fr, dy, ay); az = fma(fr, dz, az);
-            ++nacc;
-        }
-    }
-    __device__ __forceinline__ void end(unsigned i, bool active) {
-        if (active) { fx[i] = ax * prefctr; fy[i] = ay * prefctr; fz[i] = az * prefctr; }
-        etot += fma(-(double)nacc, ecut, e);
-    }
-};
-
-// K7a cell-list force kernel: every step, all 27 stencil cells, cutoff test d2 < rcut^2 (.cpp:304-305).
-__global__ void __launch_bounds__(kCellWarps * 32)
-force_cell_kernel(LJConst c, CellGrid g, const StepCtrl* __restrict__ ctrl, const double4* __restrict__ pos,
-                  double* __restrict__ fx, double* __restrict__ fy, double* __restrict__ fz,
-                  double* __restrict__ partial_epot) {
-    __shared__ double4 tile[kCellWarps][32];
-    __shared__ double red[32];
-    if (ctrl->stop) return;
-    CellForceOp op{c.rc2, c.sigma2, c.ecut, c.prefctr, fx, fy, fz, 0, 0, 0, 0, 0.0, 0};
-    cell_traverse<false>(c, g, pos, tile, op);
-    const double e = block_sum(op.etot, red);
-    if (threadIdx.x == 0) partial_epot[blockIdx.x] = e;
-}
-
-// K7b Verlet-list force kernel: one thread per atom slot, its list entries gathered as 32-byte
-// double4 sectors (served by L1/L2: neighbours of consecutive slots overlap almost completely).
-// calculate_forces, .cpp:286-319.
-__global__ void __launch_bounds__(kBlock)
-force_verlet_kernel(LJConst c, const StepCtrl* __restrict__ ctrl, const double4* __restrict__ pos,
-                    const uint32_t* __restrict__ nl, const uint32_t* __restrict__ nl_count, unsigned cap,
-                    double* __restrict__ fx, double* __restrict__ fy, double* __restrict__ fz,
-                    double* __restrict__ partial_epot) {
-    __shared__ double red[32];
-    if (ctrl->stop) return;
-    const unsigned i = blockIdx.x * kBlock + threadIdx.x;
-    const bool active = i < c.n;
-    const int far2_hi = __double2hiint(c.far2);
-    double ax = 0.0, ay = 0.0, az = 0.0, e = 0.0;
-    unsigned nacc = 0;
-    if (active) {
-        const double4 pi = ld_pos_nc(pos + i);
-        const unsigned cnt = nl_count[i];
-        const uint32_t* __restrict__ row = nl + nl_index(i, 0, cap);
-        unsigned k = 0;
-#define LJ_ACC(P)                                                                          \
-        {                                                                                  \
-            double dx = pi.x - P.x, dy = pi.y - P.y, dz = pi.z - P.z;                      \
-            double d2 = fma(dz, dz, fma(dy, dy, dx * dx));                                 \
-            if (maybe_wrapped(d2, far2_hi)) {                                              \
-                dx = min_image(dx, c.L, c.halfL); dy = min_image(dy, c.L, c.halfL);        \
-                dz = min_image(dz, c.L, c.halfL);                                          \
-                d2 = fma(dz, dz, fma(dy, dy, dx * dx));                                    \
-            }                                                                              \
-            if (d2 < c.rc2) {                                                              \
-                const double fr = lj_pair(d2, c.sigma2, e);                                \
-                ax = fma(fr, dx, ax); ay = fma(fr, dy, ay); az = fma(fr, dz, az);          \
-                ++nacc;                                                                    \
-            }                                                                              \
-        }
-        for (; k + 4 <= cnt; k += 4) {
-            const uint32_t j0 = row[(size_t)(k + 0) * 32], j1 = row[(size_t)(k + 1) * 32];
-            const uint32_t j2 = row[(size_t)(k + 2) * 32], j3 = row[(size_t)(k + 3) * 32];
-            const double4 p0 = ld_pos_nc(pos + j0), p1 = ld_pos_nc(pos + j1), p2 = ld_pos_nc(pos + j2), p3 = ld_pos_nc(pos + j3);
-            LJ_ACC(p0) LJ_ACC(p1) LJ_ACC(p2) LJ_ACC(p3)
-        }
-        for (; k < cnt; ++k) {
-            const double4 p0 = ld_pos_nc(pos + row[(size_t)k * 32]);
-            LJ_ACC(p0)
-        }
-#undef LJ_ACC
-        fx[i] = ax * c.prefctr; fy[i] = ay * c.prefctr; fz[i] = az * c.prefctr;
-    }
-    e = fma(-(double)nacc, c.ecut, e);
-    e = block_sum(e, red);
-    if (threadIdx.x == 0) partial_epot[blockIdx.x] = e;
+    CountOp op{cut2, inclusive, out_count, orig, 0};
+    cell_traverse<true>(c, g, pos, tile, op);
 }
 
 // ---------------------------------------------------------------------------------------------

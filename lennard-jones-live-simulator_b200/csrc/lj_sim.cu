@@ -2,7 +2,7 @@
 //
 // Path replaced: class LennardJonesSimulation, /root/reference/src/simulator/lennardjonessimulation.{h,cpp}
 // (".cpp"/".h" below).  No CPU fallback: every entry point fails with LJGPU_ECUDA when there is no device.
-#include "lj_kernels.cuh"
+#include "lj_tile.cuh"
 #include "../../include/ljgpu.h"
 
 #include <algorithm>
@@ -65,8 +65,10 @@ struct ljgpu_sim {
     uint32_t *cstart = nullptr, *cend = nullptr, *ccount = nullptr;
     SortScratch scr;
 
-    // Verlet list
-    uint32_t* nl = nullptr; uint32_t* nl_count = nullptr; unsigned cap = 0; size_t nl_alloc = 0;
+    // shared-memory tiles (lj_tile.cuh) and the Verlet list of 16-bit tile indices
+    uint32_t *tsrc = nullptr, *toff = nullptr;
+    unsigned nbx = 0, nby = 0, nbz = 0, nblocks_tile = 0, tcap = 0, tile_threads = 128;
+    uint32_t* nl = nullptr; uint32_t* nl_count = nullptr; unsigned capq = 0; size_t nl_alloc = 0;
 
     // reductions
     double *partial_epot = nullptr, *partial_ekin = nullptr, *partial_pred = nullptr;
@@ -153,7 +155,7 @@ ljgpu_sim::~ljgpu_sim() {
     for (int k = 0; k < 3; ++k) { dfree(dij[k]); dfree(v[k]); dfree(f[k]); dfree(v_alt[k]); dfree(f_alt[k]); dfree(apf[k]); }
     dfree(orig); dfree(orig_alt); dfree(keys); dfree(vals);
     dfree(cstart); dfree(cend); dfree(ccount);
-    dfree(nl); dfree(nl_count);
+    dfree(nl); dfree(nl_count); dfree(tsrc); dfree(toff);
     dfree(partial_epot); dfree(partial_ekin); dfree(partial_pred);
     dfree(ctrl); dfree(hist); dfree(out3); dfree(out_u32); dfree(hist_counts);
     if (h_ctrl) cudaFreeHost(h_ctrl);
@@ -216,7 +218,11 @@ void ljgpu_sim::allocate() {
         CK(cudaMalloc(&keys, N * 4)); CK(cudaMalloc(&vals, N * 4));
         CK(cudaMalloc(&cstart, (size_t)ncell * 4)); CK(cudaMalloc(&cend, (size_t)ncell * 4)); CK(cudaMalloc(&ccount, (size_t)ncell * 4));
         CK(cudaMalloc(&nl_count, N * 4));
-        nb_force = mode == LJGPU_KERNEL_VERLET ? nb_atoms : cdiv(ncell, kCellWarps);
+        nbx = cdiv(nc, kTileBX); nby = cdiv(nc, kTileBY); nbz = cdiv(nc, kTileBZ);
+        nblocks_tile = nbx * nby * nbz;
+        CK(cudaMalloc(&tsrc, (size_t)nblocks_tile * kTileCellsMax * 4));
+        CK(cudaMalloc(&toff, (size_t)nblocks_tile * (kTileCellsMax + 1) * 4));
+        nb_force = nblocks_tile * 16;          // one partial per warp, up to 512 threads per CTA
     } else {
         // j splits: enough blocks to fill 148 SMs a few times over, each split at least 64 atoms wide
         const unsigned want = std::max(1u, (4u * 148u + nb_atoms - 1) / nb_atoms);
@@ -272,6 +278,21 @@ void ljgpu_sim::rebuild() {
     cell_count_kernel<<<cdiv(ncell, kBlock), kBlock, 0, st>>>(ncell, cstart, cend, ccount);
     check_launch("cell_count");
 
+    CK(cudaMemsetAsync(&ctrl->max_tile, 0, sizeof(unsigned), st));
+    CK(cudaMemsetAsync(&ctrl->max_home, 0, sizeof(unsigned), st));
+    {
+        TileGrid g{nc, nbx, nby, nbz, nblocks_tile, tsrc, toff};
+        tile_table_kernel<<<cdiv(nblocks_tile, 4), 128, 0, st>>>(g, cstart, ccount, tsrc, toff, ctrl);
+    }
+    check_launch("tile_table");
+    fetch_ctrl();
+    tcap = ((h_ctrl->max_tile + 15) / 16) * 16;
+    tile_threads = std::min((unsigned)LJ_TILE_MAXTHREADS, std::max(64u, ((h_ctrl->max_home + 31) / 32) * 32));
+    nb_force = nblocks_tile * (tile_threads / 32);
+    if ((size_t)tcap * 24 > 200 * 1024)
+        throw LjError(LJGPU_ESTATE, "a cell neighbourhood does not fit in shared memory (density too inhomogeneous)");
+    if (h_ctrl->max_tile > 65535) throw LjError(LJGPU_ESTATE, "tile too large for 16-bit list indices");
+
     if (mode == LJGPU_KERNEL_VERLET) build_list();
     stage_end(ST_REBUILD);
     ++rebuilds;
@@ -280,30 +301,42 @@ void ljgpu_sim::rebuild() {
     dirty_since_rebuild = false;
 }
 
+template <int MODE, bool UNIT_SIGMA>
+static void launch_tile2(ljgpu_sim* s, int guarded) {
+    const size_t smem = (size_t)s->tcap * 24;
+    if (smem > 48 * 1024)
+        CK(cudaFuncSetAttribute(tile_kernel<MODE, UNIT_SIGMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TileGrid g{s->nc, s->nbx, s->nby, s->nbz, s->nblocks_tile, s->tsrc, s->toff};
+    TileArgs a{s->pos, s->nl, s->nl_count, s->f[0], s->f[1], s->f[2], s->partial_epot, s->ctrl, s->capq};
+    tile_kernel<MODE, UNIT_SIGMA><<<s->nblocks_tile, s->tile_threads, smem, s->st>>>(s->c, g, a, guarded);
+    s->check_launch("tile_kernel");
+}
+template <int MODE>
+static void launch_tile(ljgpu_sim* s, int guarded) {
+    if (MODE == TILE_FORCE_LIST && s->c.sigma2 == 1.0) launch_tile2<MODE, true>(s, guarded);
+    else launch_tile2<MODE, false>(s, guarded);
+}
+
 void ljgpu_sim::build_list() {
-    CellGrid g{cstart, ccount, nc};
-    const unsigned nbc = cdiv(ncell, kCellWarps);
     const unsigned ntiles = cdiv(n, 32);
     for (int attempt = 0; attempt < 4; ++attempt) {
         CK(cudaMemsetAsync(&ctrl->max_count, 0, sizeof(unsigned), st));
         CK(cudaMemsetAsync(&ctrl->overflow, 0, sizeof(unsigned), st));
-        if (cap == 0) {
-            list_kernel<0><<<nbc, kCellWarps * 32, 0, st>>>(c, g, pos, c.list_cut2, 1, 0, nullptr, nl_count, orig, ctrl);
-            check_launch("list_kernel<count>");
+        if (capq == 0) {
+            launch_tile<TILE_LIST_COUNT>(this, 0);
             fetch_ctrl();
-            cap = ((h_ctrl->max_count + 8 + 3) / 4) * 4;
+            capq = (h_ctrl->max_count + 8 + 7) / 8;             // quads of 8 entries: max + slack
         }
-        const size_t need = (size_t)ntiles * cap * 32;
+        const size_t need = (size_t)ntiles * capq * 32 * 4;
         if (need > nl_alloc) {
             dfree(nl);
             CK(cudaMalloc(&nl, need * 4));
             nl_alloc = need;
         }
-        list_kernel<1><<<nbc, kCellWarps * 32, 0, st>>>(c, g, pos, c.list_cut2, 1, cap, nl, nl_count, orig, ctrl);
-        check_launch("list_kernel<fill>");
+        launch_tile<TILE_LIST_FILL>(this, 0);
         fetch_ctrl();
         if (!h_ctrl->overflow) return;
-        cap = ((h_ctrl->max_count + 8 + 3) / 4) * 4;       // grow and refill
+        capq = (h_ctrl->max_count + 8 + 7) / 8;                 // grow and refill
     }
     throw LjError(LJGPU_ESTATE, "neighbour list capacity did not converge");
 }
@@ -317,12 +350,9 @@ void ljgpu_sim::launch_force(bool timed) {
         allpairs_reduce_kernel<<<nb_atoms, kBlock, 0, st>>>(c, ctrl, nsplit, apf[0], apf[1], apf[2], f[0], f[1], f[2]);
         check_launch("allpairs_reduce");
     } else if (mode == LJGPU_KERNEL_CELL) {
-        CellGrid g{cstart, ccount, nc};
-        force_cell_kernel<<<nb_force, kCellWarps * 32, 0, st>>>(c, g, ctrl, pos, f[0], f[1], f[2], partial_epot);
-        check_launch("force_cell");
+        launch_tile<TILE_FORCE_CELL>(this, 1);
     } else {
-        force_verlet_kernel<<<nb_force, kBlock, 0, st>>>(c, ctrl, pos, nl, nl_count, cap, f[0], f[1], f[2], partial_epot);
-        check_launch("force_verlet");
+        launch_tile<TILE_FORCE_LIST>(this, 1);
     }
     if (timed) stage_end(ST_FORCE);
 }
@@ -620,8 +650,8 @@ int ljgpu_get_neighbor_counts(ljgpu_sim* s, double cutoff, int inclusive, uint32
         if (s->list_mode()) {
             if (s->dirty_since_rebuild) s->rebuild();       // positions wrapped + cell-sorted again
             CellGrid g{s->cstart, s->ccount, s->nc};
-            list_kernel<2><<<cdiv(s->ncell, kCellWarps), kCellWarps * 32, 0, s->st>>>(
-                s->c, g, s->pos, cut2, inclusive, 0, nullptr, s->out_u32, s->orig, s->ctrl);
+            count_cells_kernel<<<cdiv(s->ncell, kCellWarps), kCellWarps * 32, 0, s->st>>>(
+                s->c, g, s->pos, cut2, inclusive, s->out_u32, s->orig);
         } else {
             count_allpairs_kernel<<<s->nb_atoms, kBlock, 0, s->st>>>(s->c, s->pos, s->orig, cut2, inclusive, s->out_u32);
         }
@@ -684,7 +714,7 @@ int ljgpu_get_layout(ljgpu_sim* s, int32_t* force_kernel, uint32_t* cells_per_ax
     return with_sim(s, [&] {
         if (force_kernel) *force_kernel = s->mode;
         if (cells_per_axis) *cells_per_axis = s->nc;
-        if (list_capacity) *list_capacity = s->cap;
+        if (list_capacity) *list_capacity = 8 * s->capq;
         if (n_ghosts) *n_ghosts = 0;      // no ghost atoms in this layout: periodic images are resolved per pair
     });
 }

@@ -1,0 +1,315 @@
+// lj_tile.cuh - shared-memory tile kernels: Verlet-list force, cell-list force and the list build.
+//
+// Why tiles: a per-thread gather of neighbour positions from L1/L2 costs one cache line per lane per
+// load (measured: the first Verlet kernel ran at exactly one 128-byte line per clock per SM, 85-90 %
+// of the L1 data pipe, FP64 pipe a third busy - profiles/r01b_*).  Shared memory serves 32 arbitrary
+// addresses per clock.  So one CTA owns a small brick of cells ("home block", kTileBX x kTileBY x
+// kTileBZ cells), stages the positions of the brick plus one halo cell on every side once with
+// coalesced 256-bit loads, and every home atom walks its list as 16-bit indices into that tile.
+//
+// Reference code replaced: calculate_forces (.cpp:258-330) and build_neighbor_list (.cpp:441-551) of
+// /root/reference/src/simulator/lennardjonessimulation.cpp.
+#pragma once
+#include "lj_kernels.cuh"
+
+namespace ljgpu {
+
+#ifndef LJ_TILE_BX
+#define LJ_TILE_BX 3
+#endif
+#ifndef LJ_TILE_MAXTHREADS
+#define LJ_TILE_MAXTHREADS 256
+#endif
+#ifndef LJ_TILE_MINBLOCKS
+#define LJ_TILE_MINBLOCKS 3
+#endif
+constexpr int kTileBX = LJ_TILE_BX;                    // home cells per CTA along x (contiguous slots)
+constexpr int kTileBY = 2;
+constexpr int kTileBZ = 2;
+constexpr int kTileRowsMax = (kTileBY + 2) * (kTileBZ + 2);           // x-rows in a tile
+constexpr int kTileCellsMax = (kTileBX + 2) * kTileRowsMax;           // tile cells per CTA
+constexpr int kHomeRowsMax = kTileBY * kTileBZ;
+
+struct TileGrid {
+    unsigned nc;                 // cells per axis
+    unsigned nbx, nby, nbz;      // home blocks per axis
+    unsigned nblocks;
+    const uint32_t* __restrict__ tsrc;   // [nblocks][kTileCellsMax]     first global slot of each tile cell
+    const uint32_t* __restrict__ toff;   // [nblocks][kTileCellsMax + 1] tile-local offset of each tile cell
+};
+
+struct TileGeom { unsigned x0, y0, z0, bw, bh, bd, W, H; };
+
+// Block b -> its brick.  Tile cell numbering: t = ((tz*(bh+2)) + ty)*(bw+2) + tx with one halo cell on
+// every side (tx = 0 and bw+1 etc.), so the cells of one x-row are consecutive in the tile.
+__device__ __forceinline__ TileGeom tile_geometry(unsigned b, const TileGrid& g) {
+    TileGeom t;
+    const unsigned bx = b % g.nbx, by = (b / g.nbx) % g.nby, bz = b / (g.nbx * g.nby);
+    t.x0 = bx * kTileBX; t.y0 = by * kTileBY; t.z0 = bz * kTileBZ;
+    t.bw = min((unsigned)kTileBX, g.nc - t.x0);
+    t.bh = min((unsigned)kTileBY, g.nc - t.y0);
+    t.bd = min((unsigned)kTileBZ, g.nc - t.z0);
+    t.W = t.bw + 2; t.H = t.bh + 2;
+    return t;
+}
+
+// Re-binning: per block, where each tile cell's atoms live (global slot) and where they go in the tile.
+__global__ void __launch_bounds__(128)
+tile_table_kernel(TileGrid g, const uint32_t* __restrict__ cstart, const uint32_t* __restrict__ ccount,
+                  uint32_t* __restrict__ tsrc, uint32_t* __restrict__ toff, StepCtrl* __restrict__ ctrl) {
+    const int lane = threadIdx.x & 31;
+    const unsigned b = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (b >= g.nblocks) return;
+    const TileGeom t = tile_geometry(b, g);
+    const unsigned nc = g.nc, ntc = t.W * t.H * (t.bd + 2);
+    unsigned run = 0, home = 0;
+    for (unsigned t0 = 0; t0 < ntc; t0 += 32) {
+        const unsigned k = t0 + lane;
+        unsigned cnt = 0, src = 0;
+        bool is_home = false;
+        if (k < ntc) {
+            const unsigned tx = k % t.W, ty = (k / t.W) % t.H, tz = k / (t.W * t.H);
+            const unsigned cx = (t.x0 + nc + tx - 1) % nc, cy = (t.y0 + nc + ty - 1) % nc, cz = (t.z0 + nc + tz - 1) % nc;
+            const unsigned cid = cz * nc * nc + cy * nc + cx;
+            cnt = ccount[cid]; src = cstart[cid];
+            is_home = tx >= 1 && tx <= t.bw && ty >= 1 && ty <= t.bh && tz >= 1 && tz <= t.bd;
+        }
+        unsigned inc = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+        if (k < ntc) {
+            tsrc[(size_t)b * kTileCellsMax + k] = src;
+            toff[(size_t)b * (kTileCellsMax + 1) + k] = run + inc - cnt;
+        }
+        run += __shfl_sync(0xffffffffu, inc, 31);
+        unsigned hc = is_home ? cnt : 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) hc += __shfl_xor_sync(0xffffffffu, hc, o);
+        home += hc;
+    }
+    if (lane == 0) {
+        toff[(size_t)b * (kTileCellsMax + 1) + ntc] = run;
+        atomicMax(&ctrl->max_tile, run);
+        atomicMax(&ctrl->max_home, home);
+    }
+}
+
+// 16-bit list entries, eight per 128-bit quad; groups of 32 consecutive slots are interleaved so that
+// one warp-wide 128-bit load fetches 512 contiguous bytes: quad q of slot i starts at 32-bit word
+// (((i>>5)*capq + q)*32 + (i&31))*4.  Entry k of slot i is half-word k&7 of quad k>>3.
+// Replaces the reference's flat [offsets][entries..., sentinel] vector (.cpp:543-550).
+__device__ __forceinline__ size_t nl16_index(unsigned i, unsigned k, unsigned capq) {
+    return ((((size_t)(i >> 5) * capq + (k >> 3)) * 32 + (i & 31u)) * 8) + (k & 7u);
+}
+
+enum { TILE_FORCE_LIST = 0, TILE_FORCE_CELL = 1, TILE_LIST_COUNT = 2, TILE_LIST_FILL = 3 };
+
+struct TileArgs {
+    const double4* __restrict__ pos;
+    uint32_t* __restrict__ nl32;           // list words (fill: written as uint16 halves)
+    uint32_t* __restrict__ nl_count;
+    double* __restrict__ fx; double* __restrict__ fy; double* __restrict__ fz;
+    double* __restrict__ partial_epot;     // one per warp of every CTA: [nblocks][warps_per_block]
+    StepCtrl* ctrl;
+    unsigned capq;                         // list capacity in 128-bit quads (8 entries) per atom
+};
+
+// UNIT_SIGMA: sigma == 1 exactly (reduced units): s2 = sigma^2/d2 needs no multiply.
+template <int MODE, bool UNIT_SIGMA>
+__global__ void __launch_bounds__(LJ_TILE_MAXTHREADS, LJ_TILE_MINBLOCKS)
+tile_kernel(LJConst c, TileGrid g, TileArgs a, int guarded) {
+    extern __shared__ double sm[];                      // tile positions, 3 doubles per atom (stride 24 B)
+    __shared__ uint32_t s_off[kTileCellsMax + 1];
+    __shared__ uint32_t s_src[kTileCellsMax];
+    __shared__ uint32_t s_hstart[kHomeRowsMax + 1];     // prefix of home atoms per home x-row
+    if (guarded && a.ctrl->stop) return;
+
+    const unsigned b = blockIdx.x;
+    const TileGeom tg = tile_geometry(b, g);
+    const unsigned W = tg.W, H = tg.H, ntc = W * H * (tg.bd + 2);
+    for (unsigned t = threadIdx.x; t <= ntc; t += blockDim.x) {
+        s_off[t] = g.toff[(size_t)b * (kTileCellsMax + 1) + t];
+        if (t < ntc) s_src[t] = g.tsrc[(size_t)b * kTileCellsMax + t];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned run = 0, q = 0;
+        for (unsigned hz = 1; hz <= tg.bd; ++hz)
+            for (unsigned hy = 1; hy <= tg.bh; ++hy) {
+                const unsigned r = (hz * H + hy) * W;
+                s_hstart[q++] = run;
+                run += s_off[r + 1 + tg.bw] - s_off[r + 1];
+            }
+        for (; q <= kHomeRowsMax; ++q) s_hstart[q] = run;
+    }
+
+    // stage the neighbourhood: one warp per tile cell, asynchronous global->shared copies (LDGSTS), so
+    // no thread waits on a load before issuing the next; x,y,z of an atom are 24 contiguous bytes of the
+    // 32-byte global record and go to the 24-byte shared record as three 8-byte copies
+    {
+        const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+        for (unsigned t = w; t < ntc; t += nw) {
+            const unsigned o = s_off[t], cnt = s_off[t + 1] - o, src = s_src[t];
+            for (unsigned k = lane; k < cnt; k += 32) {
+                const double* gp = reinterpret_cast<const double*>(a.pos + src + k);
+                const unsigned sp = (unsigned)__cvta_generic_to_shared(sm + 3 * (size_t)(o + k));
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(sp), "l"(gp) : "memory");
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(sp + 8), "l"(gp + 1) : "memory");
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(sp + 16), "l"(gp + 2) : "memory");
+            }
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
+    }
+    __syncthreads();
+
+    const unsigned hn = s_hstart[kHomeRowsMax];
+    const int far2_hi = __double2hiint(c.far2);
+    double etot = 0.0;
+    unsigned maxcnt = 0;
+
+    for (unsigned t = threadIdx.x; t < hn; t += blockDim.x) {
+        // home row of this atom -> global slot i and tile-local index li
+        unsigned q = 0;
+#pragma unroll
+        for (int k = 1; k < kHomeRowsMax; ++k) q += (s_hstart[k] <= t) ? 1u : 0u;
+        const unsigned hy = 1 + q % tg.bh, hz = 1 + q / tg.bh;
+        const unsigned rbase = (hz * H + hy) * W;                 // tile cell index of (tx=0, hy, hz)
+        const unsigned li = s_off[rbase + 1] + (t - s_hstart[q]);
+        const unsigned i = s_src[rbase + 1] + (t - s_hstart[q]);
+        const double* pi = sm + 3 * (size_t)li;
+        const double pix = pi[0], piy = pi[1], piz = pi[2];
+        double ax = 0.0, ay = 0.0, az = 0.0, e = 0.0;
+        unsigned nacc = 0, cnt = 0;
+
+#define LJ_TILE_PAIR(J)                                                                     \
+        {                                                                                   \
+            const double* pj = sm + 3 * (size_t)(J);                                        \
+            double dx = pix - pj[0], dy = piy - pj[1], dz = piz - pj[2];                    \
+            double d2 = fma(dz, dz, fma(dy, dy, dx * dx));                                  \
+            if (maybe_wrapped(d2, far2_hi)) {                                               \
+                dx = min_image(dx, c.L, c.halfL); dy = min_image(dy, c.L, c.halfL);         \
+                dz = min_image(dz, c.L, c.halfL);                                           \
+                d2 = fma(dz, dz, fma(dy, dy, dx * dx));                                     \
+            }                                                                               \
+            if (d2 < c.rc2) {                                                               \
+                const double fr = lj_pair(d2, c.sigma2, e);                                 \
+                ax = fma(fr, dx, ax); ay = fma(fr, dy, ay); az = fma(fr, dz, az);           \
+                ++nacc;                                                                     \
+            }                                                                               \
+        }
+
+        if (MODE == TILE_FORCE_LIST) {
+            // Branch-free groups of four entries: all twelve shared-memory loads and the four
+            // distance evaluations are issued back to back and the Lennard-Jones term is evaluated
+            // for every entry, accumulated under a predicate.  (With 32 lanes and ~60 % of the entries
+            // inside the cutoff a warp would execute the term for practically every entry anyway;
+            // without the branches the four dependent chains overlap.)  The only branch left is the
+            // rare minimum-image fix-up for pairs that straddle the box.  List quads (8 entries) are
+            // fetched one iteration ahead with a single 128-bit load.
+            const unsigned n = a.nl_count[i];
+            const uint4* __restrict__ row = reinterpret_cast<const uint4*>(a.nl32) + ((size_t)(i >> 5) * a.capq) * 32 + (i & 31u);
+            const unsigned nq = (n + 7) >> 3;
+            const uint32_t selfw = li | (li << 16);
+            uint4 cur = make_uint4(selfw, selfw, selfw, selfw);
+            if (nq > 0) cur = __ldg(row);
+            for (unsigned q = 0; q < nq; ++q) {
+                uint4 nxt = make_uint4(selfw, selfw, selfw, selfw);
+                if (q + 1 < nq) nxt = __ldg(row + (size_t)(q + 1) * 32);
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const uint32_t w0 = half ? cur.z : cur.x, w1 = half ? cur.w : cur.y;
+                    unsigned jj[4] = { w0 & 0xffffu, w0 >> 16, w1 & 0xffffu, w1 >> 16 };
+                    double dx[4], dy[4], dz[4], d2[4];
+                    int far = 0;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const double* pj = sm + 3 * (size_t)jj[u];
+                        dx[u] = pix - pj[0]; dy[u] = piy - pj[1]; dz[u] = piz - pj[2];
+                        d2[u] = fma(dz[u], dz[u], fma(dy[u], dy[u], dx[u] * dx[u]));
+                        far = max(far, __double2hiint(d2[u]));
+                    }
+                    if (far >= far2_hi) {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if (maybe_wrapped(d2[u], far2_hi)) {
+                                dx[u] = min_image(dx[u], c.L, c.halfL); dy[u] = min_image(dy[u], c.L, c.halfL);
+                                dz[u] = min_image(dz[u], c.L, c.halfL);
+                                d2[u] = fma(dz[u], dz[u], fma(dy[u], dy[u], dx[u] * dx[u]));
+                            }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        // padding entries point at the atom itself (d2 == 0): excluded by index
+                        const bool in = (d2[u] < c.rc2) && (jj[u] != li);
+                        const double inv = fast_rcp(d2[u]);
+                        const double s2 = UNIT_SIGMA ? inv : c.sigma2 * inv;
+                        const double s6 = s2 * s2 * s2;
+                        const double t = fma(s6, s6, -s6);          // s12 - s6
+                        const double fr = fma(s6, s6, t) * inv;     // (2 s12 - s6) / d2
+                        if (in) {
+                            e += t;
+                            ax = fma(fr, dx[u], ax); ay = fma(fr, dy[u], ay); az = fma(fr, dz[u], az);
+                            ++nacc;
+                        }
+                    }
+                }
+                cur = nxt;
+            }
+        } else {
+            // home cell of this atom along x, then the 3x3 x-rows around it: 3 consecutive tile cells each
+            unsigned h = 0;
+            while (h + 1 < tg.bw && s_off[rbase + 2 + h] <= li) ++h;
+            for (unsigned rz = hz - 1; rz <= hz + 1; ++rz)
+            for (unsigned ry = hy - 1; ry <= hy + 1; ++ry) {
+                const unsigned r = (rz * H + ry) * W + h;
+                const unsigned j0 = s_off[r], j1 = s_off[r + 3];
+                for (unsigned j = j0; j < j1; ++j) {
+                    if (MODE == TILE_FORCE_CELL) {
+                        if (j != li) LJ_TILE_PAIR(j)
+                    } else {
+                        const double* pj = sm + 3 * (size_t)j;
+                        double dx = pix - pj[0], dy = piy - pj[1], dz = piz - pj[2];
+                        double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
+                        if (maybe_wrapped(d2, far2_hi)) {
+                            dx = min_image(dx, c.L, c.halfL); dy = min_image(dy, c.L, c.halfL);
+                            dz = min_image(dz, c.L, c.halfL);
+                            d2 = fma(dz, dz, fma(dy, dy, dx * dx));
+                        }
+                        if (d2 <= c.list_cut2 && j != li) {
+                            if (MODE == TILE_LIST_FILL && cnt < 8 * a.capq)
+                                reinterpret_cast<unsigned short*>(a.nl32)[nl16_index(i, cnt, a.capq)] = (unsigned short)j;
+                            ++cnt;
+                        }
+                    }
+                }
+            }
+        }
+#undef LJ_TILE_PAIR
+
+        if (MODE == TILE_FORCE_LIST || MODE == TILE_FORCE_CELL) {
+            a.fx[i] = ax * c.prefctr; a.fy[i] = ay * c.prefctr; a.fz[i] = az * c.prefctr;
+            etot += fma(-(double)nacc, c.ecut, e);
+        } else {
+            if (MODE == TILE_LIST_FILL)                     // the unused tail of the last quad points at the atom itself
+                for (unsigned k = min(cnt, 8 * a.capq); k & 7u; ++k)
+                    reinterpret_cast<unsigned short*>(a.nl32)[nl16_index(i, k, a.capq)] = (unsigned short)li;
+            a.nl_count[i] = MODE == TILE_LIST_FILL ? min(cnt, 8 * a.capq) : cnt;
+            maxcnt = max(maxcnt, cnt);
+        }
+    }
+
+    if (MODE == TILE_FORCE_LIST || MODE == TILE_FORCE_CELL) {
+        // one partial per warp (no block barrier: a finished warp frees its issue slots at once)
+        const double e = warp_sum(etot);
+        if ((threadIdx.x & 31) == 0) a.partial_epot[(size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)] = e;
+    } else {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) maxcnt = max(maxcnt, __shfl_xor_sync(0xffffffffu, maxcnt, o));
+        if ((threadIdx.x & 31) == 0 && maxcnt) {
+            atomicMax(&a.ctrl->max_count, maxcnt);
+            if (MODE == TILE_LIST_FILL && maxcnt > 8 * a.capq) atomicExch(&a.ctrl->overflow, 1u);
+        }
+    }
+}
+
+} // namespace ljgpu
