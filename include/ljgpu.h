@@ -179,6 +179,23 @@ int ljgpu_reset_timers(ljgpu_sim* s);
 int ljgpu_get_layout(ljgpu_sim* s, int32_t* force_kernel, uint32_t* cells_per_axis,
                      uint32_t* list_capacity, uint64_t* n_ghosts);
 
+/* ---- several devices: z-slab decomposition ------------------------------------------------------
+ * The box is cut into `world` slabs of whole cell layers along z (the slowest index of the reference's
+ * cell id, lennardjonessimulation.cpp:476); device `rank` integrates the atoms of its layers and keeps
+ * one halo layer from each ring neighbour.  Per step: boundary-layer positions to both neighbours
+ * (NCCL send/recv over NVLink) and one 4-double all-reduce (kinetic sums for the thermostat,
+ * potential energy, re-binning vote); at re-binning atoms that crossed a slab face migrate.
+ * One process per device.  Every call on a slab handle is COLLECTIVE: all ranks make the same calls in
+ * the same order.  Rank 0 obtains the id, the caller distributes it (e.g. torch.distributed, a file).
+ * Every rank passes the WHOLE initial state; getters return the whole system on every rank. */
+int ljgpu_slab_layers(uint32_t cells_per_axis, int world, int rank, uint32_t* first_layer, uint32_t* end_layer);
+int ljgpu_slab_unique_id(void* id128);
+int ljgpu_create_slab(const ljgpu_params* p, int rank, int world, const void* nccl_unique_id,
+                      const double* x, const double* y, const double* z,
+                      const double* vx, const double* vy, const double* vz, ljgpu_sim** out);
+int ljgpu_slab_info(ljgpu_sim* s, int32_t* rank, int32_t* world, uint32_t* first_layer, uint32_t* n_layers,
+                    uint64_t* atoms_owned, uint64_t* atoms_halo);
+
 /* Mean and maximum Verlet-list length per atom of the current list (0 on the other paths). */
 int ljgpu_get_list_stats(ljgpu_sim* s, double* mean_length, uint32_t* max_length);
 

@@ -20,6 +20,7 @@ EXPORTED_SYMBOLS = [
     "ljgpu_maxwell_boltzmann", "ljgpu_get_cell_ids", "ljgpu_get_neighbor_counts",
     "ljgpu_write_movie_frame", "ljgpu_set_profiling", "ljgpu_get_timers", "ljgpu_reset_timers",
     "ljgpu_get_layout", "ljgpu_step_n_timed", "ljgpu_get_list_stats", "ljgpu_alloc_host", "ljgpu_free_host",
+    "ljgpu_slab_layers", "ljgpu_slab_unique_id", "ljgpu_create_slab", "ljgpu_slab_info",
 ]
 
 
@@ -93,6 +94,11 @@ def load_library():
     lib.ljgpu_get_list_stats.argtypes = [vp, dp, C.POINTER(C.c_uint32)]
     lib.ljgpu_alloc_host.argtypes = [C.c_size_t, C.POINTER(vp)]
     lib.ljgpu_free_host.argtypes = [vp]
+    lib.ljgpu_slab_layers.argtypes = [C.c_uint32, C.c_int, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    lib.ljgpu_slab_unique_id.argtypes = [vp]
+    lib.ljgpu_create_slab.argtypes = [C.POINTER(LJParams), C.c_int, C.c_int, vp] + [vp] * 6 + [C.POINTER(vp)]
+    lib.ljgpu_slab_info.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_uint32),
+                                    C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     _LIB = lib
     return lib
 
@@ -144,6 +150,23 @@ class LennardJonesParameters:
                         g("rcut"), g("epsilon"), g("tau"), g("shell"), g("stepsize"), device, 0)
 
 
+def slab_layers(cells_per_axis, world, rank):
+    """[first, end) cell layers along z that `rank` of `world` owns (ljgpu_slab_layers)."""
+    lo, hi = C.c_uint32(), C.c_uint32()
+    rc = load_library().ljgpu_slab_layers(cells_per_axis, world, rank, C.byref(lo), C.byref(hi))
+    if rc != 0:
+        raise LJGpuError(f"ljgpu_slab_layers failed ({rc})")
+    return lo.value, hi.value
+
+
+def slab_unique_id():
+    """128-byte NCCL id, to be created on rank 0 and handed to every rank."""
+    buf = C.create_string_buffer(128)
+    lib = load_library()
+    _check(lib, lib.ljgpu_slab_unique_id(buf))
+    return buf.raw
+
+
 def host_rng_reset():
     load_library().ljgpu_host_rng_reset()
 
@@ -171,7 +194,8 @@ def maxwell_boltzmann(kT, mass, n, nbins=100, vmax=10.0):
 class LennardJonesSimulation:
     """Same public surface as the reference class (lennardjonessimulation.h:113-155), GPU-backed."""
 
-    def __init__(self, params, state=None, force_kernel=KERNEL_AUTO, device=-1):
+    def __init__(self, params, state=None, force_kernel=KERNEL_AUTO, device=-1, slab=None):
+        """slab = (rank, world, nccl_unique_id_bytes) selects the multi-device z-slab path (collective)."""
         self._lib = load_library()
         self._h = C.c_void_p()
         self.params = params
@@ -182,7 +206,13 @@ class LennardJonesSimulation:
         state = [np.ascontiguousarray(a, dtype=np.float64) for a in state]
         if len(state) != 6 or any(a.shape != (self.n,) for a in state):
             raise ValueError("state must be six arrays of nr_particles float64")
-        _check(self._lib, self._lib.ljgpu_create(C.byref(self._struct), *[_ptr(a) for a in state], C.byref(self._h)))
+        if slab is None:
+            _check(self._lib, self._lib.ljgpu_create(C.byref(self._struct), *[_ptr(a) for a in state], C.byref(self._h)))
+        else:
+            rank, world, uid = slab
+            idbuf = C.create_string_buffer(bytes(uid), 128)
+            _check(self._lib, self._lib.ljgpu_create_slab(C.byref(self._struct), rank, world, idbuf,
+                                                          *[_ptr(a) for a in state], C.byref(self._h)))
 
     def close(self):
         if self._h:
@@ -311,6 +341,13 @@ class LennardJonesSimulation:
 
     def reset_timers(self):
         _check(self._lib, self._lib.ljgpu_reset_timers(self._h))
+
+    def slab_info(self):
+        r, w, lo, nl, own, halo = C.c_int32(), C.c_int32(), C.c_uint32(), C.c_uint32(), C.c_uint64(), C.c_uint64()
+        _check(self._lib, self._lib.ljgpu_slab_info(self._h, C.byref(r), C.byref(w), C.byref(lo), C.byref(nl),
+                                                    C.byref(own), C.byref(halo)))
+        return {"rank": r.value, "world": w.value, "first_layer": lo.value, "n_layers": nl.value,
+                "atoms_owned": own.value, "atoms_halo": halo.value}
 
     def get_layout(self):
         k, nc, cap, g = C.c_int32(), C.c_uint32(), C.c_uint32(), C.c_uint64()

@@ -66,6 +66,10 @@ struct LJConst {
     double cell_edge;             // L / cells_per_axis                         (.cpp:455-457)
     unsigned nc;                  // cells per axis                             (.cpp:447-453)
     unsigned n;                   // atoms owned by this device
+    // z-slab decomposition (slab == 0: one device owns the whole box)
+    unsigned slab;                // 1 on the multi-device path
+    unsigned zlo;                 // first cell layer (global iz) owned by this device
+    unsigned nzl;                 // number of owned cell layers
 };
 
 // Device-resident control block: accumulators, published energies, batch bookkeeping.
@@ -81,6 +85,7 @@ struct StepCtrl {
     unsigned int max_tile;        // largest shared-memory tile (atoms) over all home blocks
     unsigned int max_home;        // most home atoms in one block
     unsigned long long hist_head; // energy history ring: entries written so far
+    double red[4];                // slab path: {epot_sum, ekin_sum, pred_sum, rebuild votes}, local then all-reduced
 };
 
 constexpr int kHistCap = 4096;    // entries in the energy history ring

@@ -354,8 +354,99 @@ wrap_key_kernel(LJConst c, const double4* __restrict__ pos, double4* __restrict_
     const unsigned ix = cell_coord(p.x, c.cell_edge, c.nc);
     const unsigned iy = cell_coord(p.y, c.cell_edge, c.nc);
     const unsigned iz = cell_coord(p.z, c.cell_edge, c.nc);
-    keys[i] = iz * c.nc * c.nc + iy * c.nc + ix;
+    if (!c.slab) {
+        keys[i] = iz * c.nc * c.nc + iy * c.nc + ix;
+    } else {
+        // local table: layer 0 = lower halo, 1..nzl = owned, nzl+1 = upper halo; atoms that left the slab
+        // get the two keys past the table (down / up movers) and are handed to the neighbour device
+        const unsigned lz = (iz + c.nc - c.zlo) % c.nc;
+        const unsigned ncell_loc = c.nc * c.nc * (c.nzl + 2);
+        if (lz < c.nzl) keys[i] = (lz + 1) * c.nc * c.nc + iy * c.nc + ix;
+        else keys[i] = (lz == c.nzl) ? ncell_loc + 1 : ncell_loc;        // one layer above : anything else is "below"
+    }
     vals[i] = i;
+}
+
+// ---- slab path: atom migration, halo cell table, split finalize -------------------------------------
+constexpr int kMoverDoubles = 11;      // x y z vx vy vz fx fy fz orig(as bits) pad
+__global__ void __launch_bounds__(kBlock)
+pack_movers_kernel(unsigned first, unsigned cnt, const double4* __restrict__ pos,
+                   const double* __restrict__ vx, const double* __restrict__ vy, const double* __restrict__ vz,
+                   const double* __restrict__ fx, const double* __restrict__ fy, const double* __restrict__ fz,
+                   const uint32_t* __restrict__ orig, double* __restrict__ buf) {
+    const unsigned k = blockIdx.x * kBlock + threadIdx.x;
+    if (k >= cnt) return;
+    const unsigned i = first + k;
+    const double4 p = pos[i];
+    double* b = buf + (size_t)k * kMoverDoubles;
+    b[0] = p.x; b[1] = p.y; b[2] = p.z;
+    b[3] = vx[i]; b[4] = vy[i]; b[5] = vz[i];
+    b[6] = fx[i]; b[7] = fy[i]; b[8] = fz[i];
+    b[9] = __longlong_as_double((long long)orig[i]); b[10] = 0.0;
+}
+
+__global__ void __launch_bounds__(kBlock)
+unpack_movers_kernel(unsigned first, unsigned cnt, const double* __restrict__ buf, double4* __restrict__ pos,
+                     double* __restrict__ vx, double* __restrict__ vy, double* __restrict__ vz,
+                     double* __restrict__ fx, double* __restrict__ fy, double* __restrict__ fz,
+                     uint32_t* __restrict__ orig) {
+    const unsigned k = blockIdx.x * kBlock + threadIdx.x;
+    if (k >= cnt) return;
+    const unsigned i = first + k;
+    const double* b = buf + (size_t)k * kMoverDoubles;
+    pos[i] = make_double4(b[0], b[1], b[2], 0.0);
+    vx[i] = b[3]; vy[i] = b[4]; vz[i] = b[5];
+    fx[i] = b[6]; fy[i] = b[7]; fz[i] = b[8];
+    orig[i] = (uint32_t)__double_as_longlong(b[9]);
+}
+
+// cell table of one halo layer: counts received from the neighbour, slots appended after the owned atoms
+__global__ void __launch_bounds__(kBlock)
+halo_cells_kernel(unsigned ncell_layer, unsigned layer_first_cell, unsigned base_slot,
+                  const uint32_t* __restrict__ counts, const uint32_t* __restrict__ offsets,
+                  uint32_t* __restrict__ cstart, uint32_t* __restrict__ ccount) {
+    const unsigned k = blockIdx.x * kBlock + threadIdx.x;
+    if (k >= ncell_layer) return;
+    cstart[layer_first_cell + k] = base_slot + offsets[k];
+    ccount[layer_first_cell + k] = counts[k];
+}
+
+// local part of the step's reductions (fixed order) -> ctrl->red, to be all-reduced over the devices
+__global__ void __launch_bounds__(kFinalizeThreads)
+slab_reduce_kernel(LJConst c, StepCtrl* __restrict__ ctrl,
+                   const double* __restrict__ partial_epot, unsigned nb_epot,
+                   const double* __restrict__ partial_ekin, const double* __restrict__ partial_pred, unsigned nb_kick) {
+    __shared__ double red[32];
+    double se = strided_sum(partial_epot, nb_epot);
+    double sk = partial_ekin ? strided_sum(partial_ekin, nb_kick) : 0.0;
+    double sp = strided_sum(partial_pred, nb_kick);
+    se = block_sum(se, red);
+    sk = block_sum(sk, red);
+    sp = block_sum(sp, red);
+    if (threadIdx.x == 0) {
+        ctrl->red[0] = se; ctrl->red[1] = sk; ctrl->red[2] = sp;
+        ctrl->red[3] = (__longlong_as_double((long long)ctrl->maxdisp2) > c.disp_thresh) ? 1.0 : 0.0;
+        ctrl->maxdisp2 = 0ull;
+    }
+}
+
+// what: 0 = full step (energies, history, rebuild flag), 1 = constructor (epot only), 2 = predict (pred_sum only)
+__global__ void slab_publish_kernel(LJConst c, StepCtrl* __restrict__ ctrl, HistEntry* __restrict__ hist, unsigned step, int what) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (what == 2) { ctrl->pred_sum = ctrl->red[2]; return; }
+    const double se = ctrl->red[0];
+    const double epot = xmul(xmul(xmul(se, 4.0), c.epsilon), 0.5);
+    ctrl->epot_sum = se;
+    if (what == 1) { ctrl->epot = epot; return; }
+    if (ctrl->stop) return;
+    const double ekin = xmul(xmul(0.5, c.mass), ctrl->red[1]);
+    ctrl->pred_sum = ctrl->red[2];
+    ctrl->ekin = ekin; ctrl->epot = epot; ctrl->etot = xadd(ekin, epot);
+    HistEntry& h = hist[ctrl->hist_head % kHistCap];
+    h.ekin = ekin; h.epot = epot; h.step = step; h.pad = 0;
+    ctrl->hist_head += 1;
+    ctrl->steps_done += 1;
+    if (ctrl->red[3] > 0.0) ctrl->stop = 1;
 }
 
 __global__ void __launch_bounds__(kBlock)

@@ -3,6 +3,7 @@
 // Path replaced: class LennardJonesSimulation, /root/reference/src/simulator/lennardjonessimulation.{h,cpp}
 // (".cpp"/".h" below).  No CPU fallback: every entry point fails with LJGPU_ECUDA when there is no device.
 #include "lj_tile.cuh"
+#include "lj_nccl.h"
 #include "../../include/ljgpu.h"
 
 #include <algorithm>
@@ -40,6 +41,31 @@ enum Stage { ST_PREDICT = 0, ST_KICK_DRIFT, ST_GHOST, ST_FORCE, ST_KICK2, ST_REB
 template <class T>
 void dfree(T*& p) { if (p) { cudaFree(p); p = nullptr; } }
 
+#define NCK(call)                                                                                  \
+    do {                                                                                           \
+        int r__ = (call);                                                                          \
+        if (r__ != 0)                                                                              \
+            throw LjError(LJGPU_ENCCL, std::string(#call) + ": " + ljnccl::api().GetErrorString(r__)); \
+    } while (0)
+
+// z-slab decomposition state: cell layers [zlo, zlo+nzl) of the global grid belong to
+// this device; one halo layer from each ring neighbour.
+struct Slab {
+    bool on = false;
+    int rank = 0, world = 1, down = 0, up = 0;
+    ljnccl::Comm comm = nullptr;
+    unsigned zlo = 0, nzl = 0;
+    unsigned c_lo = 0, c_hi = 0;          // atoms in my first / last owned layer (what I send every step)
+    unsigned h_lo = 0, h_hi = 0;          // atoms in my lower / upper halo layer (what I receive every step)
+    double* sendbuf[2] = {nullptr, nullptr};
+    double* recvbuf[2] = {nullptr, nullptr};
+    size_t mover_cap = 0;                 // atoms per mover buffer
+    uint32_t* hcount[2] = {nullptr, nullptr};   // per-cell counts of the halo layers as received
+    uint32_t* hoff[2] = {nullptr, nullptr};     // their exclusive scans
+    uint32_t* xchg = nullptr;             // device scratch for count exchanges (8 words)
+    uint32_t* h_xchg = nullptr;           // pinned mirror
+};
+
 } // namespace
 
 struct ljgpu_sim {
@@ -49,7 +75,13 @@ struct ljgpu_sim {
     int device = 0;
     cudaStream_t st = nullptr;
     LJConst c{};
-    unsigned n = 0, nc = 0, ncell = 0;
+    unsigned n = 0;                 // atoms owned by this device
+    unsigned nglobal = 0;           // atoms of the whole system
+    unsigned nc = 0;                // cells per axis (global)
+    unsigned ncz = 0;               // cell layers of the local table
+    unsigned ncell = 0;             // cells of the local table (+2 mover bins on a slab)
+    size_t cap_atoms = 0, pos_cap = 0;
+    Slab slab;
 
     // state, device order (cell-sorted on the list paths, caller order on the all-pairs path)
     double4* pos = nullptr; double4* pos_tmp = nullptr;
@@ -72,7 +104,7 @@ struct ljgpu_sim {
 
     // reductions
     double *partial_epot = nullptr, *partial_ekin = nullptr, *partial_pred = nullptr;
-    unsigned nb_atoms = 0, nb_force = 0;
+    unsigned nb_force = 0;
     double* apf[3] = {nullptr, nullptr, nullptr}; unsigned nsplit = 1, jchunk = 0;
 
     StepCtrl* ctrl = nullptr; StepCtrl* h_ctrl = nullptr;
@@ -129,15 +161,26 @@ struct ljgpu_sim {
     }
 
     bool list_mode() const { return mode != LJGPU_KERNEL_ALLPAIRS; }
+    unsigned nb_atoms() const { return std::max(1u, cdiv(n, kBlock)); }
+    TileGrid tile_grid() const {
+        return TileGrid{nc, ncz, slab.on ? 0u : 1u, slab.on ? 1u : 0u, slab.on ? slab.nzl : nc,
+                        nbx, nby, nbz, nblocks_tile, tsrc, toff};
+    }
 
     void setup_constants();
     void allocate();
     void upload_state(const double* x, const double* y, const double* z,
                       const double* vx, const double* vy, const double* vz);
+    void sort_by_cell();
+    void migrate();
+    void halo_setup();
+    void halo_exchange();
+    void allreduce_red();
     void rebuild();
     void build_list();
-    void launch_force(bool guarded);
+    void launch_force(bool timed);
     void initial_forces();
+    void finalize_epot_only();
     void launch_predict(double dt);
     void enqueue_step(unsigned step, double dt);
     void run_steps(unsigned first, unsigned nsteps, double dt);
@@ -151,6 +194,7 @@ struct ljgpu_sim {
 ljgpu_sim::~ljgpu_sim() {
     cudaSetDevice(device);
     if (st) cudaStreamSynchronize(st);
+    if (slab.comm) ljnccl::api().CommDestroy(slab.comm);
     dfree(pos); dfree(pos_tmp);
     for (int k = 0; k < 3; ++k) { dfree(dij[k]); dfree(v[k]); dfree(f[k]); dfree(v_alt[k]); dfree(f_alt[k]); dfree(apf[k]); }
     dfree(orig); dfree(orig_alt); dfree(keys); dfree(vals);
@@ -158,6 +202,9 @@ ljgpu_sim::~ljgpu_sim() {
     dfree(nl); dfree(nl_count); dfree(tsrc); dfree(toff);
     dfree(partial_epot); dfree(partial_ekin); dfree(partial_pred);
     dfree(ctrl); dfree(hist); dfree(out3); dfree(out_u32); dfree(hist_counts);
+    for (int k = 0; k < 2; ++k) { dfree(slab.sendbuf[k]); dfree(slab.recvbuf[k]); dfree(slab.hcount[k]); dfree(slab.hoff[k]); }
+    dfree(slab.xchg);
+    if (slab.h_xchg) cudaFreeHost(slab.h_xchg);
     if (h_ctrl) cudaFreeHost(h_ctrl);
     sort_scratch_free(scr);
     for (auto& q : pending) { cudaEventDestroy(q.a); cudaEventDestroy(q.b); }
@@ -185,105 +232,270 @@ void ljgpu_sim::setup_constants() {
     ncells = std::max(1u, ncells);
     c.nc = ncells;
     c.cell_edge = L / (double)ncells;                                   // .cpp:455-457
-    c.n = (unsigned)p.nr_particles;
-    c.dt_over_tau = 0.0;
-    nc = ncells; ncell = nc * nc * nc;
+    c.n = n;
+    c.slab = slab.on ? 1u : 0u; c.zlo = slab.zlo; c.nzl = slab.nzl;
+    nc = ncells;
+    nglobal = (unsigned)p.nr_particles;
+    ncz = slab.on ? slab.nzl + 2 : nc;
+    ncell = nc * nc * ncz + (slab.on ? 2u : 0u);
 }
 
 void ljgpu_sim::allocate() {
-    const size_t N = n;
-    nb_atoms = cdiv(N, kBlock);
-    CK(cudaMalloc(&pos, N * sizeof(double4)));
-    CK(cudaMemset(pos, 0, N * sizeof(double4)));
-    for (int k = 0; k < 3; ++k) {
-        CK(cudaMalloc(&v[k], N * 8)); CK(cudaMalloc(&f[k], N * 8));
-        CK(cudaMemset(f[k], 0, N * 8));
+    const size_t N = nglobal;
+    if (slab.on) {
+        cap_atoms = N / slab.world + N / slab.world / 4 + 65536;
+        const size_t layer = N / nc + 1;
+        pos_cap = cap_atoms + 2 * (layer + layer / 2 + 4096);
+    } else {
+        cap_atoms = N; pos_cap = N;
     }
-    CK(cudaMalloc(&orig, N * 4));
+    const size_t A = cap_atoms;
+    const unsigned nbmax = cdiv(A, kBlock);
+    CK(cudaMalloc(&pos, pos_cap * sizeof(double4)));
+    CK(cudaMemset(pos, 0, pos_cap * sizeof(double4)));
+    for (int k = 0; k < 3; ++k) {
+        CK(cudaMalloc(&v[k], A * 8)); CK(cudaMalloc(&f[k], A * 8));
+        CK(cudaMemset(f[k], 0, A * 8));
+    }
+    CK(cudaMalloc(&orig, A * 4));
     CK(cudaMalloc(&ctrl, sizeof(StepCtrl))); CK(cudaMemset(ctrl, 0, sizeof(StepCtrl)));
     CK(cudaMallocHost(&h_ctrl, sizeof(StepCtrl))); std::memset(h_ctrl, 0, sizeof(StepCtrl));
     CK(cudaMalloc(&hist, sizeof(HistEntry) * kHistCap)); CK(cudaMemset(hist, 0, sizeof(HistEntry) * kHistCap));
     CK(cudaMalloc(&out3, 3 * N * 8));
     CK(cudaMalloc(&out_u32, N * 4));
     CK(cudaMalloc(&hist_counts, kMaxBins * sizeof(unsigned long long)));
-    CK(cudaMalloc(&partial_ekin, (size_t)nb_atoms * 8));
-    CK(cudaMalloc(&partial_pred, (size_t)nb_atoms * 8));
+    CK(cudaMalloc(&partial_ekin, (size_t)nbmax * 8));
+    CK(cudaMalloc(&partial_pred, (size_t)nbmax * 8));
 
     if (list_mode()) {
-        CK(cudaMalloc(&pos_tmp, N * sizeof(double4)));
+        CK(cudaMalloc(&pos_tmp, A * sizeof(double4)));
         for (int k = 0; k < 3; ++k) {
-            CK(cudaMalloc(&dij[k], N * 8)); CK(cudaMalloc(&v_alt[k], N * 8)); CK(cudaMalloc(&f_alt[k], N * 8));
+            CK(cudaMalloc(&dij[k], A * 8)); CK(cudaMalloc(&v_alt[k], A * 8)); CK(cudaMalloc(&f_alt[k], A * 8));
         }
-        CK(cudaMalloc(&orig_alt, N * 4));
-        CK(cudaMalloc(&keys, N * 4)); CK(cudaMalloc(&vals, N * 4));
+        CK(cudaMalloc(&orig_alt, A * 4));
+        CK(cudaMalloc(&keys, A * 4)); CK(cudaMalloc(&vals, A * 4));
         CK(cudaMalloc(&cstart, (size_t)ncell * 4)); CK(cudaMalloc(&cend, (size_t)ncell * 4)); CK(cudaMalloc(&ccount, (size_t)ncell * 4));
-        CK(cudaMalloc(&nl_count, N * 4));
-        nbx = cdiv(nc, kTileBX); nby = cdiv(nc, kTileBY); nbz = cdiv(nc, kTileBZ);
+        CK(cudaMalloc(&nl_count, A * 4));
+        const unsigned nhz = slab.on ? slab.nzl : nc;
+        nbx = cdiv(nc, kTileBX); nby = cdiv(nc, kTileBY); nbz = cdiv(nhz, kTileBZ);
         nblocks_tile = nbx * nby * nbz;
         CK(cudaMalloc(&tsrc, (size_t)nblocks_tile * kTileCellsMax * 4));
         CK(cudaMalloc(&toff, (size_t)nblocks_tile * (kTileCellsMax + 1) * 4));
-        nb_force = nblocks_tile * 16;          // one partial per warp, up to 512 threads per CTA
+        nb_force = nblocks_tile * (LJ_TILE_MAXTHREADS / 32);       // one partial per warp
     } else {
         // j splits: enough blocks to fill 148 SMs a few times over, each split at least 64 atoms wide
-        const unsigned want = std::max(1u, (4u * 148u + nb_atoms - 1) / nb_atoms);
+        const unsigned nba = cdiv(N, kBlock);
+        const unsigned want = std::max(1u, (4u * 148u + nba - 1) / nba);
         nsplit = std::max(1u, std::min(want, (unsigned)((N + 63) / 64)));
         jchunk = cdiv(N, nsplit);
         nsplit = cdiv(N, jchunk);
         for (int k = 0; k < 3; ++k) CK(cudaMalloc(&apf[k], (size_t)nsplit * N * 8));
-        nb_force = nb_atoms * nsplit;
+        nb_force = nba * nsplit;
     }
     CK(cudaMalloc(&partial_epot, (size_t)std::max(nb_force, 1u) * 8));
+
+    if (slab.on) {
+        const size_t layer = N / nc + 1;
+        slab.mover_cap = layer / 4 + 4096;
+        for (int k = 0; k < 2; ++k) {
+            CK(cudaMalloc(&slab.sendbuf[k], slab.mover_cap * kMoverDoubles * 8));
+            CK(cudaMalloc(&slab.recvbuf[k], slab.mover_cap * kMoverDoubles * 8));
+            CK(cudaMalloc(&slab.hcount[k], (size_t)nc * nc * 4));
+            CK(cudaMalloc(&slab.hoff[k], (size_t)nc * nc * 4));
+        }
+        CK(cudaMalloc(&slab.xchg, 16 * 4));
+        CK(cudaMallocHost(&slab.h_xchg, 16 * 4));
+    }
+}
+
+// Host-side owner test of the slab path: the cell layer of a wrapped coordinate, same arithmetic as
+// wrap_coord + cell_coord on the device (this translation unit is built without FMA contraction on the host).
+static unsigned host_layer(double z, double L, double invL, double edge, unsigned ncells) {
+    const double w = z - L * std::floor(z * invL);
+    unsigned i = (unsigned)(w / edge);
+    return i < ncells - 1 ? i : ncells - 1;
 }
 
 void ljgpu_sim::upload_state(const double* x, const double* y, const double* z,
                              const double* vx, const double* vy, const double* vz) {
-    const size_t N = n, B = N * 8;
-    CK(cudaMemcpyAsync(out3, x, B, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(out3 + N, y, B, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(out3 + 2 * N, z, B, cudaMemcpyHostToDevice, st));
-    import_state_kernel<<<nb_atoms, kBlock, 0, st>>>(n, out3, out3 + N, out3 + 2 * N, pos, orig);
-    check_launch("import_state");
-    CK(cudaMemcpyAsync(v[0], vx, B, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(v[1], vy, B, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(v[2], vz, B, cudaMemcpyHostToDevice, st));
-    for (int k = 0; k < 3; ++k) CK(cudaMemsetAsync(f[k], 0, B, st));
     CK(cudaMemsetAsync(ctrl, 0, sizeof(StepCtrl), st));
     pred_valid = false;
     since_rebuild = 0;
+    if (!slab.on) {
+        const size_t N = nglobal, B = N * 8;
+        n = nglobal; c.n = n;
+        CK(cudaMemcpyAsync(out3, x, B, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(out3 + N, y, B, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(out3 + 2 * N, z, B, cudaMemcpyHostToDevice, st));
+        import_state_kernel<<<nb_atoms(), kBlock, 0, st>>>(n, out3, out3 + N, out3 + 2 * N, pos, orig);
+        check_launch("import_state");
+        CK(cudaMemcpyAsync(v[0], vx, B, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(v[1], vy, B, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(v[2], vz, B, cudaMemcpyHostToDevice, st));
+        for (int k = 0; k < 3; ++k) CK(cudaMemsetAsync(f[k], 0, B, st));
+        return;
+    }
+    // slab: every rank is handed the whole system and keeps the atoms of its cell layers
+    std::vector<double> hx, hy, hz, hvx, hvy, hvz;
+    std::vector<uint32_t> ho;
+    for (uint32_t i = 0; i < nglobal; ++i) {
+        const unsigned lz = (host_layer(z[i], c.L, c.invL, c.cell_edge, nc) + nc - slab.zlo) % nc;
+        if (lz >= slab.nzl) continue;
+        hx.push_back(x[i]); hy.push_back(y[i]); hz.push_back(z[i]);
+        hvx.push_back(vx[i]); hvy.push_back(vy[i]); hvz.push_back(vz[i]);
+        ho.push_back(i);
+    }
+    n = (unsigned)ho.size(); c.n = n;
+    if (n > cap_atoms) throw LjError(LJGPU_ESTATE, "slab holds more atoms than its capacity (very inhomogeneous start state)");
+    const size_t B = (size_t)n * 8;
+    // stage through out3 (3 N doubles): x y z, then import; velocities straight into place
+    CK(cudaMemcpy(out3, hx.data(), B, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(out3 + n, hy.data(), B, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(out3 + 2 * (size_t)n, hz.data(), B, cudaMemcpyHostToDevice));
+    import_state_kernel<<<nb_atoms(), kBlock, 0, st>>>(n, out3, out3 + n, out3 + 2 * (size_t)n, pos, orig);
+    check_launch("import_state");
+    CK(cudaMemcpyAsync(orig, ho.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(v[0], hvx.data(), B, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(v[1], hvy.data(), B, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(v[2], hvz.data(), B, cudaMemcpyHostToDevice, st));
+    for (int k = 0; k < 3; ++k) CK(cudaMemsetAsync(f[k], 0, B, st));
+    CK(cudaStreamSynchronize(st));        // host vectors go out of scope
 }
 
-// Re-binning: wrap (.cpp:419-435), cell keys (.cpp:467-478), stable radix sort, permutation of the
-// whole state, cell table, dij = 0 (.cpp:484-486), and on the Verlet path the list itself (.cpp:480-550).
+// wrap (.cpp:419-435), cell keys (.cpp:467-478), stable radix sort, permutation of the whole state,
+// cell table of the owned atoms.
+void ljgpu_sim::sort_by_cell() {
+    wrap_key_kernel<<<nb_atoms(), kBlock, 0, st>>>(c, pos, pos_tmp, keys, vals);
+    check_launch("wrap_key");
+    int bits = 1; while ((1ull << bits) < (unsigned long long)ncell) ++bits;
+    launches += radix_sort_pairs(keys, vals, n, bits, scr, st);
+    permute_kernel<<<nb_atoms(), kBlock, 0, st>>>(n, vals, pos_tmp, pos,
+                                                  v[0], v[1], v[2], f[0], f[1], f[2], orig,
+                                                  v_alt[0], v_alt[1], v_alt[2], f_alt[0], f_alt[1], f_alt[2], orig_alt);
+    check_launch("permute");
+    for (int k = 0; k < 3; ++k) { std::swap(v[k], v_alt[k]); std::swap(f[k], f_alt[k]); }
+    std::swap(orig, orig_alt);
+    CK(cudaMemsetAsync(cstart, 0, (size_t)ncell * 4, st));
+    CK(cudaMemsetAsync(cend, 0, (size_t)ncell * 4, st));
+    if (n) {
+        cell_bounds_kernel<<<nb_atoms(), kBlock, 0, st>>>(n, keys, cstart, cend);
+        check_launch("cell_bounds");
+    }
+    cell_count_kernel<<<cdiv(ncell, kBlock), kBlock, 0, st>>>(ncell, cstart, cend, ccount);
+    check_launch("cell_count");
+}
+
+// Slab path: hand the atoms that left my cell layers to the ring neighbours (they sit at the tail of the
+// sorted state: keys ncell-2 = down, ncell-1 = up), take theirs.  {x,v,f,orig} travel, 88 bytes per atom.
+void ljgpu_sim::migrate() {
+    auto& A = ljnccl::api();
+    uint32_t hc[4];
+    CK(cudaMemcpyAsync(hc, ccount + (ncell - 2), 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(hc + 2, cstart + (ncell - 2), 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const unsigned n_down = hc[0], n_up = hc[1];
+    const unsigned first_down = n_down ? hc[2] : n, first_up = n_up ? hc[3] : n;
+    const unsigned n_stay = n - n_down - n_up;
+    if (n_down > slab.mover_cap || n_up > slab.mover_cap) throw LjError(LJGPU_ESTATE, "too many atoms crossing a slab face");
+    // counts first
+    slab.h_xchg[0] = n_down; slab.h_xchg[1] = n_up;
+    CK(cudaMemcpyAsync(slab.xchg, slab.h_xchg, 8, cudaMemcpyHostToDevice, st));
+    NCK(A.GroupStart());
+    NCK(A.Send(slab.xchg + 0, 1, ljnccl::kUint32, slab.down, slab.comm, st));
+    NCK(A.Send(slab.xchg + 1, 1, ljnccl::kUint32, slab.up, slab.comm, st));
+    NCK(A.Recv(slab.xchg + 2, 1, ljnccl::kUint32, slab.up, slab.comm, st));      // what the upper neighbour sends down to me
+    NCK(A.Recv(slab.xchg + 3, 1, ljnccl::kUint32, slab.down, slab.comm, st));    // what the lower neighbour sends up to me
+    NCK(A.GroupEnd());
+    CK(cudaMemcpyAsync(slab.h_xchg + 2, slab.xchg + 2, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const unsigned from_up = slab.h_xchg[2], from_down = slab.h_xchg[3];
+    if (from_up > slab.mover_cap || from_down > slab.mover_cap) throw LjError(LJGPU_ESTATE, "too many atoms arriving over a slab face");
+    if ((size_t)n_stay + from_up + from_down > cap_atoms) throw LjError(LJGPU_ESTATE, "slab capacity exceeded after migration");
+
+    if (n_down) { pack_movers_kernel<<<cdiv(n_down, kBlock), kBlock, 0, st>>>(first_down, n_down, pos, v[0], v[1], v[2], f[0], f[1], f[2], orig, slab.sendbuf[0]); check_launch("pack_movers"); }
+    if (n_up)   { pack_movers_kernel<<<cdiv(n_up, kBlock), kBlock, 0, st>>>(first_up, n_up, pos, v[0], v[1], v[2], f[0], f[1], f[2], orig, slab.sendbuf[1]); check_launch("pack_movers"); }
+    // data; at least one record per message so both sides always post matching calls
+    NCK(A.GroupStart());
+    NCK(A.Send(slab.sendbuf[0], (size_t)std::max(n_down, 1u) * kMoverDoubles, ljnccl::kFloat64, slab.down, slab.comm, st));
+    NCK(A.Send(slab.sendbuf[1], (size_t)std::max(n_up, 1u) * kMoverDoubles, ljnccl::kFloat64, slab.up, slab.comm, st));
+    NCK(A.Recv(slab.recvbuf[1], (size_t)std::max(from_up, 1u) * kMoverDoubles, ljnccl::kFloat64, slab.up, slab.comm, st));
+    NCK(A.Recv(slab.recvbuf[0], (size_t)std::max(from_down, 1u) * kMoverDoubles, ljnccl::kFloat64, slab.down, slab.comm, st));
+    NCK(A.GroupEnd());
+    // arrivals overwrite the tail that held my leavers (their data has been packed)
+    if (from_down) { unpack_movers_kernel<<<cdiv(from_down, kBlock), kBlock, 0, st>>>(n_stay, from_down, slab.recvbuf[0], pos, v[0], v[1], v[2], f[0], f[1], f[2], orig); check_launch("unpack_movers"); }
+    if (from_up)   { unpack_movers_kernel<<<cdiv(from_up, kBlock), kBlock, 0, st>>>(n_stay + from_down, from_up, slab.recvbuf[1], pos, v[0], v[1], v[2], f[0], f[1], f[2], orig); check_launch("unpack_movers"); }
+    const bool changed = n_down + n_up + from_up + from_down > 0;
+    n = n_stay + from_down + from_up; c.n = n;
+    if (changed) sort_by_cell();
+    cnt[ST_HALO]++;
+}
+
+// Slab path, at re-binning: tell the neighbours how my boundary layers are populated (per-cell counts),
+// build the cell table of my two halo layers from what they tell me.
+void ljgpu_sim::halo_setup() {
+    auto& A = ljnccl::api();
+    const unsigned nc2 = nc * nc;
+    const uint32_t* my_lo = ccount + (size_t)1 * nc2;              // first owned layer
+    const uint32_t* my_hi = ccount + (size_t)slab.nzl * nc2;       // last owned layer
+    NCK(A.GroupStart());
+    NCK(A.Send(my_lo, nc2, ljnccl::kUint32, slab.down, slab.comm, st));
+    NCK(A.Send(my_hi, nc2, ljnccl::kUint32, slab.up, slab.comm, st));
+    NCK(A.Recv(slab.hcount[1], nc2, ljnccl::kUint32, slab.up, slab.comm, st));     // upper halo = up neighbour's first layer
+    NCK(A.Recv(slab.hcount[0], nc2, ljnccl::kUint32, slab.down, slab.comm, st));   // lower halo = down neighbour's last layer
+    NCK(A.GroupEnd());
+    for (int k = 0; k < 2; ++k) {
+        CK(cudaMemcpyAsync(slab.hoff[k], slab.hcount[k], (size_t)nc2 * 4, cudaMemcpyDeviceToDevice, st));
+        launches += exclusive_scan_u32(slab.hoff[k], nc2, slab.xchg + 4 + k, scr, st);
+    }
+    // my own boundary layer sizes: slots [0, c_lo) and [n - c_hi, n)
+    CK(cudaMemcpyAsync(slab.h_xchg + 4, slab.xchg + 4, 8, cudaMemcpyDeviceToHost, st));
+    std::vector<uint32_t> lo(nc2), hi(nc2);
+    CK(cudaMemcpyAsync(lo.data(), my_lo, (size_t)nc2 * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(hi.data(), my_hi, (size_t)nc2 * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    slab.h_lo = slab.h_xchg[4]; slab.h_hi = slab.h_xchg[5];
+    slab.c_lo = 0; slab.c_hi = 0;
+    for (uint32_t q : lo) slab.c_lo += q;
+    for (uint32_t q : hi) slab.c_hi += q;
+    if ((size_t)n + slab.h_lo + slab.h_hi > pos_cap) throw LjError(LJGPU_ESTATE, "halo does not fit the position buffer");
+    halo_cells_kernel<<<cdiv(nc2, kBlock), kBlock, 0, st>>>(nc2, 0, n, slab.hcount[0], slab.hoff[0], cstart, ccount);
+    check_launch("halo_cells");
+    halo_cells_kernel<<<cdiv(nc2, kBlock), kBlock, 0, st>>>(nc2, (slab.nzl + 1) * nc2, n + slab.h_lo, slab.hcount[1], slab.hoff[1], cstart, ccount);
+    check_launch("halo_cells");
+}
+
+// Slab path, every step: my boundary layers are contiguous slot ranges of the cell-sorted positions, so
+// they go out as they lie (no packing) and land in the neighbours' halo slots.
+void ljgpu_sim::halo_exchange() {
+    auto& A = ljnccl::api();
+    stage_begin();
+    NCK(A.GroupStart());
+    NCK(A.Send(pos, (size_t)std::max(slab.c_lo, 1u) * 4, ljnccl::kFloat64, slab.down, slab.comm, st));
+    NCK(A.Send(pos + (n - slab.c_hi), (size_t)std::max(slab.c_hi, 1u) * 4, ljnccl::kFloat64, slab.up, slab.comm, st));
+    NCK(A.Recv(pos + n + slab.h_lo, (size_t)std::max(slab.h_hi, 1u) * 4, ljnccl::kFloat64, slab.up, slab.comm, st));
+    NCK(A.Recv(pos + n, (size_t)std::max(slab.h_lo, 1u) * 4, ljnccl::kFloat64, slab.down, slab.comm, st));
+    NCK(A.GroupEnd());
+    stage_end(ST_HALO);
+}
+
+void ljgpu_sim::allreduce_red() {
+    NCK(ljnccl::api().AllReduce(ctrl->red, ctrl->red, 4, ljnccl::kFloat64, ljnccl::kSum, slab.comm, st));
+}
+
+// Re-binning: the reference's list rebuild (.cpp:441-551) on the device layout: sort by cell, dij = 0
+// (.cpp:484-486), tile tables, and on the Verlet path the list itself.
 void ljgpu_sim::rebuild() {
     stage_begin();
     CK(cudaMemsetAsync(&ctrl->stop, 0, sizeof(unsigned), st));
     CK(cudaMemsetAsync(&ctrl->maxdisp2, 0, sizeof(unsigned long long), st));
-
-    wrap_key_kernel<<<nb_atoms, kBlock, 0, st>>>(c, pos, pos_tmp, keys, vals);
-    check_launch("wrap_key");
-    int bits = 1; while ((1ull << bits) < (unsigned long long)ncell) ++bits;
-    launches += radix_sort_pairs(keys, vals, n, bits, scr, st);
-    permute_kernel<<<nb_atoms, kBlock, 0, st>>>(n, vals, pos_tmp, pos,
-                                                v[0], v[1], v[2], f[0], f[1], f[2], orig,
-                                                v_alt[0], v_alt[1], v_alt[2], f_alt[0], f_alt[1], f_alt[2], orig_alt);
-    check_launch("permute");
-    for (int k = 0; k < 3; ++k) { std::swap(v[k], v_alt[k]); std::swap(f[k], f_alt[k]); }
-    std::swap(orig, orig_alt);
-    for (int k = 0; k < 3; ++k) CK(cudaMemsetAsync(dij[k], 0, (size_t)n * 8, st));
-
-    CK(cudaMemsetAsync(cstart, 0, (size_t)ncell * 4, st));
-    CK(cudaMemsetAsync(cend, 0, (size_t)ncell * 4, st));
-    cell_bounds_kernel<<<nb_atoms, kBlock, 0, st>>>(n, keys, cstart, cend);
-    check_launch("cell_bounds");
-    cell_count_kernel<<<cdiv(ncell, kBlock), kBlock, 0, st>>>(ncell, cstart, cend, ccount);
-    check_launch("cell_count");
+    sort_by_cell();
+    if (slab.on) migrate();
+    if (n) for (int k = 0; k < 3; ++k) CK(cudaMemsetAsync(dij[k], 0, (size_t)n * 8, st));
+    if (slab.on) { halo_setup(); halo_exchange(); }
 
     CK(cudaMemsetAsync(&ctrl->max_tile, 0, sizeof(unsigned), st));
     CK(cudaMemsetAsync(&ctrl->max_home, 0, sizeof(unsigned), st));
-    {
-        TileGrid g{nc, nbx, nby, nbz, nblocks_tile, tsrc, toff};
-        tile_table_kernel<<<cdiv(nblocks_tile, 4), 128, 0, st>>>(g, cstart, ccount, tsrc, toff, ctrl);
-    }
+    tile_table_kernel<<<cdiv(nblocks_tile, 4), 128, 0, st>>>(tile_grid(), cstart, ccount, tsrc, toff, ctrl);
     check_launch("tile_table");
     fetch_ctrl();
     tcap = ((h_ctrl->max_tile + 15) / 16) * 16;
@@ -306,9 +518,8 @@ static void launch_tile2(ljgpu_sim* s, int guarded) {
     const size_t smem = (size_t)s->tcap * 24;
     if (smem > 48 * 1024)
         CK(cudaFuncSetAttribute(tile_kernel<MODE, UNIT_SIGMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    TileGrid g{s->nc, s->nbx, s->nby, s->nbz, s->nblocks_tile, s->tsrc, s->toff};
     TileArgs a{s->pos, s->nl, s->nl_count, s->f[0], s->f[1], s->f[2], s->partial_epot, s->ctrl, s->capq};
-    tile_kernel<MODE, UNIT_SIGMA><<<s->nblocks_tile, s->tile_threads, smem, s->st>>>(s->c, g, a, guarded);
+    tile_kernel<MODE, UNIT_SIGMA><<<s->nblocks_tile, s->tile_threads, smem, s->st>>>(s->c, s->tile_grid(), a, guarded);
     s->check_launch("tile_kernel");
 }
 template <int MODE>
@@ -318,14 +529,23 @@ static void launch_tile(ljgpu_sim* s, int guarded) {
 }
 
 void ljgpu_sim::build_list() {
-    const unsigned ntiles = cdiv(n, 32);
+    const unsigned ntiles = cdiv(cap_atoms, 32);
     for (int attempt = 0; attempt < 4; ++attempt) {
         CK(cudaMemsetAsync(&ctrl->max_count, 0, sizeof(unsigned), st));
         CK(cudaMemsetAsync(&ctrl->overflow, 0, sizeof(unsigned), st));
         if (capq == 0) {
             launch_tile<TILE_LIST_COUNT>(this, 0);
             fetch_ctrl();
-            capq = (h_ctrl->max_count + 8 + 7) / 8;             // quads of 8 entries: max + slack
+            unsigned mx = h_ctrl->max_count;
+            if (slab.on) {          // every device must use the same capacity decision sequence (same NCCL call order)
+                slab.h_xchg[8] = mx;
+                CK(cudaMemcpyAsync(slab.xchg + 8, slab.h_xchg + 8, 4, cudaMemcpyHostToDevice, st));
+                NCK(ljnccl::api().AllReduce(slab.xchg + 8, slab.xchg + 8, 1, ljnccl::kUint32, ljnccl::kMax, slab.comm, st));
+                CK(cudaMemcpyAsync(slab.h_xchg + 8, slab.xchg + 8, 4, cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+                mx = slab.h_xchg[8];
+            }
+            capq = (mx + 12 + 7) / 8;                             // quads of 8 entries: max + slack
         }
         const size_t need = (size_t)ntiles * capq * 32 * 4;
         if (need > nl_alloc) {
@@ -335,8 +555,17 @@ void ljgpu_sim::build_list() {
         }
         launch_tile<TILE_LIST_FILL>(this, 0);
         fetch_ctrl();
-        if (!h_ctrl->overflow) return;
-        capq = (h_ctrl->max_count + 8 + 7) / 8;                 // grow and refill
+        unsigned over = h_ctrl->overflow, mx = h_ctrl->max_count;
+        if (slab.on) {
+            slab.h_xchg[8] = mx; slab.h_xchg[9] = over;
+            CK(cudaMemcpyAsync(slab.xchg + 8, slab.h_xchg + 8, 8, cudaMemcpyHostToDevice, st));
+            NCK(ljnccl::api().AllReduce(slab.xchg + 8, slab.xchg + 8, 2, ljnccl::kUint32, ljnccl::kMax, slab.comm, st));
+            CK(cudaMemcpyAsync(slab.h_xchg + 8, slab.xchg + 8, 8, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            mx = slab.h_xchg[8]; over = slab.h_xchg[9];
+        }
+        if (!over) return;
+        capq = (mx + 12 + 7) / 8;                                 // grow and refill
     }
     throw LjError(LJGPU_ESTATE, "neighbour list capacity did not converge");
 }
@@ -344,10 +573,10 @@ void ljgpu_sim::build_list() {
 void ljgpu_sim::launch_force(bool timed) {
     if (timed) stage_begin();
     if (mode == LJGPU_KERNEL_ALLPAIRS) {
-        dim3 grid(nb_atoms, nsplit);
+        dim3 grid(nb_atoms(), nsplit);
         force_allpairs_kernel<<<grid, kBlock, 0, st>>>(c, ctrl, pos, jchunk, apf[0], apf[1], apf[2], partial_epot);
         check_launch("force_allpairs");
-        allpairs_reduce_kernel<<<nb_atoms, kBlock, 0, st>>>(c, ctrl, nsplit, apf[0], apf[1], apf[2], f[0], f[1], f[2]);
+        allpairs_reduce_kernel<<<nb_atoms(), kBlock, 0, st>>>(c, ctrl, nsplit, apf[0], apf[1], apf[2], f[0], f[1], f[2]);
         check_launch("allpairs_reduce");
     } else if (mode == LJGPU_KERNEL_CELL) {
         launch_tile<TILE_FORCE_CELL>(this, 1);
@@ -357,22 +586,42 @@ void ljgpu_sim::launch_force(bool timed) {
     if (timed) stage_end(ST_FORCE);
 }
 
+void ljgpu_sim::finalize_epot_only() {
+    if (slab.on) {
+        slab_reduce_kernel<<<1, kFinalizeThreads, 0, st>>>(c, ctrl, partial_epot, nb_force, nullptr, partial_pred, 0);
+        check_launch("slab_reduce");
+        allreduce_red();
+        slab_publish_kernel<<<1, 32, 0, st>>>(c, ctrl, hist, 0, 1);
+        check_launch("slab_publish");
+    } else {
+        init_finalize_kernel<<<1, kFinalizeThreads, 0, st>>>(c, ctrl, partial_epot, nb_force);
+        check_launch("init_finalize");
+    }
+}
+
 // Constructor tail, .cpp:57-62: list, forces, publish; ekin stays 0.
 void ljgpu_sim::initial_forces() {
     if (list_mode()) rebuild();
     launch_force(false);
-    init_finalize_kernel<<<1, kFinalizeThreads, 0, st>>>(c, ctrl, partial_epot, nb_force);
-    check_launch("init_finalize");
+    finalize_epot_only();
     sync();
 }
 
 void ljgpu_sim::launch_predict(double dt) {
     const double a = 0.5 * dt / p.mass;                                  // .cpp:339
     stage_begin();
-    predict_kernel<<<nb_atoms, kBlock, 0, st>>>(n, a, v[0], v[1], v[2], f[0], f[1], f[2], partial_pred);
+    predict_kernel<<<nb_atoms(), kBlock, 0, st>>>(n, a, v[0], v[1], v[2], f[0], f[1], f[2], partial_pred);
     check_launch("predict");
-    predict_finalize_kernel<<<1, kFinalizeThreads, 0, st>>>(ctrl, partial_pred, nb_atoms);
-    check_launch("predict_finalize");
+    if (slab.on) {
+        slab_reduce_kernel<<<1, kFinalizeThreads, 0, st>>>(c, ctrl, partial_epot, 0, nullptr, partial_pred, nb_atoms());
+        check_launch("slab_reduce");
+        allreduce_red();
+        slab_publish_kernel<<<1, 32, 0, st>>>(c, ctrl, hist, 0, 2);
+        check_launch("slab_publish");
+    } else {
+        predict_finalize_kernel<<<1, kFinalizeThreads, 0, st>>>(ctrl, partial_pred, nb_atoms());
+        check_launch("predict_finalize");
+    }
     stage_end(ST_PREDICT);
     pred_valid = true; pred_dt = dt;
 }
@@ -382,26 +631,36 @@ void ljgpu_sim::enqueue_step(unsigned step, double dt) {
     c.dt_over_tau = dt / p.tau;                                          // .cpp:375
     stage_begin();
     if (list_mode())
-        kick_drift_kernel<true><<<nb_atoms, kBlock, 0, st>>>(c, dt, a, ctrl, pos, dij[0], dij[1], dij[2],
-                                                             v[0], v[1], v[2], f[0], f[1], f[2]);
+        kick_drift_kernel<true><<<nb_atoms(), kBlock, 0, st>>>(c, dt, a, ctrl, pos, dij[0], dij[1], dij[2],
+                                                               v[0], v[1], v[2], f[0], f[1], f[2]);
     else
-        kick_drift_kernel<false><<<nb_atoms, kBlock, 0, st>>>(c, dt, a, ctrl, pos, nullptr, nullptr, nullptr,
-                                                              v[0], v[1], v[2], f[0], f[1], f[2]);
+        kick_drift_kernel<false><<<nb_atoms(), kBlock, 0, st>>>(c, dt, a, ctrl, pos, nullptr, nullptr, nullptr,
+                                                                v[0], v[1], v[2], f[0], f[1], f[2]);
     check_launch("kick_drift");
     stage_end(ST_KICK_DRIFT);
+    if (slab.on) halo_exchange();
     launch_force(true);
     stage_begin();
-    kick2_kernel<<<nb_atoms, kBlock, 0, st>>>(c, a, ctrl, v[0], v[1], v[2], f[0], f[1], f[2], partial_ekin, partial_pred);
+    kick2_kernel<<<nb_atoms(), kBlock, 0, st>>>(c, a, ctrl, v[0], v[1], v[2], f[0], f[1], f[2], partial_ekin, partial_pred);
     check_launch("kick2");
-    step_finalize_kernel<<<1, kFinalizeThreads, 0, st>>>(c, ctrl, hist, step, partial_epot, nb_force,
-                                                         partial_ekin, partial_pred, nb_atoms);
-    check_launch("step_finalize");
+    if (slab.on) {
+        slab_reduce_kernel<<<1, kFinalizeThreads, 0, st>>>(c, ctrl, partial_epot, nb_force, partial_ekin, partial_pred, nb_atoms());
+        check_launch("slab_reduce");
+        allreduce_red();
+        slab_publish_kernel<<<1, 32, 0, st>>>(c, ctrl, hist, step, 0);
+        check_launch("slab_publish");
+    } else {
+        step_finalize_kernel<<<1, kFinalizeThreads, 0, st>>>(c, ctrl, hist, step, partial_epot, nb_force,
+                                                             partial_ekin, partial_pred, nb_atoms());
+        check_launch("step_finalize");
+    }
     stage_end(ST_KICK2);
 }
 
 // n integrate() calls.  Steps are enqueued in batches without host round trips; once a step finds a
 // displacement beyond shell/2 (.cpp:557-568) the device raises `stop`, the rest of the batch turns
-// into no-ops, and the host re-bins (.cpp:89-91) before continuing.
+// into no-ops, and the host re-bins (.cpp:89-91) before continuing.  On the slab path the flag is part
+// of the per-step all-reduce, so every device stops at the same step and issues the same NCCL calls.
 void ljgpu_sim::run_steps(unsigned first, unsigned nsteps, double dt) {
     unsigned step = first, remaining = nsteps;
     while (remaining) {
@@ -423,14 +682,19 @@ void ljgpu_sim::run_steps(unsigned first, unsigned nsteps, double dt) {
 }
 
 void ljgpu_sim::export3(int what, double* a, double* b, double* cc) {
-    const size_t N = n;
-    if (what == 0) {
-        export_positions_kernel<<<nb_atoms, kBlock, 0, st>>>(c, pos, orig, out3, out3 + N, out3 + 2 * N);
-    } else {
-        double** src = what == 1 ? v : f;
-        export_soa_kernel<<<nb_atoms, kBlock, 0, st>>>(n, src[0], src[1], src[2], orig, out3, out3 + N, out3 + 2 * N);
+    const size_t N = nglobal;
+    if (slab.on) CK(cudaMemsetAsync(out3, 0, 3 * N * 8, st));
+    if (n) {
+        if (what == 0) {
+            export_positions_kernel<<<nb_atoms(), kBlock, 0, st>>>(c, pos, orig, out3, out3 + N, out3 + 2 * N);
+        } else {
+            double** src = what == 1 ? v : f;
+            export_soa_kernel<<<nb_atoms(), kBlock, 0, st>>>(n, src[0], src[1], src[2], orig, out3, out3 + N, out3 + 2 * N);
+        }
+        check_launch("export");
     }
-    check_launch("export");
+    if (slab.on)     // every device contributes its atoms at their original indices; the sum is the whole system
+        NCK(ljnccl::api().AllReduce(out3, out3, 3 * N, ljnccl::kFloat64, ljnccl::kSum, slab.comm, st));
     CK(cudaMemcpyAsync(a, out3, N * 8, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(b, out3 + N, N * 8, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(cc, out3 + 2 * N, N * 8, cudaMemcpyDeviceToHost, st));
@@ -488,8 +752,9 @@ int ljgpu_device_count(void) {
     return n;
 }
 
-int ljgpu_create(const ljgpu_params* p, const double* x, const double* y, const double* z,
-                 const double* vx, const double* vy, const double* vz, ljgpu_sim** out) {
+static int create_common(const ljgpu_params* p, int rank, int world, const void* nccl_id,
+                         const double* x, const double* y, const double* z,
+                         const double* vx, const double* vy, const double* vz, ljgpu_sim** out) {
     if (!p || !x || !y || !z || !vx || !vy || !vz || !out) return fail(LJGPU_EINVAL, "null argument");
     *out = nullptr;
     ljgpu_sim* s = nullptr;
@@ -506,8 +771,25 @@ int ljgpu_create(const ljgpu_params* p, const double* x, const double* y, const 
         if (dev >= ndev) throw LjError(LJGPU_EINVAL, "device ordinal out of range");
         CK(cudaSetDevice(dev));
         s = new ljgpu_sim;
-        s->p = *p; s->mode = mode; s->device = dev; s->n = (unsigned)p->nr_particles;
+        s->p = *p; s->mode = mode; s->device = dev;
+        if (world > 1) {
+            if (mode == LJGPU_KERNEL_ALLPAIRS) { mode = LJGPU_KERNEL_VERLET; s->mode = mode; }   // slabs need the cell structure
+            const unsigned ncells = std::max(1u, (unsigned)(p->cell_length / (p->rcut + p->shell)));
+            if ((unsigned)world > ncells) throw LjError(LJGPU_EINVAL, "more devices than cell layers along z");
+            if (!nccl_id) throw LjError(LJGPU_EINVAL, "slab path needs the NCCL unique id of rank 0");
+            auto& A = ljnccl::api();
+            if (!A.ok) throw LjError(LJGPU_ENCCL, A.error);
+            s->slab.on = true; s->slab.rank = rank; s->slab.world = world;
+            s->slab.down = (rank + world - 1) % world; s->slab.up = (rank + 1) % world;
+            uint32_t lo = 0, hi = 0;
+            ljgpu_slab_layers(ncells, world, rank, &lo, &hi);
+            s->slab.zlo = lo; s->slab.nzl = hi - lo;
+            ljnccl::UniqueId id;
+            std::memcpy(id.internal, nccl_id, sizeof id.internal);
+            NCK(A.CommInitRank(&s->slab.comm, world, id, rank));
+        }
         CK(cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking));
+        s->n = 0;
         s->setup_constants();
         s->allocate();
         s->upload_state(x, y, z, vx, vy, vz);
@@ -516,6 +798,51 @@ int ljgpu_create(const ljgpu_params* p, const double* x, const double* y, const 
     if (rc != LJGPU_OK) { delete s; return rc; }
     *out = s;
     return LJGPU_OK;
+}
+
+int ljgpu_create(const ljgpu_params* p, const double* x, const double* y, const double* z,
+                 const double* vx, const double* vy, const double* vz, ljgpu_sim** out) {
+    return create_common(p, 0, 1, nullptr, x, y, z, vx, vy, vz, out);
+}
+
+// ---- slab path ------------------------------------------------------------------------------------
+int ljgpu_slab_layers(uint32_t cells_per_axis, int world, int rank, uint32_t* first_layer, uint32_t* end_layer) {
+    if (world < 1 || rank < 0 || rank >= world || !first_layer || !end_layer) return LJGPU_EINVAL;
+    const uint32_t base = cells_per_axis / (uint32_t)world, extra = cells_per_axis % (uint32_t)world;
+    const uint32_t r = (uint32_t)rank;
+    *first_layer = r * base + std::min(r, extra);
+    *end_layer = *first_layer + base + (r < extra ? 1u : 0u);
+    return LJGPU_OK;
+}
+
+int ljgpu_slab_unique_id(void* id128) {
+    if (!id128) return fail(LJGPU_EINVAL, "null argument");
+    return guarded([&] {
+        auto& A = ljnccl::api();
+        if (!A.ok) throw LjError(LJGPU_ENCCL, A.error);
+        ljnccl::UniqueId id;
+        NCK(A.GetUniqueId(&id));
+        std::memcpy(id128, id.internal, sizeof id.internal);
+    });
+}
+
+int ljgpu_create_slab(const ljgpu_params* p, int rank, int world, const void* nccl_unique_id,
+                      const double* x, const double* y, const double* z,
+                      const double* vx, const double* vy, const double* vz, ljgpu_sim** out) {
+    if (world < 2 || rank < 0 || rank >= world) return fail(LJGPU_EINVAL, "slab path needs world >= 2 and 0 <= rank < world");
+    return create_common(p, rank, world, nccl_unique_id, x, y, z, vx, vy, vz, out);
+}
+
+int ljgpu_slab_info(ljgpu_sim* s, int32_t* rank, int32_t* world, uint32_t* first_layer, uint32_t* n_layers,
+                    uint64_t* atoms_owned, uint64_t* atoms_halo) {
+    return with_sim(s, [&] {
+        if (rank) *rank = s->slab.rank;
+        if (world) *world = s->slab.world;
+        if (first_layer) *first_layer = s->slab.on ? s->slab.zlo : 0;
+        if (n_layers) *n_layers = s->slab.on ? s->slab.nzl : s->nc;
+        if (atoms_owned) *atoms_owned = s->n;
+        if (atoms_halo) *atoms_halo = s->slab.on ? (uint64_t)s->slab.h_lo + s->slab.h_hi : 0;
+    });
 }
 
 void ljgpu_destroy(ljgpu_sim* s) { delete s; }
@@ -541,9 +868,9 @@ int ljgpu_update_params(ljgpu_sim* s, const ljgpu_params* p) {
         s->c.dt_over_tau = dto;
         s->pred_valid = false;                         // mass enters the kick factor
         if (force_changed) {                           // forces of the current positions under the new potential
+            if (s->slab.on) s->halo_exchange();
             s->launch_force(false);
-            init_finalize_kernel<<<1, kFinalizeThreads, 0, s->st>>>(s->c, s->ctrl, s->partial_epot, s->nb_force);
-            s->check_launch("init_finalize");
+            s->finalize_epot_only();
             s->sync();
         }
     });
@@ -621,9 +948,11 @@ int ljgpu_get_speed_histogram(ljgpu_sim* s, uint32_t nbins, double vmax, uint64_
     if (nbins == 0 || nbins > (uint32_t)kMaxBins || !(vmax > 0)) return fail(LJGPU_EINVAL, "nbins must be 1..1024 and vmax positive");
     return with_sim(s, [&] {
         CK(cudaMemsetAsync(s->hist_counts, 0, nbins * sizeof(unsigned long long), s->st));
-        const unsigned blocks = std::min(cdiv(s->n, 256), 148u * 8u);
+        const unsigned blocks = std::max(1u, std::min(cdiv(s->n, 256), 148u * 8u));
         speed_histogram_kernel<<<blocks, 256, 0, s->st>>>(s->n, s->v[0], s->v[1], s->v[2], nbins, vmax, s->hist_counts);
         s->check_launch("speed_histogram");
+        if (s->slab.on)
+            NCK(ljnccl::api().AllReduce(s->hist_counts, s->hist_counts, nbins, ljnccl::kUint64, ljnccl::kSum, s->slab.comm, s->st));
         static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "");
         CK(cudaMemcpyAsync(counts, s->hist_counts, nbins * sizeof(uint64_t), cudaMemcpyDeviceToHost, s->st));
         s->sync();
@@ -633,9 +962,12 @@ int ljgpu_get_speed_histogram(ljgpu_sim* s, uint32_t nbins, double vmax, uint64_
 int ljgpu_get_cell_ids(ljgpu_sim* s, uint32_t* cell_of_atom, uint32_t dims[3]) {
     if (!cell_of_atom) return fail(LJGPU_EINVAL, "null argument");
     return with_sim(s, [&] {
-        cell_id_probe_kernel<<<s->nb_atoms, kBlock, 0, s->st>>>(s->c, s->pos, s->orig, s->out_u32);
+        if (s->slab.on) CK(cudaMemsetAsync(s->out_u32, 0, (size_t)s->nglobal * 4, s->st));
+        cell_id_probe_kernel<<<s->nb_atoms(), kBlock, 0, s->st>>>(s->c, s->pos, s->orig, s->out_u32);
         s->check_launch("cell_id_probe");
-        CK(cudaMemcpyAsync(cell_of_atom, s->out_u32, (size_t)s->n * 4, cudaMemcpyDeviceToHost, s->st));
+        if (s->slab.on)
+            NCK(ljnccl::api().AllReduce(s->out_u32, s->out_u32, s->nglobal, ljnccl::kUint32, ljnccl::kSum, s->slab.comm, s->st));
+        CK(cudaMemcpyAsync(cell_of_atom, s->out_u32, (size_t)s->nglobal * 4, cudaMemcpyDeviceToHost, s->st));
         s->sync();
         if (dims) dims[0] = dims[1] = dims[2] = s->nc;
     });
@@ -646,6 +978,7 @@ int ljgpu_get_neighbor_counts(ljgpu_sim* s, double cutoff, int inclusive, uint32
     return with_sim(s, [&] {
         if (!(cutoff > 0) || cutoff > s->p.rcut + s->p.shell)
             throw LjError(LJGPU_EINVAL, "cutoff must be in (0, rcut + shell]");
+        if (s->slab.on) throw LjError(LJGPU_ESTATE, "the neighbour-count probe is not available on the slab path");
         const double cut2 = cutoff * cutoff;
         if (s->list_mode()) {
             if (s->dirty_since_rebuild) s->rebuild();       // positions wrapped + cell-sorted again
@@ -653,7 +986,7 @@ int ljgpu_get_neighbor_counts(ljgpu_sim* s, double cutoff, int inclusive, uint32
             count_cells_kernel<<<cdiv(s->ncell, kCellWarps), kCellWarps * 32, 0, s->st>>>(
                 s->c, g, s->pos, cut2, inclusive, s->out_u32, s->orig);
         } else {
-            count_allpairs_kernel<<<s->nb_atoms, kBlock, 0, s->st>>>(s->c, s->pos, s->orig, cut2, inclusive, s->out_u32);
+            count_allpairs_kernel<<<s->nb_atoms(), kBlock, 0, s->st>>>(s->c, s->pos, s->orig, cut2, inclusive, s->out_u32);
         }
         s->check_launch("neighbor_count");
         CK(cudaMemcpyAsync(count_of_atom, s->out_u32, (size_t)s->n * 4, cudaMemcpyDeviceToHost, s->st));
@@ -664,10 +997,11 @@ int ljgpu_get_neighbor_counts(ljgpu_sim* s, double cutoff, int inclusive, uint32
 int ljgpu_write_movie_frame(ljgpu_sim* s, const char* path, int create) {
     if (!path) return fail(LJGPU_EINVAL, "null argument");
     return with_sim(s, [&] {
-        const size_t N = s->n;
+        const size_t N = s->nglobal;
         std::vector<double> buf(6 * N);
         s->export3(0, &buf[0], &buf[N], &buf[2 * N]);
         s->export3(1, &buf[3 * N], &buf[4 * N], &buf[5 * N]);
+        if (s->slab.on && s->slab.rank != 0) return;             // every device holds the frame; rank 0 writes it
         FILE* fp = std::fopen(path, create ? "wb" : "ab");                 // .cpp:131-138
         if (!fp) throw LjError(LJGPU_EINVAL, std::string("cannot open ") + path);
         if (create) { const uint32_t n32 = (uint32_t)N; std::fwrite(&n32, sizeof n32, 1, fp); }

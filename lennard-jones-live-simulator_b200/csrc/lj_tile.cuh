@@ -31,7 +31,10 @@ constexpr int kTileCellsMax = (kTileBX + 2) * kTileRowsMax;           // tile ce
 constexpr int kHomeRowsMax = kTileBY * kTileBZ;
 
 struct TileGrid {
-    unsigned nc;                 // cells per axis
+    unsigned nc;                 // cells per axis in x and y (periodic)
+    unsigned ncz;                // cell layers of the local table (nc, or owned layers + 2 halo layers on a slab)
+    unsigned zper;               // z periodic within this table (single device) or bounded by halo layers (slab)
+    unsigned hz0, nhz;           // first home layer and number of home layers
     unsigned nbx, nby, nbz;      // home blocks per axis
     unsigned nblocks;
     const uint32_t* __restrict__ tsrc;   // [nblocks][kTileCellsMax]     first global slot of each tile cell
@@ -45,10 +48,10 @@ struct TileGeom { unsigned x0, y0, z0, bw, bh, bd, W, H; };
 __device__ __forceinline__ TileGeom tile_geometry(unsigned b, const TileGrid& g) {
     TileGeom t;
     const unsigned bx = b % g.nbx, by = (b / g.nbx) % g.nby, bz = b / (g.nbx * g.nby);
-    t.x0 = bx * kTileBX; t.y0 = by * kTileBY; t.z0 = bz * kTileBZ;
+    t.x0 = bx * kTileBX; t.y0 = by * kTileBY; t.z0 = g.hz0 + bz * kTileBZ;
     t.bw = min((unsigned)kTileBX, g.nc - t.x0);
     t.bh = min((unsigned)kTileBY, g.nc - t.y0);
-    t.bd = min((unsigned)kTileBZ, g.nc - t.z0);
+    t.bd = min((unsigned)kTileBZ, g.hz0 + g.nhz - t.z0);
     t.W = t.bw + 2; t.H = t.bh + 2;
     return t;
 }
@@ -69,7 +72,8 @@ tile_table_kernel(TileGrid g, const uint32_t* __restrict__ cstart, const uint32_
         bool is_home = false;
         if (k < ntc) {
             const unsigned tx = k % t.W, ty = (k / t.W) % t.H, tz = k / (t.W * t.H);
-            const unsigned cx = (t.x0 + nc + tx - 1) % nc, cy = (t.y0 + nc + ty - 1) % nc, cz = (t.z0 + nc + tz - 1) % nc;
+            const unsigned cx = (t.x0 + nc + tx - 1) % nc, cy = (t.y0 + nc + ty - 1) % nc;
+            const unsigned cz = g.zper ? (t.z0 + g.ncz + tz - 1) % g.ncz : (t.z0 + tz - 1);   // a slab always has a layer below and above
             const unsigned cid = cz * nc * nc + cy * nc + cx;
             cnt = ccount[cid]; src = cstart[cid];
             is_home = tx >= 1 && tx <= t.bw && ty >= 1 && ty <= t.bh && tz >= 1 && tz <= t.bd;
