@@ -54,7 +54,9 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-FP64_PEAK_TFLOPS = 37.2   # nominal: 148 SM x 64 DFMA/clk x 2 x 1.965 GHz (no fp64 entry in MEASURED_PEAKS.json)
+# MEASURED_PEAKS.json has no fp64 entry; measured on this pool's B200 with scripts/fp64_peak.cu (8 independent
+# DFMA chains per thread, 64 warps/SM): 33.9 TFLOP/s (nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz = 37.2)
+FP64_PEAK_TFLOPS = 33.9
 
 
 class ClockSampler:
@@ -153,7 +155,8 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "atom-steps/s fp64", "value": rate, "unit": "atom-steps/s",
         "n_gpus": args.gpus, "steps": k, "warmup": args.warmup, "ms_per_step": secs / k * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "N=1048576 LJ liquid rho*=0.8 kT=1 rc=2.5 (BASELINE configs[3])", "sample_atoms": n},
+        "config": {"workload": "N=1048576 LJ liquid rho*=0.8 kT=1 rc=2.5 shell=0.4 tau=0.5 dt=0.001 (BASELINE configs[3])",
+                   "sample_atoms": n},
         "cpu_baseline": {"value": rate, "unit": "atom-steps/s", "cores": 1, "kind": kind, "sample": sample,
                          "host_cores_available": os.cpu_count()},
         "e2e": {"value": rate, "unit": "atom-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -162,13 +165,19 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def dbg(msg):
+    if os.environ.get("LJGPU_BENCH_DEBUG"):
+        print(f"[bench rank {os.environ.get('RANK', '0')}] {msg}", file=sys.stderr, flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=200)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--atoms", type=int, default=1048576)
+    ap.add_argument("--atoms", type=int, default=1048576, help="atoms of the whole system (strong scaling over --gpus)")
+    ap.add_argument("--atoms-per-gpu", type=int, default=0, help="weak scaling instead: this many atoms per device")
     ap.add_argument("--equil", type=int, default=2000, help="untimed equilibration steps before the warm-up")
     ap.add_argument("--kernel", type=int, default=3, help="LJGPU_KERNEL_* (3 = Verlet list)")
     ap.add_argument("--e2e-steps", type=int, default=200)
@@ -192,19 +201,28 @@ def main():
         raise SystemExit("bench.py: no CUDA device (the integrator has no CPU fallback)")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.init_process_group("cpu:gloo,cuda:nccl", device_id=torch.device("cuda", local_rank))
 
     lj = importlib.import_module(PKG)
-    n = args.atoms
+    weak = args.atoms_per_gpu > 0
+    n = args.atoms_per_gpu * world if weak else args.atoms
     cfg = params_dict(n)
     params = lj.LennardJonesParameters(**cfg)
     lj.host_rng_reset()
-    state = lj.host_initialize(params)
-    # TODO(slab path): until the z-slab decomposition lands every rank integrates the full system
-    sim = lj.LennardJonesSimulation(params, state, force_kernel=args.kernel, device=local_rank)
+    state = lj.host_initialize(params)           # every rank builds the same start state (same generator, same seed)
+    if world > 1:
+        # z-slab decomposition: one process per device, NCCL halo/migration/all-reduce inside libljgpu
+        uid = [lj.slab_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0, device=torch.device("cpu"))
+        sim = lj.LennardJonesSimulation(params, state, force_kernel=lj.KERNEL_VERLET, device=local_rank,
+                                        slab=(rank, world, uid[0]))
+    else:
+        sim = lj.LennardJonesSimulation(params, state, force_kernel=args.kernel, device=local_rank)
 
+    dbg(f"created {sim.get_layout()} {sim.slab_info()}")
     step = 1
     sim.integrate_n(step, args.equil, DT); step += args.equil
+    dbg("equilibrated")
     sim.integrate_n(step, args.warmup, DT); step += args.warmup
 
     def barrier():
@@ -227,6 +245,7 @@ def main():
         step += chunk; done += chunk
         if step % 1000 == 0:
             sim.get_speed_histogram(100, 10.0)       # signal_velocities cadence, threadintegrate.cpp:57-62
+    dbg("timed steps done")
     barrier()
     wall_s = time.perf_counter() - t_wall0
     clocks = sampler.stop()
@@ -239,6 +258,7 @@ def main():
     value = n * args.steps / (dev_ms * 1e-3)
     mean_len, max_len = sim.get_list_stats()
     layout = sim.get_layout()
+    dbg(f"value {value:.4e}")
 
     # ---- timed region 2: end to end through the drop-in call pattern --------------------------------
     pinned = [torch.empty(n, dtype=torch.float64, pin_memory=True) for _ in range(3)]
@@ -259,7 +279,13 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e_value = n * args.e2e_steps / e2e_s
+    dbg(f"e2e {e2e_value:.4e}")
+    if world > 1:
+        sim.close()
+        dist.barrier()
 
+    if world > 1:
+        dist.destroy_process_group()
     if rank != 0:
         return
 
@@ -272,9 +298,10 @@ def main():
         bytes_per_atom = 24 + 24 + 4 * (mean_len + 1)    # x,y,z in + f out + the atom's list
     else:
         bytes_per_atom = 48
-    alg_bytes = bytes_per_atom * n
+    n_dev = n / world                                 # atoms one launch of the kernel processes (rank 0's device)
+    alg_bytes = bytes_per_atom * n_dev
     achieved_gbs = alg_bytes / (force_us * 1e-6) / 1e9
-    alg_flops = 28.0 * n_rc * n
+    alg_flops = 28.0 * n_rc * n_dev
     achieved_tf = alg_flops / (force_us * 1e-6) / 1e12
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
@@ -285,18 +312,19 @@ def main():
         except Exception:
             traffic = None
     step_us = dev_ms / args.steps * 1e3
-    stage_share = {k: timers["ms_" + k] / dev_ms for k in ("kick_drift", "force", "kick2", "rebuild", "predict")}
+    stage_share = {k: timers["ms_" + k] / dev_ms for k in ("kick_drift", "force", "kick2", "rebuild", "predict", "halo")}
 
     line = {
         "metric": "atom-steps/s fp64", "value": value, "unit": "atom-steps/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "higher_is_better": True, "scaling": "weak" if weak else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"N={n} LJ liquid rho*=0.8 kT=1 rc=2.5 shell=0.4 tau=0.5 dt=0.001 (BASELINE configs[3])",
                    "force_kernel": {1: "allpairs", 2: "cell", 3: "verlet"}[layout["force_kernel"]],
                    "cells_per_axis": layout["cells_per_axis"], "list_capacity": layout["list_capacity"],
                    "mean_list_length": mean_len, "equilibration_steps": args.equil,
                    "l2": "working set (positions, velocities, forces, displacements, list) is several times the 126 MB L2; no flush needed",
-                   "parallelism": "single device" if world == 1 else f"{world} replicas (slab path pending)"},
+                   "parallelism": "single device" if world == 1 else
+                   f"{world} z-slabs, NCCL halo exchange + 4-double all-reduce per step, migration at re-binning"},
         "e2e": {"value": e2e_value, "unit": "atom-steps/s", "h2d_bytes_per_step": 12, "d2h_bytes_per_step": 24 * n + 24,
                 "steps": args.e2e_steps, "ms_per_step": e2e_s / args.e2e_steps * 1e3,
                 "pattern": "integrate(step, dt) + positions (3 x f64 x N, pinned) + energies read back after every step"},
@@ -309,20 +337,21 @@ def main():
                      "share_of_step": stage_share["force"]},
         "roofline_fp64": {"kernel": "force kernel", "bound": "fp64", "achieved": achieved_tf, "peak": FP64_PEAK_TFLOPS,
                           "unit": "TFLOP/s", "frac": achieved_tf / FP64_PEAK_TFLOPS,
-                          "algorithmic_flops_per_atom": 28.0 * n_rc, "peak_source": "nominal 148 SM x 64 DFMA/clk x 1.965 GHz"},
-        "whole_step": {"us": step_us, "hbm_gbs_at_240B_per_atom_step": 240.0 * n / (step_us * 1e-6) / 1e9,
-                       "stage_share": stage_share, "rebuilds": int(timers["rebuilds"])},
+                          "algorithmic_flops_per_atom": 28.0 * n_rc,
+                          "peak_source": "measured DFMA throughput on this pool (scripts/fp64_peak.cu); nominal 37.2"},
+        "whole_step": {"us": step_us, "hbm_gbs_at_240B_per_atom_step": 240.0 * n / (step_us * 1e-6) / 1e9 / world,
+                       "stage_share": stage_share, "rebuilds": int(timers["rebuilds"]),
+                       "stage_us_per_call": {k: timers["ms_" + k] / max(1, timers["n_" + k]) * 1e3
+                                             for k in ("kick_drift", "force", "kick2", "rebuild", "halo")}},
         "wall_s_timed_region": wall_s,
         "energies_after": {"ekin": ek, "epot": ep, "etot": et},
     }
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:
         rate, kind, secs = cpu_reference_rate(n, args.cpu_steps)
         line["cpu_baseline"] = {"value": rate, "unit": "atom-steps/s", "cores": 1, "kind": kind,
                                 "host_cores_available": os.cpu_count(),
                                 "sample": f"N={n} start lattice, {args.cpu_steps} integrate() calls after 2 warm-up, constructor excluded, {secs:.1f} s"}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -7,6 +7,8 @@
 #include "../../include/ljgpu.h"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -123,7 +125,6 @@ struct ljgpu_sim {
     struct Pending { int stage; cudaEvent_t a, b; };
     std::vector<Pending> pending;
     std::vector<cudaEvent_t> pool;
-    cudaEvent_t cur_a = nullptr;
     double ms[ST_COUNT] = {0};
     uint64_t cnt[ST_COUNT] = {0};
     uint64_t steps = 0, rebuilds = 0, launches = 0;
@@ -135,20 +136,26 @@ struct ljgpu_sim {
         if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
         cudaEvent_t e; CK(cudaEventCreate(&e)); return e;
     }
-    void stage_begin() { if (prof) { cur_a = get_event(); CK(cudaEventRecord(cur_a, st)); } }
-    void stage_end(int stage) {
+    // stage timers nest (a re-binning contains halo exchanges): the caller keeps its start event
+    cudaEvent_t stage_begin() {
+        if (!prof) return nullptr;
+        cudaEvent_t a = get_event();
+        CK(cudaEventRecord(a, st));
+        return a;
+    }
+    void stage_end(int stage, cudaEvent_t a) {
         cnt[stage]++;
-        if (prof) {
+        if (prof && a) {
             cudaEvent_t b = get_event();
             CK(cudaEventRecord(b, st));
-            pending.push_back({stage, cur_a, b});
-            cur_a = nullptr;
+            pending.push_back({stage, a, b});
         }
     }
     void resolve_pending() {      // stream must be idle
         for (auto& q : pending) {
             float t = 0.f;
             if (cudaEventElapsedTime(&t, q.a, q.b) == cudaSuccess) ms[q.stage] += t;
+            else cudaGetLastError();
             pool.push_back(q.a); pool.push_back(q.b);
         }
         pending.clear();
@@ -468,14 +475,14 @@ void ljgpu_sim::halo_setup() {
 // they go out as they lie (no packing) and land in the neighbours' halo slots.
 void ljgpu_sim::halo_exchange() {
     auto& A = ljnccl::api();
-    stage_begin();
+    cudaEvent_t ev = stage_begin();
     NCK(A.GroupStart());
     NCK(A.Send(pos, (size_t)std::max(slab.c_lo, 1u) * 4, ljnccl::kFloat64, slab.down, slab.comm, st));
     NCK(A.Send(pos + (n - slab.c_hi), (size_t)std::max(slab.c_hi, 1u) * 4, ljnccl::kFloat64, slab.up, slab.comm, st));
     NCK(A.Recv(pos + n + slab.h_lo, (size_t)std::max(slab.h_hi, 1u) * 4, ljnccl::kFloat64, slab.up, slab.comm, st));
     NCK(A.Recv(pos + n, (size_t)std::max(slab.h_lo, 1u) * 4, ljnccl::kFloat64, slab.down, slab.comm, st));
     NCK(A.GroupEnd());
-    stage_end(ST_HALO);
+    stage_end(ST_HALO, ev);
 }
 
 void ljgpu_sim::allreduce_red() {
@@ -485,13 +492,24 @@ void ljgpu_sim::allreduce_red() {
 // Re-binning: the reference's list rebuild (.cpp:441-551) on the device layout: sort by cell, dij = 0
 // (.cpp:484-486), tile tables, and on the Verlet path the list itself.
 void ljgpu_sim::rebuild() {
-    stage_begin();
+    cudaEvent_t ev = stage_begin();
+    static const bool trace = std::getenv("LJGPU_TRACE_REBUILD") != nullptr;     // developer aid: host wall time per section
+    auto t0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!trace) return;
+        static const bool nosync = std::getenv("LJGPU_TRACE_NOSYNC") != nullptr;
+        if (!nosync) cudaStreamSynchronize(st);
+        auto t1 = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[ljgpu rebuild r%d] %-12s %8.1f us\n", slab.rank, what, std::chrono::duration<double, std::micro>(t1 - t0).count());
+        t0 = t1;
+    };
     CK(cudaMemsetAsync(&ctrl->stop, 0, sizeof(unsigned), st));
     CK(cudaMemsetAsync(&ctrl->maxdisp2, 0, sizeof(unsigned long long), st));
     sort_by_cell();
-    if (slab.on) migrate();
+    lap("sort");
+    if (slab.on) { migrate(); lap("migrate"); }
     if (n) for (int k = 0; k < 3; ++k) CK(cudaMemsetAsync(dij[k], 0, (size_t)n * 8, st));
-    if (slab.on) { halo_setup(); halo_exchange(); }
+    if (slab.on) { halo_setup(); lap("halo_setup"); halo_exchange(); lap("halo_xchg"); }
 
     CK(cudaMemsetAsync(&ctrl->max_tile, 0, sizeof(unsigned), st));
     CK(cudaMemsetAsync(&ctrl->max_home, 0, sizeof(unsigned), st));
@@ -505,8 +523,10 @@ void ljgpu_sim::rebuild() {
         throw LjError(LJGPU_ESTATE, "a cell neighbourhood does not fit in shared memory (density too inhomogeneous)");
     if (h_ctrl->max_tile > 65535) throw LjError(LJGPU_ESTATE, "tile too large for 16-bit list indices");
 
+    lap("tile_table");
     if (mode == LJGPU_KERNEL_VERLET) build_list();
-    stage_end(ST_REBUILD);
+    lap("build_list");
+    stage_end(ST_REBUILD, ev);
     ++rebuilds;
     if (since_rebuild > 0) last_interval = since_rebuild;
     since_rebuild = 0;
@@ -571,7 +591,7 @@ void ljgpu_sim::build_list() {
 }
 
 void ljgpu_sim::launch_force(bool timed) {
-    if (timed) stage_begin();
+    cudaEvent_t ev = timed ? stage_begin() : nullptr;
     if (mode == LJGPU_KERNEL_ALLPAIRS) {
         dim3 grid(nb_atoms(), nsplit);
         force_allpairs_kernel<<<grid, kBlock, 0, st>>>(c, ctrl, pos, jchunk, apf[0], apf[1], apf[2], partial_epot);
@@ -583,7 +603,7 @@ void ljgpu_sim::launch_force(bool timed) {
     } else {
         launch_tile<TILE_FORCE_LIST>(this, 1);
     }
-    if (timed) stage_end(ST_FORCE);
+    if (timed) stage_end(ST_FORCE, ev);
 }
 
 void ljgpu_sim::finalize_epot_only() {
@@ -609,7 +629,7 @@ void ljgpu_sim::initial_forces() {
 
 void ljgpu_sim::launch_predict(double dt) {
     const double a = 0.5 * dt / p.mass;                                  // .cpp:339
-    stage_begin();
+    cudaEvent_t ev = stage_begin();
     predict_kernel<<<nb_atoms(), kBlock, 0, st>>>(n, a, v[0], v[1], v[2], f[0], f[1], f[2], partial_pred);
     check_launch("predict");
     if (slab.on) {
@@ -622,14 +642,14 @@ void ljgpu_sim::launch_predict(double dt) {
         predict_finalize_kernel<<<1, kFinalizeThreads, 0, st>>>(ctrl, partial_pred, nb_atoms());
         check_launch("predict_finalize");
     }
-    stage_end(ST_PREDICT);
+    stage_end(ST_PREDICT, ev);
     pred_valid = true; pred_dt = dt;
 }
 
 void ljgpu_sim::enqueue_step(unsigned step, double dt) {
     const double a = 0.5 * dt / p.mass;                                  // .cpp:339
     c.dt_over_tau = dt / p.tau;                                          // .cpp:375
-    stage_begin();
+    cudaEvent_t ev = stage_begin();
     if (list_mode())
         kick_drift_kernel<true><<<nb_atoms(), kBlock, 0, st>>>(c, dt, a, ctrl, pos, dij[0], dij[1], dij[2],
                                                                v[0], v[1], v[2], f[0], f[1], f[2]);
@@ -637,10 +657,10 @@ void ljgpu_sim::enqueue_step(unsigned step, double dt) {
         kick_drift_kernel<false><<<nb_atoms(), kBlock, 0, st>>>(c, dt, a, ctrl, pos, nullptr, nullptr, nullptr,
                                                                 v[0], v[1], v[2], f[0], f[1], f[2]);
     check_launch("kick_drift");
-    stage_end(ST_KICK_DRIFT);
+    stage_end(ST_KICK_DRIFT, ev);
     if (slab.on) halo_exchange();
     launch_force(true);
-    stage_begin();
+    ev = stage_begin();
     kick2_kernel<<<nb_atoms(), kBlock, 0, st>>>(c, a, ctrl, v[0], v[1], v[2], f[0], f[1], f[2], partial_ekin, partial_pred);
     check_launch("kick2");
     if (slab.on) {
@@ -654,7 +674,7 @@ void ljgpu_sim::enqueue_step(unsigned step, double dt) {
                                                              partial_ekin, partial_pred, nb_atoms());
         check_launch("step_finalize");
     }
-    stage_end(ST_KICK2);
+    stage_end(ST_KICK2, ev);
 }
 
 // n integrate() calls.  Steps are enqueued in batches without host round trips; once a step finds a
