@@ -288,7 +288,7 @@ void ljgpu_sim::allocate() {
         nblocks_tile = nbx * nby * nbz;
         CK(cudaMalloc(&tsrc, (size_t)nblocks_tile * kTileCellsMax * 4));
         CK(cudaMalloc(&toff, (size_t)nblocks_tile * (kTileCellsMax + 1) * 4));
-        nb_force = nblocks_tile * (LJ_TILE_MAXTHREADS / 32);       // one partial per warp
+        nb_force = nblocks_tile;                                   // one partial per CTA
     } else {
         // j splits: enough blocks to fill 148 SMs a few times over, each split at least 64 atoms wide
         const unsigned nba = cdiv(N, kBlock);
@@ -518,7 +518,7 @@ void ljgpu_sim::rebuild() {
     fetch_ctrl();
     tcap = ((h_ctrl->max_tile + 15) / 16) * 16;
     tile_threads = std::min((unsigned)LJ_TILE_MAXTHREADS, std::max(64u, ((h_ctrl->max_home + 31) / 32) * 32));
-    nb_force = nblocks_tile * (tile_threads / 32);
+    nb_force = nblocks_tile;
     if ((size_t)tcap * 24 > 200 * 1024)
         throw LjError(LJGPU_ESTATE, "a cell neighbourhood does not fit in shared memory (density too inhomogeneous)");
     if (h_ctrl->max_tile > 65535) throw LjError(LJGPU_ESTATE, "tile too large for 16-bit list indices");

@@ -113,7 +113,7 @@ struct TileArgs {
     uint32_t* __restrict__ nl32;           // list words (fill: written as uint16 halves)
     uint32_t* __restrict__ nl_count;
     double* __restrict__ fx; double* __restrict__ fy; double* __restrict__ fz;
-    double* __restrict__ partial_epot;     // one per warp of every CTA: [nblocks][warps_per_block]
+    double* __restrict__ partial_epot;     // one per CTA
     StepCtrl* ctrl;
     unsigned capq;                         // list capacity in 128-bit quads (8 entries) per atom
 };
@@ -126,6 +126,8 @@ tile_kernel(LJConst c, TileGrid g, TileArgs a, int guarded) {
     __shared__ uint32_t s_off[kTileCellsMax + 1];
     __shared__ uint32_t s_src[kTileCellsMax];
     __shared__ uint32_t s_hstart[kHomeRowsMax + 1];     // prefix of home atoms per home x-row
+    __shared__ double s_epot[LJ_TILE_MAXTHREADS / 32];
+    __shared__ unsigned s_ticket;
     if (guarded && a.ctrl->stop) return;
 
     const unsigned b = blockIdx.x;
@@ -137,6 +139,7 @@ tile_kernel(LJConst c, TileGrid g, TileArgs a, int guarded) {
     }
     __syncthreads();
     if (threadIdx.x == 0) {
+        s_ticket = 0;
         unsigned run = 0, q = 0;
         for (unsigned hz = 1; hz <= tg.bd; ++hz)
             for (unsigned hy = 1; hy <= tg.bh; ++hy) {
@@ -184,6 +187,7 @@ tile_kernel(LJConst c, TileGrid g, TileArgs a, int guarded) {
         const double pix = pi[0], piy = pi[1], piz = pi[2];
         double ax = 0.0, ay = 0.0, az = 0.0, e = 0.0;
         unsigned nacc = 0, cnt = 0;
+        uint4 quad = make_uint4(0u, 0u, 0u, 0u);
 
 #define LJ_TILE_PAIR(J)                                                                     \
         {                                                                                   \
@@ -218,7 +222,12 @@ tile_kernel(LJConst c, TileGrid g, TileArgs a, int guarded) {
             if (nq > 0) cur = __ldg(row);
             for (unsigned q = 0; q < nq; ++q) {
                 uint4 nxt = make_uint4(selfw, selfw, selfw, selfw);
+#ifdef LJ_EXP_NOLIST     /* timing experiment only: no list traffic */
+                nxt = make_uint4(cur.x + 0x00010001u, cur.y + 0x00010001u, cur.z + 0x00010001u, cur.w + 0x00010001u);
+                nxt.x &= 0x03ff03ffu; nxt.y &= 0x03ff03ffu; nxt.z &= 0x03ff03ffu; nxt.w &= 0x03ff03ffu;
+#else
                 if (q + 1 < nq) nxt = __ldg(row + (size_t)(q + 1) * 32);
+#endif
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
                     const uint32_t w0 = half ? cur.z : cur.x, w1 = half ? cur.w : cur.y;
@@ -227,8 +236,13 @@ tile_kernel(LJConst c, TileGrid g, TileArgs a, int guarded) {
                     int far = 0;
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
+#ifdef LJ_EXP_NOLDS      /* timing experiment only: no shared-memory gather */
+                        const double fake = __hiloint2double(0x3ff00000 + (int)(jj[u] << 8), 0);
+                        dx[u] = fake; dy[u] = fake * 0.5; dz[u] = fake * 0.25;
+#else
                         const double* pj = sm + 3 * (size_t)jj[u];
                         dx[u] = pix - pj[0]; dy[u] = piy - pj[1]; dz[u] = piz - pj[2];
+#endif
                         d2[u] = fma(dz[u], dz[u], fma(dy[u], dy[u], dx[u] * dx[u]));
                         far = max(far, __double2hiint(d2[u]));
                     }
@@ -248,13 +262,12 @@ tile_kernel(LJConst c, TileGrid g, TileArgs a, int guarded) {
                         const double inv = fast_rcp(d2[u]);
                         const double s2 = UNIT_SIGMA ? inv : c.sigma2 * inv;
                         const double s6 = s2 * s2 * s2;
-                        const double t = fma(s6, s6, -s6);          // s12 - s6
-                        const double fr = fma(s6, s6, t) * inv;     // (2 s12 - s6) / d2
-                        if (in) {
-                            e += t;
-                            ax = fma(fr, dx[u], ax); ay = fma(fr, dy[u], ay); az = fma(fr, dz[u], az);
-                            ++nacc;
-                        }
+                        const double t0 = fma(s6, s6, -s6);         // s12 - s6
+                        const double fr0 = fma(s6, s6, t0) * inv;   // (2 s12 - s6) / d2
+                        const double t = in ? t0 : 0.0, fr = in ? fr0 : 0.0;     // selects, not a divergent branch
+                        e += t;
+                        ax = fma(fr, dx[u], ax); ay = fma(fr, dy[u], ay); az = fma(fr, dz[u], az);
+                        nacc += in ? 1u : 0u;
                     }
                 }
                 cur = nxt;
@@ -267,22 +280,52 @@ tile_kernel(LJConst c, TileGrid g, TileArgs a, int guarded) {
             for (unsigned ry = hy - 1; ry <= hy + 1; ++ry) {
                 const unsigned r = (rz * H + ry) * W + h;
                 const unsigned j0 = s_off[r], j1 = s_off[r + 3];
-                for (unsigned j = j0; j < j1; ++j) {
-                    if (MODE == TILE_FORCE_CELL) {
+                if (MODE == TILE_FORCE_CELL) {
+                    for (unsigned j = j0; j < j1; ++j)
                         if (j != li) LJ_TILE_PAIR(j)
-                    } else {
-                        const double* pj = sm + 3 * (size_t)j;
-                        double dx = pix - pj[0], dy = piy - pj[1], dz = piz - pj[2];
-                        double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
-                        if (maybe_wrapped(d2, far2_hi)) {
-                            dx = min_image(dx, c.L, c.halfL); dy = min_image(dy, c.L, c.halfL);
-                            dz = min_image(dz, c.L, c.halfL);
-                            d2 = fma(dz, dz, fma(dy, dy, dx * dx));
+                } else {
+                    // list build / count: four candidates per round, loads and distances batched
+                    for (unsigned jb = j0; jb < j1; jb += 4) {
+                        double d2[4];
+                        int far = 0;
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const unsigned j = min(jb + u, j1 - 1);
+                            const double* pj = sm + 3 * (size_t)j;
+                            const double dx = pix - pj[0], dy = piy - pj[1], dz = piz - pj[2];
+                            d2[u] = fma(dz, dz, fma(dy, dy, dx * dx));
+                            far = max(far, __double2hiint(d2[u]));
                         }
-                        if (d2 <= c.list_cut2 && j != li) {
-                            if (MODE == TILE_LIST_FILL && cnt < 8 * a.capq)
-                                reinterpret_cast<unsigned short*>(a.nl32)[nl16_index(i, cnt, a.capq)] = (unsigned short)j;
-                            ++cnt;
+                        if (far >= far2_hi) {
+#pragma unroll
+                            for (int u = 0; u < 4; ++u)
+                                if (maybe_wrapped(d2[u], far2_hi)) {
+                                    const unsigned j = min(jb + u, j1 - 1);
+                                    const double* pj = sm + 3 * (size_t)j;
+                                    const double dx = min_image(pix - pj[0], c.L, c.halfL), dy = min_image(piy - pj[1], c.L, c.halfL);
+                                    const double dz = min_image(piz - pj[2], c.L, c.halfL);
+                                    d2[u] = fma(dz, dz, fma(dy, dy, dx * dx));
+                                }
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const unsigned j = jb + u;
+                            if (j < j1 && d2[u] <= c.list_cut2 && j != li) {
+                                if (MODE == TILE_LIST_FILL) {
+                                    // entries are collected in registers and leave as whole 16-byte quads
+                                    const unsigned slot = cnt & 7u;
+                                    const uint32_t val = j << ((slot & 1u) * 16);
+                                    const unsigned wsel = slot >> 1;
+                                    quad.x |= wsel == 0 ? val : 0u; quad.y |= wsel == 1 ? val : 0u;
+                                    quad.z |= wsel == 2 ? val : 0u; quad.w |= wsel == 3 ? val : 0u;
+                                    if (slot == 7u) {
+                                        if ((cnt >> 3) < a.capq)
+                                            reinterpret_cast<uint4*>(a.nl32)[((size_t)(i >> 5) * a.capq + (cnt >> 3)) * 32 + (i & 31u)] = quad;
+                                        quad = make_uint4(0u, 0u, 0u, 0u);
+                                    }
+                                }
+                                ++cnt;
+                            }
                         }
                     }
                 }
@@ -294,18 +337,37 @@ tile_kernel(LJConst c, TileGrid g, TileArgs a, int guarded) {
             a.fx[i] = ax * c.prefctr; a.fy[i] = ay * c.prefctr; a.fz[i] = az * c.prefctr;
             etot += fma(-(double)nacc, c.ecut, e);
         } else {
-            if (MODE == TILE_LIST_FILL)                     // the unused tail of the last quad points at the atom itself
-                for (unsigned k = min(cnt, 8 * a.capq); k & 7u; ++k)
-                    reinterpret_cast<unsigned short*>(a.nl32)[nl16_index(i, k, a.capq)] = (unsigned short)li;
+            if (MODE == TILE_LIST_FILL && (cnt & 7u) && (cnt >> 3) < a.capq) {
+                // flush the last, partial quad; its unused tail points at the atom itself
+                for (unsigned slot = cnt & 7u; slot < 8u; ++slot) {
+                    const uint32_t val = li << ((slot & 1u) * 16);
+                    const unsigned wsel = slot >> 1;
+                    quad.x |= wsel == 0 ? val : 0u; quad.y |= wsel == 1 ? val : 0u;
+                    quad.z |= wsel == 2 ? val : 0u; quad.w |= wsel == 3 ? val : 0u;
+                }
+                reinterpret_cast<uint4*>(a.nl32)[((size_t)(i >> 5) * a.capq + (cnt >> 3)) * 32 + (i & 31u)] = quad;
+            }
             a.nl_count[i] = MODE == TILE_LIST_FILL ? min(cnt, 8 * a.capq) : cnt;
             maxcnt = max(maxcnt, cnt);
         }
     }
 
     if (MODE == TILE_FORCE_LIST || MODE == TILE_FORCE_CELL) {
-        // one partial per warp (no block barrier: a finished warp frees its issue slots at once)
+        // one partial per CTA without a block barrier (a finished warp frees its issue slots at once): every
+        // warp parks its sum in shared memory, the last one to arrive adds them in warp order (fixed order
+        // => reproducible) and writes the CTA's partial
         const double e = warp_sum(etot);
-        if ((threadIdx.x & 31) == 0) a.partial_epot[(size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)] = e;
+        if ((threadIdx.x & 31) == 0) {
+            s_epot[threadIdx.x >> 5] = e;
+            __threadfence_block();
+            const unsigned nw = blockDim.x >> 5;
+            if (atomicAdd(&s_ticket, 1u) == nw - 1) {
+                __threadfence_block();
+                double tot = 0.0;
+                for (unsigned w = 0; w < nw; ++w) tot += ((volatile double*)s_epot)[w];
+                a.partial_epot[blockIdx.x] = tot;
+            }
+        }
     } else {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) maxcnt = max(maxcnt, __shfl_xor_sync(0xffffffffu, maxcnt, o));
