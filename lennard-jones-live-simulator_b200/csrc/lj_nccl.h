@@ -19,6 +19,7 @@ struct Api {
     int (*GetUniqueId)(UniqueId*) = nullptr;
     int (*CommInitRank)(Comm*, int, UniqueId, int) = nullptr;
     int (*CommDestroy)(Comm) = nullptr;
+    int (*CommAbort)(Comm) = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, Comm, cudaStream_t) = nullptr;
     int (*Send)(const void*, size_t, int, int, Comm, cudaStream_t) = nullptr;
@@ -44,6 +45,7 @@ inline Api& api() {
     a.GetUniqueId = (int (*)(UniqueId*))sym("ncclGetUniqueId");
     a.CommInitRank = (int (*)(Comm*, int, UniqueId, int))sym("ncclCommInitRank");
     a.CommDestroy = (int (*)(Comm))sym("ncclCommDestroy");
+    a.CommAbort = (int (*)(Comm))sym("ncclCommAbort");
     a.GetErrorString = (const char* (*)(int))sym("ncclGetErrorString");
     a.AllReduce = (int (*)(const void*, void*, size_t, int, int, Comm, cudaStream_t))sym("ncclAllReduce");
     a.Send = (int (*)(const void*, size_t, int, int, Comm, cudaStream_t))sym("ncclSend");

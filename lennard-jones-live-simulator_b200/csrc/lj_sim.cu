@@ -84,6 +84,7 @@ struct ljgpu_sim {
     unsigned ncell = 0;             // cells of the local table (+2 mover bins on a slab)
     size_t cap_atoms = 0, pos_cap = 0;
     Slab slab;
+    bool failed = false;            // a call on this handle threw: NCCL state is undefined
 
     // state, device order (cell-sorted on the list paths, caller order on the all-pairs path)
     double4* pos = nullptr; double4* pos_tmp = nullptr;
@@ -201,7 +202,8 @@ struct ljgpu_sim {
 ljgpu_sim::~ljgpu_sim() {
     cudaSetDevice(device);
     if (st) cudaStreamSynchronize(st);
-    if (slab.comm) ljnccl::api().CommDestroy(slab.comm);
+    // after a failure the peers may be inside a collective this rank will never join: abort, do not wait
+    if (slab.comm) { if (failed) ljnccl::api().CommAbort(slab.comm); else ljnccl::api().CommDestroy(slab.comm); }
     dfree(pos); dfree(pos_tmp);
     for (int k = 0; k < 3; ++k) { dfree(dij[k]); dfree(v[k]); dfree(f[k]); dfree(v_alt[k]); dfree(f_alt[k]); dfree(apf[k]); }
     dfree(orig); dfree(orig_alt); dfree(keys); dfree(vals);
@@ -536,7 +538,8 @@ void ljgpu_sim::rebuild() {
 template <int MODE, bool UNIT_SIGMA>
 static void launch_tile2(ljgpu_sim* s, int guarded) {
     const size_t smem = (size_t)s->tcap * 24;
-    if (smem > 48 * 1024)
+    // static shared memory counts against the 48 KB default too: opt in well before the limit
+    if (smem > 40 * 1024)
         CK(cudaFuncSetAttribute(tile_kernel<MODE, UNIT_SIGMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     TileArgs a{s->pos, s->nl, s->nl_count, s->f[0], s->f[1], s->f[2], s->partial_epot, s->ctrl, s->capq};
     tile_kernel<MODE, UNIT_SIGMA><<<s->nblocks_tile, s->tile_threads, smem, s->st>>>(s->c, s->tile_grid(), a, guarded);
@@ -550,12 +553,19 @@ static void launch_tile(ljgpu_sim* s, int guarded) {
 
 void ljgpu_sim::build_list() {
     const unsigned ntiles = cdiv(cap_atoms, 32);
+    static const bool trace = std::getenv("LJGPU_TRACE_REBUILD") != nullptr;
+    auto note = [&](const char* what) {
+        if (trace) std::fprintf(stderr, "[ljgpu build_list r%d] %s n=%u halo=%u+%u tcap=%u threads=%u capq=%u blocks=%u\n",
+                                slab.rank, what, n, slab.h_lo, slab.h_hi, tcap, tile_threads, capq, nblocks_tile);
+    };
+    note("enter");
     for (int attempt = 0; attempt < 4; ++attempt) {
         CK(cudaMemsetAsync(&ctrl->max_count, 0, sizeof(unsigned), st));
         CK(cudaMemsetAsync(&ctrl->overflow, 0, sizeof(unsigned), st));
         if (capq == 0) {
             launch_tile<TILE_LIST_COUNT>(this, 0);
             fetch_ctrl();
+            note("count kernel done");
             unsigned mx = h_ctrl->max_count;
             if (slab.on) {          // every device must use the same capacity decision sequence (same NCCL call order)
                 slab.h_xchg[8] = mx;
@@ -566,6 +576,7 @@ void ljgpu_sim::build_list() {
                 mx = slab.h_xchg[8];
             }
             capq = (mx + 12 + 7) / 8;                             // quads of 8 entries: max + slack
+            note("capacity agreed");
         }
         const size_t need = (size_t)ntiles * capq * 32 * 4;
         if (need > nl_alloc) {
@@ -575,6 +586,7 @@ void ljgpu_sim::build_list() {
         }
         launch_tile<TILE_LIST_FILL>(this, 0);
         fetch_ctrl();
+        note("fill kernel done");
         unsigned over = h_ctrl->overflow, mx = h_ctrl->max_count;
         if (slab.on) {
             slab.h_xchg[8] = mx; slab.h_xchg[9] = over;
@@ -738,11 +750,13 @@ int guarded(F&& fn) {
 template <class F>
 int with_sim(ljgpu_sim* s, F&& fn) {
     if (!s) return fail(LJGPU_EINVAL, "null simulation handle");
-    return guarded([&] {
+    const int rc = guarded([&] {
         std::lock_guard<std::mutex> lk(s->mu);
         CK(cudaSetDevice(s->device));
         fn();
     });
+    if (rc == LJGPU_ECUDA || rc == LJGPU_ENCCL || rc == LJGPU_ESTATE) s->failed = true;
+    return rc;
 }
 
 void validate(const ljgpu_params& p, int& mode) {
@@ -815,7 +829,7 @@ static int create_common(const ljgpu_params* p, int rank, int world, const void*
         s->upload_state(x, y, z, vx, vy, vz);
         s->initial_forces();
     });
-    if (rc != LJGPU_OK) { delete s; return rc; }
+    if (rc != LJGPU_OK) { if (s) s->failed = true; delete s; return rc; }
     *out = s;
     return LJGPU_OK;
 }
