@@ -88,6 +88,16 @@ struct StepCtrl {
     double red[4];                // slab path: {epot_sum, ekin_sum, pred_sum, rebuild votes}, local then all-reduced
 };
 
+// Slab path, peer-memory exchange: every device owns one mailbox that its peers write over NVLink.
+constexpr int kMaxPeers = 16;
+struct Mailbox {
+    unsigned long long halo_flag[2];                 // [0]: written by my lower neighbour, [1]: by my upper; value = step sequence
+    unsigned long long red_flag[2][kMaxPeers];       // [parity][source rank] = sequence number of the deposited sums
+    double red[2][kMaxPeers][4];                     // [parity][source rank]{epot_sum, ekin_sum, pred_sum, rebuild vote}
+    unsigned int error;                              // a wait timed out (peer gone): results are invalid
+    unsigned int pad;
+};
+
 constexpr int kHistCap = 4096;    // entries in the energy history ring
 struct HistEntry { double ekin, epot; unsigned int step; unsigned int pad; };
 

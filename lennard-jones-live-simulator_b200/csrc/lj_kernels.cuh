@@ -430,6 +430,112 @@ slab_reduce_kernel(LJConst c, StepCtrl* __restrict__ ctrl,
     }
 }
 
+// ---- slab path over peer memory (NVLink loads/stores, no NCCL in the step loop) ----------------------
+__device__ __forceinline__ unsigned long long ld_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_sys_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ double ld_sys_f64(const double* p) {
+    double v;
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+// Spin until *flag >= seq; gives up after ~2 s (a peer died) so that no kernel can hang the device.
+__device__ __forceinline__ bool wait_flag(const unsigned long long* flag, unsigned long long seq, unsigned int* error) {
+    const long long t0 = clock64();
+    while (ld_sys_u64(flag) < seq) {
+        if (clock64() - t0 > 4000000000ll) { atomicExch(error, 1u); return false; }
+        __nanosleep(100);
+    }
+    __threadfence_system();
+    return true;
+}
+
+// Halo push: my two boundary layers are contiguous slot ranges; write them straight into the halo slots of
+// the ring neighbours' position arrays (peer pointers), then publish the step sequence in their mailboxes.
+__global__ void __launch_bounds__(256)
+halo_push_kernel(const StepCtrl* __restrict__ ctrl, const double4* __restrict__ pos, unsigned n, unsigned c_lo, unsigned c_hi,
+                 double4* __restrict__ down_dst, double4* __restrict__ up_dst,
+                 Mailbox* down_mail, Mailbox* up_mail, unsigned long long seq, unsigned int* ticket) {
+    if (ctrl->stop) return;
+    const unsigned total = c_lo + c_hi;
+    for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < total; k += gridDim.x * blockDim.x) {
+        if (k < c_lo) st_pos(down_dst + k, ld_pos(pos + k));
+        else st_pos(up_dst + (k - c_lo), ld_pos(pos + (n - c_hi) + (k - c_lo)));
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (atomicAdd(ticket, 1u) == gridDim.x - 1) {          // last block: every store of every block is fenced
+            *ticket = 0;
+            __threadfence_system();
+            st_sys_u64(&down_mail->halo_flag[1], seq);          // I am my lower neighbour's upper neighbour
+            st_sys_u64(&up_mail->halo_flag[0], seq);
+        }
+    }
+}
+
+// Local reductions + all-reduce through the mailboxes + publication, one launch.
+//   what: 0 = full step, 1 = constructor (epot only), 2 = predict (pred_sum only)
+__global__ void __launch_bounds__(kFinalizeThreads)
+slab_exchange_kernel(LJConst c, StepCtrl* __restrict__ ctrl, HistEntry* __restrict__ hist, unsigned step, int what,
+                     const double* __restrict__ partial_epot, unsigned nb_epot,
+                     const double* __restrict__ partial_ekin, const double* __restrict__ partial_pred, unsigned nb_kick,
+                     Mailbox* mine, Mailbox* const* __restrict__ peers, int rank, int world, unsigned long long seq) {
+    __shared__ double red[32];
+    __shared__ double tot[4];
+    if (what == 0 && ctrl->stop) return;
+    double se = strided_sum(partial_epot, nb_epot);
+    double sk = partial_ekin ? strided_sum(partial_ekin, nb_kick) : 0.0;
+    double sp = strided_sum(partial_pred, nb_kick);
+    se = block_sum(se, red);
+    sk = block_sum(sk, red);
+    sp = block_sum(sp, red);
+    const unsigned par = (unsigned)(seq & 1ull);
+    if (threadIdx.x == 0) {
+        tot[0] = se; tot[1] = sk; tot[2] = sp;
+        tot[3] = (__longlong_as_double((long long)ctrl->maxdisp2) > c.disp_thresh) ? 1.0 : 0.0;
+        ctrl->maxdisp2 = 0ull;
+    }
+    __syncthreads();
+    // thread r deposits my four sums in peer r's mailbox (its own included), fences, raises the flag
+    if ((int)threadIdx.x < world) {
+        Mailbox* dst = peers[threadIdx.x];
+        double* slot = dst->red[par][rank];
+        slot[0] = tot[0]; slot[1] = tot[1]; slot[2] = tot[2]; slot[3] = tot[3];
+        __threadfence_system();
+        st_sys_u64(&dst->red_flag[par][rank], seq);
+        // ... and waits for peer r's deposit in mine
+        wait_flag(&mine->red_flag[par][threadIdx.x], seq, &mine->error);
+    }
+    __syncthreads();                                       // every deposit has arrived before anyone reads
+    __shared__ double dep[kMaxPeers * 4];
+    if ((int)threadIdx.x < world * 4) dep[threadIdx.x] = ld_sys_f64(&mine->red[par][threadIdx.x >> 2][threadIdx.x & 3]);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double g[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int r = 0; r < world; ++r)                    // rank order on every device: identical sums everywhere
+            for (int k = 0; k < 4; ++k) g[k] += dep[r * 4 + k];
+        ctrl->red[0] = g[0]; ctrl->red[1] = g[1]; ctrl->red[2] = g[2]; ctrl->red[3] = g[3];
+        if (what == 2) { ctrl->pred_sum = g[2]; return; }
+        const double epot = xmul(xmul(xmul(g[0], 4.0), c.epsilon), 0.5);
+        ctrl->epot_sum = g[0];
+        if (what == 1) { ctrl->epot = epot; return; }
+        const double ekin = xmul(xmul(0.5, c.mass), g[1]);
+        ctrl->pred_sum = g[2];
+        ctrl->ekin = ekin; ctrl->epot = epot; ctrl->etot = xadd(ekin, epot);
+        HistEntry& h = hist[ctrl->hist_head % kHistCap];
+        h.ekin = ekin; h.epot = epot; h.step = step; h.pad = 0;
+        ctrl->hist_head += 1;
+        ctrl->steps_done += 1;
+        if (g[3] > 0.0) ctrl->stop = 1;
+    }
+}
+
 // what: 0 = full step (energies, history, rebuild flag), 1 = constructor (epot only), 2 = predict (pred_sum only)
 __global__ void slab_publish_kernel(LJConst c, StepCtrl* __restrict__ ctrl, HistEntry* __restrict__ hist, unsigned step, int what) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;

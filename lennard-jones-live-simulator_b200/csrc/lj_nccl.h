@@ -22,6 +22,7 @@ struct Api {
     int (*CommAbort)(Comm) = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, Comm, cudaStream_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, Comm, cudaStream_t) = nullptr;
     int (*Send)(const void*, size_t, int, int, Comm, cudaStream_t) = nullptr;
     int (*Recv)(void*, size_t, int, int, Comm, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
@@ -48,6 +49,7 @@ inline Api& api() {
     a.CommAbort = (int (*)(Comm))sym("ncclCommAbort");
     a.GetErrorString = (const char* (*)(int))sym("ncclGetErrorString");
     a.AllReduce = (int (*)(const void*, void*, size_t, int, int, Comm, cudaStream_t))sym("ncclAllReduce");
+    a.AllGather = (int (*)(const void*, void*, size_t, int, Comm, cudaStream_t))sym("ncclAllGather");
     a.Send = (int (*)(const void*, size_t, int, int, Comm, cudaStream_t))sym("ncclSend");
     a.Recv = (int (*)(void*, size_t, int, int, Comm, cudaStream_t))sym("ncclRecv");
     a.GroupStart = (int (*)())sym("ncclGroupStart");

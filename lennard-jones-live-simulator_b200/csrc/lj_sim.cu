@@ -64,8 +64,19 @@ struct Slab {
     size_t mover_cap = 0;                 // atoms per mover buffer
     uint32_t* hcount[2] = {nullptr, nullptr};   // per-cell counts of the halo layers as received
     uint32_t* hoff[2] = {nullptr, nullptr};     // their exclusive scans
-    uint32_t* xchg = nullptr;             // device scratch for count exchanges (8 words)
+    uint32_t* xchg = nullptr;             // device scratch for count exchanges (16 words)
     uint32_t* h_xchg = nullptr;           // pinned mirror
+    // peer-memory exchange (NVLink loads/stores through CUDA IPC mappings); NCCL remains for re-binning
+    bool p2p = false;
+    Mailbox* mail = nullptr;              // mine (peers write into it)
+    Mailbox* peer_mail[kMaxPeers] = {nullptr};
+    Mailbox** d_peer_mail = nullptr;      // device copy of the pointer table
+    double4* peer_pos[2] = {nullptr, nullptr};    // position arrays of my lower / upper neighbour
+    void* ipc_opened[kMaxPeers + 2] = {nullptr};  // mappings to close
+    int n_ipc_opened = 0;
+    unsigned nb_n[2] = {0, 0}, nb_hlo[2] = {0, 0};   // owned atoms and lower-halo size of the two neighbours
+    unsigned long long halo_seq = 0, red_seq = 0;
+    unsigned int* push_ticket = nullptr;
 };
 
 } // namespace
@@ -184,6 +195,8 @@ struct ljgpu_sim {
     void halo_setup();
     void halo_exchange();
     void allreduce_red();
+    void setup_p2p();
+    void slab_finalize(int what, unsigned step, unsigned nb_epot, const double* pekin, unsigned nb_kick);
     void rebuild();
     void build_list();
     void launch_force(bool timed);
@@ -194,7 +207,10 @@ struct ljgpu_sim {
     void run_steps(unsigned first, unsigned nsteps, double dt);
     void fetch_ctrl() {
         CK(cudaMemcpyAsync(h_ctrl, ctrl, sizeof(StepCtrl), cudaMemcpyDeviceToHost, st));
+        unsigned err = 0;
+        if (slab.p2p) CK(cudaMemcpyAsync(&err, &slab.mail->error, 4, cudaMemcpyDeviceToHost, st));
         sync();
+        if (err) throw LjError(LJGPU_ENCCL, "a peer device stopped answering (mailbox wait timed out)");
     }
     void export3(int what, double* a, double* b, double* cc);
 };
@@ -213,6 +229,8 @@ ljgpu_sim::~ljgpu_sim() {
     dfree(ctrl); dfree(hist); dfree(out3); dfree(out_u32); dfree(hist_counts);
     for (int k = 0; k < 2; ++k) { dfree(slab.sendbuf[k]); dfree(slab.recvbuf[k]); dfree(slab.hcount[k]); dfree(slab.hoff[k]); }
     dfree(slab.xchg);
+    for (int k = 0; k < slab.n_ipc_opened; ++k) cudaIpcCloseMemHandle(slab.ipc_opened[k]);
+    dfree(slab.mail); dfree(slab.d_peer_mail); dfree(slab.push_ticket);
     if (slab.h_xchg) cudaFreeHost(slab.h_xchg);
     if (h_ctrl) cudaFreeHost(h_ctrl);
     sort_scratch_free(scr);
@@ -467,6 +485,20 @@ void ljgpu_sim::halo_setup() {
     for (uint32_t q : lo) slab.c_lo += q;
     for (uint32_t q : hi) slab.c_hi += q;
     if ((size_t)n + slab.h_lo + slab.h_hi > pos_cap) throw LjError(LJGPU_ESTATE, "halo does not fit the position buffer");
+    if (slab.p2p) {     // where my boundary layers land in the neighbours' position arrays
+        slab.h_xchg[10] = n; slab.h_xchg[11] = slab.h_lo;
+        CK(cudaMemcpyAsync(slab.xchg + 10, slab.h_xchg + 10, 8, cudaMemcpyHostToDevice, st));
+        NCK(A.GroupStart());
+        NCK(A.Send(slab.xchg + 10, 2, ljnccl::kUint32, slab.down, slab.comm, st));
+        NCK(A.Send(slab.xchg + 10, 2, ljnccl::kUint32, slab.up, slab.comm, st));
+        NCK(A.Recv(slab.xchg + 12, 2, ljnccl::kUint32, slab.down, slab.comm, st));
+        NCK(A.Recv(slab.xchg + 14, 2, ljnccl::kUint32, slab.up, slab.comm, st));
+        NCK(A.GroupEnd());
+        CK(cudaMemcpyAsync(slab.h_xchg + 12, slab.xchg + 12, 16, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        slab.nb_n[0] = slab.h_xchg[12]; slab.nb_hlo[0] = slab.h_xchg[13];
+        slab.nb_n[1] = slab.h_xchg[14]; slab.nb_hlo[1] = slab.h_xchg[15];
+    }
     halo_cells_kernel<<<cdiv(nc2, kBlock), kBlock, 0, st>>>(nc2, 0, n, slab.hcount[0], slab.hoff[0], cstart, ccount);
     check_launch("halo_cells");
     halo_cells_kernel<<<cdiv(nc2, kBlock), kBlock, 0, st>>>(nc2, (slab.nzl + 1) * nc2, n + slab.h_lo, slab.hcount[1], slab.hoff[1], cstart, ccount);
@@ -478,6 +510,19 @@ void ljgpu_sim::halo_setup() {
 void ljgpu_sim::halo_exchange() {
     auto& A = ljnccl::api();
     cudaEvent_t ev = stage_begin();
+    if (slab.p2p) {
+        ++slab.halo_seq;
+        // my first layer -> lower neighbour's UPPER halo slots; my last layer -> upper neighbour's LOWER halo slots
+        double4* down_dst = slab.peer_pos[0] + slab.nb_n[0] + slab.nb_hlo[0];
+        double4* up_dst = slab.peer_pos[1] + slab.nb_n[1];
+        const unsigned total = slab.c_lo + slab.c_hi;
+        const unsigned blocks = std::max(1u, std::min(cdiv(total, 256), 296u));
+        halo_push_kernel<<<blocks, 256, 0, st>>>(ctrl, pos, n, slab.c_lo, slab.c_hi, down_dst, up_dst,
+                                                 slab.peer_mail[slab.down], slab.peer_mail[slab.up], slab.halo_seq, slab.push_ticket);
+        check_launch("halo_push");
+        stage_end(ST_HALO, ev);
+        return;
+    }
     NCK(A.GroupStart());
     NCK(A.Send(pos, (size_t)std::max(slab.c_lo, 1u) * 4, ljnccl::kFloat64, slab.down, slab.comm, st));
     NCK(A.Send(pos + (n - slab.c_hi), (size_t)std::max(slab.c_hi, 1u) * 4, ljnccl::kFloat64, slab.up, slab.comm, st));
@@ -489,6 +534,59 @@ void ljgpu_sim::halo_exchange() {
 
 void ljgpu_sim::allreduce_red() {
     NCK(ljnccl::api().AllReduce(ctrl->red, ctrl->red, 4, ljnccl::kFloat64, ljnccl::kSum, slab.comm, st));
+}
+
+// Slab path: local sums -> global sums -> publication.  Over peer memory this is ONE kernel (mailbox
+// all-reduce inside); on the NCCL fallback it is reduce kernel + ncclAllReduce + publish kernel.
+void ljgpu_sim::slab_finalize(int what, unsigned step, unsigned nb_epot, const double* pekin, unsigned nb_kick) {
+    if (slab.p2p) {
+        ++slab.red_seq;
+        slab_exchange_kernel<<<1, kFinalizeThreads, 0, st>>>(c, ctrl, hist, step, what, partial_epot, nb_epot, pekin, partial_pred, nb_kick,
+                                                             slab.mail, slab.d_peer_mail, slab.rank, slab.world, slab.red_seq);
+        check_launch("slab_exchange");
+        return;
+    }
+    slab_reduce_kernel<<<1, kFinalizeThreads, 0, st>>>(c, ctrl, partial_epot, nb_epot, pekin, partial_pred, nb_kick);
+    check_launch("slab_reduce");
+    allreduce_red();
+    slab_publish_kernel<<<1, 32, 0, st>>>(c, ctrl, hist, step, what);
+    check_launch("slab_publish");
+}
+
+// Map the neighbours' position arrays and every rank's mailbox into this process (CUDA IPC over NVLink).
+void ljgpu_sim::setup_p2p() {
+    auto& A = ljnccl::api();
+    if (std::getenv("LJGPU_SLAB_NCCL") || slab.world > kMaxPeers) return;
+    CK(cudaMalloc(&slab.mail, sizeof(Mailbox)));
+    CK(cudaMemset(slab.mail, 0, sizeof(Mailbox)));
+    CK(cudaMalloc(&slab.push_ticket, sizeof(unsigned)));
+    CK(cudaMemset(slab.push_ticket, 0, sizeof(unsigned)));
+    struct Handles { cudaIpcMemHandle_t pos, mail; };
+    static_assert(sizeof(Handles) == 128, "two 64-byte IPC handles");
+    Handles mine;
+    CK(cudaIpcGetMemHandle(&mine.pos, pos));
+    CK(cudaIpcGetMemHandle(&mine.mail, slab.mail));
+    Handles* d_all = nullptr;
+    CK(cudaMalloc(&d_all, sizeof(Handles) * (slab.world + 1)));
+    CK(cudaMemcpy(d_all + slab.world, &mine, sizeof(Handles), cudaMemcpyHostToDevice));
+    NCK(A.AllGather(d_all + slab.world, d_all, sizeof(Handles), ljnccl::kUint8, slab.comm, st));
+    CK(cudaStreamSynchronize(st));
+    std::vector<Handles> all(slab.world);
+    CK(cudaMemcpy(all.data(), d_all, sizeof(Handles) * slab.world, cudaMemcpyDeviceToHost));
+    cudaFree(d_all);
+    auto open = [&](const cudaIpcMemHandle_t& h) {
+        void* p = nullptr;
+        CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        slab.ipc_opened[slab.n_ipc_opened++] = p;
+        return p;
+    };
+    for (int r = 0; r < slab.world; ++r)
+        slab.peer_mail[r] = r == slab.rank ? slab.mail : static_cast<Mailbox*>(open(all[r].mail));
+    slab.peer_pos[0] = static_cast<double4*>(open(all[slab.down].pos));
+    slab.peer_pos[1] = slab.up == slab.down ? slab.peer_pos[0] : static_cast<double4*>(open(all[slab.up].pos));
+    CK(cudaMalloc(&slab.d_peer_mail, sizeof(Mailbox*) * kMaxPeers));
+    CK(cudaMemcpy(slab.d_peer_mail, slab.peer_mail, sizeof(Mailbox*) * kMaxPeers, cudaMemcpyHostToDevice));
+    slab.p2p = true;
 }
 
 // Re-binning: the reference's list rebuild (.cpp:441-551) on the device layout: sort by cell, dij = 0
@@ -541,7 +639,8 @@ static void launch_tile2(ljgpu_sim* s, int guarded) {
     // static shared memory counts against the 48 KB default too: opt in well before the limit
     if (smem > 40 * 1024)
         CK(cudaFuncSetAttribute(tile_kernel<MODE, UNIT_SIGMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    TileArgs a{s->pos, s->nl, s->nl_count, s->f[0], s->f[1], s->f[2], s->partial_epot, s->ctrl, s->capq};
+    TileArgs a{s->pos, s->nl, s->nl_count, s->f[0], s->f[1], s->f[2], s->partial_epot, s->ctrl, s->capq,
+               s->slab.p2p ? s->slab.mail : nullptr, s->slab.halo_seq};
     tile_kernel<MODE, UNIT_SIGMA><<<s->nblocks_tile, s->tile_threads, smem, s->st>>>(s->c, s->tile_grid(), a, guarded);
     s->check_launch("tile_kernel");
 }
@@ -620,11 +719,7 @@ void ljgpu_sim::launch_force(bool timed) {
 
 void ljgpu_sim::finalize_epot_only() {
     if (slab.on) {
-        slab_reduce_kernel<<<1, kFinalizeThreads, 0, st>>>(c, ctrl, partial_epot, nb_force, nullptr, partial_pred, 0);
-        check_launch("slab_reduce");
-        allreduce_red();
-        slab_publish_kernel<<<1, 32, 0, st>>>(c, ctrl, hist, 0, 1);
-        check_launch("slab_publish");
+        slab_finalize(1, 0, nb_force, nullptr, 0);
     } else {
         init_finalize_kernel<<<1, kFinalizeThreads, 0, st>>>(c, ctrl, partial_epot, nb_force);
         check_launch("init_finalize");
@@ -645,11 +740,7 @@ void ljgpu_sim::launch_predict(double dt) {
     predict_kernel<<<nb_atoms(), kBlock, 0, st>>>(n, a, v[0], v[1], v[2], f[0], f[1], f[2], partial_pred);
     check_launch("predict");
     if (slab.on) {
-        slab_reduce_kernel<<<1, kFinalizeThreads, 0, st>>>(c, ctrl, partial_epot, 0, nullptr, partial_pred, nb_atoms());
-        check_launch("slab_reduce");
-        allreduce_red();
-        slab_publish_kernel<<<1, 32, 0, st>>>(c, ctrl, hist, 0, 2);
-        check_launch("slab_publish");
+        slab_finalize(2, 0, 0, nullptr, nb_atoms());
     } else {
         predict_finalize_kernel<<<1, kFinalizeThreads, 0, st>>>(ctrl, partial_pred, nb_atoms());
         check_launch("predict_finalize");
@@ -676,11 +767,7 @@ void ljgpu_sim::enqueue_step(unsigned step, double dt) {
     kick2_kernel<<<nb_atoms(), kBlock, 0, st>>>(c, a, ctrl, v[0], v[1], v[2], f[0], f[1], f[2], partial_ekin, partial_pred);
     check_launch("kick2");
     if (slab.on) {
-        slab_reduce_kernel<<<1, kFinalizeThreads, 0, st>>>(c, ctrl, partial_epot, nb_force, partial_ekin, partial_pred, nb_atoms());
-        check_launch("slab_reduce");
-        allreduce_red();
-        slab_publish_kernel<<<1, 32, 0, st>>>(c, ctrl, hist, step, 0);
-        check_launch("slab_publish");
+        slab_finalize(0, step, nb_force, partial_ekin, nb_atoms());
     } else {
         step_finalize_kernel<<<1, kFinalizeThreads, 0, st>>>(c, ctrl, hist, step, partial_epot, nb_force,
                                                              partial_ekin, partial_pred, nb_atoms());
@@ -826,6 +913,7 @@ static int create_common(const ljgpu_params* p, int rank, int world, const void*
         s->n = 0;
         s->setup_constants();
         s->allocate();
+        if (s->slab.on) s->setup_p2p();
         s->upload_state(x, y, z, vx, vy, vz);
         s->initial_forces();
     });

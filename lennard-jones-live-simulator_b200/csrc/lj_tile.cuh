@@ -47,7 +47,10 @@ struct TileGeom { unsigned x0, y0, z0, bw, bh, bd, W, H; };
 // every side (tx = 0 and bw+1 etc.), so the cells of one x-row are consecutive in the tile.
 __device__ __forceinline__ TileGeom tile_geometry(unsigned b, const TileGrid& g) {
     TileGeom t;
-    const unsigned bx = b % g.nbx, by = (b / g.nbx) % g.nby, bz = b / (g.nbx * g.nby);
+    const unsigned bx = b % g.nbx, by = (b / g.nbx) % g.nby;
+    unsigned bz = b / (g.nbx * g.nby);
+    if (!g.zper && g.nbz > 2)        // slab: the two bricks that touch halo layers are scheduled last (they wait for the neighbours)
+        bz = bz < g.nbz - 2 ? bz + 1 : (bz == g.nbz - 2 ? 0u : g.nbz - 1);
     t.x0 = bx * kTileBX; t.y0 = by * kTileBY; t.z0 = g.hz0 + bz * kTileBZ;
     t.bw = min((unsigned)kTileBX, g.nc - t.x0);
     t.bh = min((unsigned)kTileBY, g.nc - t.y0);
@@ -116,6 +119,9 @@ struct TileArgs {
     double* __restrict__ partial_epot;     // one per CTA
     StepCtrl* ctrl;
     unsigned capq;                         // list capacity in 128-bit quads (8 entries) per atom
+    // slab path over peer memory: wait until both neighbours have pushed this step's halo (null: no wait)
+    Mailbox* mail;
+    unsigned long long halo_seq;
 };
 
 // UNIT_SIGMA: sigma == 1 exactly (reduced units): s2 = sigma^2/d2 needs no multiply.
@@ -129,9 +135,15 @@ tile_kernel(LJConst c, TileGrid g, TileArgs a, int guarded) {
     __shared__ double s_epot[LJ_TILE_MAXTHREADS / 32];
     __shared__ unsigned s_ticket;
     if (guarded && a.ctrl->stop) return;
-
     const unsigned b = blockIdx.x;
     const TileGeom tg = tile_geometry(b, g);
+    if (a.mail) {       // slab over peer memory: only bricks whose tile reaches a halo layer wait for that neighbour's push
+        if (threadIdx.x == 0) {
+            if (tg.z0 == g.hz0) wait_flag(&a.mail->halo_flag[0], a.halo_seq, &a.mail->error);
+            if (tg.z0 + tg.bd == g.hz0 + g.nhz) wait_flag(&a.mail->halo_flag[1], a.halo_seq, &a.mail->error);
+        }
+        __syncthreads();
+    }
     const unsigned W = tg.W, H = tg.H, ntc = W * H * (tg.bd + 2);
     for (unsigned t = threadIdx.x; t <= ntc; t += blockDim.x) {
         s_off[t] = g.toff[(size_t)b * (kTileCellsMax + 1) + t];
