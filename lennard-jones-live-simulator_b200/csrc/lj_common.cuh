@@ -64,6 +64,9 @@ struct LJConst {
     double list_cut2;             // (rcut+shell)^2                             (.cpp:445)
     double disp_thresh;           // shell*shell*0.25                           (.cpp:559-560)
     double cell_edge;             // L / cells_per_axis                         (.cpp:455-457)
+    double prune_cut2;            // (rcut + s_in)^2: cutoff of the pruned inner list
+    double prune_half;            // s_in / 2: how far atoms may have moved since the pruning
+    double dt;                    // this step's dt (set per step)
     unsigned nc;                  // cells per axis                             (.cpp:447-453)
     unsigned n;                   // atoms owned by this device
     // z-slab decomposition (slab == 0: one device owns the whole box)
@@ -85,6 +88,12 @@ struct StepCtrl {
     unsigned int max_tile;        // largest shared-memory tile (atoms) over all home blocks
     unsigned int max_home;        // most home atoms in one block
     unsigned long long hist_head; // energy history ring: entries written so far
+    // pruned inner list (single-device Verlet path): valid while drift_bound <= prune_half
+    unsigned long long vmax2;     // bits of max_i |v_i|^2 of the current step's drift velocities
+    double drift_bound;           // sum over the steps since the pruning of max_i |v_i| dt
+    unsigned int inner_valid;     // an inner list exists
+    unsigned int inner_used;      // steps that used it (statistics)
+    double vmax_last;             // max_i |v_i| of the last completed step (host sizes the pruning cadence from it)
     double red[4];                // slab path: {epot_sum, ekin_sum, pred_sum, rebuild votes}, local then all-reduced
 };
 

@@ -82,7 +82,7 @@ kick_drift_kernel(LJConst c, double dt, double a, StepCtrl* __restrict__ ctrl,
     const double lambda = xsqrt(xadd(1.0, xmul(c.dt_over_tau, xsub(xdiv(c.ekin0, ek), 1.0))));
 
     const unsigned i = blockIdx.x * kBlock + threadIdx.x;
-    double d2 = 0.0;
+    double d2 = 0.0, v2 = 0.0;
     if (i < c.n) {
         double4 p = ld_pos(pos + i);
         p.x = wrap_coord(p.x, c.L, c.invL);
@@ -96,6 +96,7 @@ kick_drift_kernel(LJConst c, double dt, double a, StepCtrl* __restrict__ ctrl,
         p.x = xadd(p.x, incx); p.y = xadd(p.y, incy); p.z = xadd(p.z, incz);
         vx[i] = ux; vy[i] = uy; vz[i] = uz;
         st_pos(pos + i, p);
+        if (TRACK_DISP) v2 = fma(uz, uz, fma(uy, uy, ux * ux));
         if (TRACK_DISP) {
             const double ax = xadd(dijx[i], incx), ay = xadd(dijy[i], incy), az = xadd(dijz[i], incz);
             dijx[i] = ax; dijy[i] = ay; dijz[i] = az;
@@ -103,9 +104,24 @@ kick_drift_kernel(LJConst c, double dt, double a, StepCtrl* __restrict__ ctrl,
         }
     }
     if (TRACK_DISP) {
-        d2 = block_max(d2, red);
-        if (threadIdx.x == 0 && d2 > c.disp_thresh)
-            atomicMax(&ctrl->maxdisp2, (unsigned long long)__double_as_longlong(d2));
+        // two maxima in one pass over the block
+        d2 = warp_max(d2); v2 = warp_max(v2);
+        __shared__ double red2[32];
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+        if (lane == 0) { red[w] = d2; red2[w] = v2; }
+        __syncthreads();
+        if (w == 0) {
+            d2 = lane < kBlock / 32 ? red[lane] : 0.0;
+            v2 = lane < kBlock / 32 ? red2[lane] : 0.0;
+            d2 = warp_max(d2); v2 = warp_max(v2);
+            if (lane == 0) {
+                if (d2 > c.disp_thresh) atomicMax(&ctrl->maxdisp2, (unsigned long long)__double_as_longlong(d2));
+                // fastest atom of this step: bounds how far any pair distance can have shrunk since the pruning
+                v2 *= (1.0 + 1e-12);
+                if (v2 > __longlong_as_double((long long)*(volatile unsigned long long*)&ctrl->vmax2))
+                    atomicMax(&ctrl->vmax2, (unsigned long long)__double_as_longlong(v2));
+            }
+        }
     }
 }
 
@@ -322,7 +338,17 @@ step_finalize_kernel(LJConst c, StepCtrl* __restrict__ ctrl, HistEntry* __restri
         ctrl->steps_done += 1;
         if (__longlong_as_double((long long)ctrl->maxdisp2) > c.disp_thresh) ctrl->stop = 1;
         ctrl->maxdisp2 = 0ull;
+        const double vmax = sqrt(__longlong_as_double((long long)ctrl->vmax2));
+        ctrl->vmax_last = vmax;
+        ctrl->drift_bound += vmax * c.dt;
+        ctrl->vmax2 = 0ull;
     }
+}
+
+// After a pruning pass: the inner list is exact for the current positions.
+__global__ void prune_commit_kernel(StepCtrl* __restrict__ ctrl) {
+    if (ctrl->stop) return;
+    ctrl->inner_valid = 1; ctrl->drift_bound = 0.0; ctrl->vmax2 = 0ull;
 }
 
 // Constructor path: energies after the first force pass; ekin stays 0 (.cpp:57-62).

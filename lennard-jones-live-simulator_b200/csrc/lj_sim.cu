@@ -115,6 +115,9 @@ struct ljgpu_sim {
     uint32_t *tsrc = nullptr, *toff = nullptr;
     unsigned nbx = 0, nby = 0, nbz = 0, nblocks_tile = 0, tcap = 0, tile_threads = 128;
     uint32_t* nl = nullptr; uint32_t* nl_count = nullptr; unsigned capq = 0; size_t nl_alloc = 0;
+    // pruned inner list (single-device Verlet path)
+    uint32_t* nl_in = nullptr; uint32_t* nl_in_count = nullptr;
+    double prune_skin = 0.0; unsigned prune_interval = 8, since_prune = 0;
 
     // reductions
     double *partial_epot = nullptr, *partial_ekin = nullptr, *partial_pred = nullptr;
@@ -224,7 +227,7 @@ ljgpu_sim::~ljgpu_sim() {
     for (int k = 0; k < 3; ++k) { dfree(dij[k]); dfree(v[k]); dfree(f[k]); dfree(v_alt[k]); dfree(f_alt[k]); dfree(apf[k]); }
     dfree(orig); dfree(orig_alt); dfree(keys); dfree(vals);
     dfree(cstart); dfree(cend); dfree(ccount);
-    dfree(nl); dfree(nl_count); dfree(tsrc); dfree(toff);
+    dfree(nl); dfree(nl_count); dfree(nl_in); dfree(nl_in_count); dfree(tsrc); dfree(toff);
     dfree(partial_epot); dfree(partial_ekin); dfree(partial_pred);
     dfree(ctrl); dfree(hist); dfree(out3); dfree(out_u32); dfree(hist_counts);
     for (int k = 0; k < 2; ++k) { dfree(slab.sendbuf[k]); dfree(slab.recvbuf[k]); dfree(slab.hcount[k]); dfree(slab.hoff[k]); }
@@ -255,6 +258,14 @@ void ljgpu_sim::setup_constants() {
     const double csc = p.rcut + p.shell;                                // .cpp:443-445
     c.list_cut2 = csc * csc;
     c.disp_thresh = p.shell * p.shell * 0.25;                           // .cpp:559-560
+    {   // inner-list skin: LJGPU_PRUNE_SKIN (in sigma units of length; 0 disables), default 0.12, never beyond the shell
+        const char* e = std::getenv("LJGPU_PRUNE_SKIN");
+        prune_skin = e ? std::atof(e) : 0.12;
+        if (prune_skin >= p.shell || slab.on || mode != LJGPU_KERNEL_VERLET) prune_skin = 0.0;
+        c.prune_cut2 = (p.rcut + prune_skin) * (p.rcut + prune_skin);
+        c.prune_half = 0.5 * prune_skin;
+        c.dt = 0.0;
+    }
     unsigned ncells = (unsigned)(L / csc);                              // .cpp:447-453
     ncells = std::max(1u, ncells);
     c.nc = ncells;
@@ -303,6 +314,7 @@ void ljgpu_sim::allocate() {
         CK(cudaMalloc(&keys, A * 4)); CK(cudaMalloc(&vals, A * 4));
         CK(cudaMalloc(&cstart, (size_t)ncell * 4)); CK(cudaMalloc(&cend, (size_t)ncell * 4)); CK(cudaMalloc(&ccount, (size_t)ncell * 4));
         CK(cudaMalloc(&nl_count, A * 4));
+        if (prune_skin > 0.0) CK(cudaMalloc(&nl_in_count, A * 4));
         const unsigned nhz = slab.on ? slab.nzl : nc;
         nbx = cdiv(nc, kTileBX); nby = cdiv(nc, kTileBY); nbz = cdiv(nhz, kTileBZ);
         nblocks_tile = nbx * nby * nbz;
@@ -605,6 +617,8 @@ void ljgpu_sim::rebuild() {
     };
     CK(cudaMemsetAsync(&ctrl->stop, 0, sizeof(unsigned), st));
     CK(cudaMemsetAsync(&ctrl->maxdisp2, 0, sizeof(unsigned long long), st));
+    CK(cudaMemsetAsync(&ctrl->inner_valid, 0, sizeof(unsigned), st));       // slots are about to be permuted
+    since_prune = ~0u / 2;                                                  // prune at the next step
     sort_by_cell();
     lap("sort");
     if (slab.on) { migrate(); lap("migrate"); }
@@ -639,14 +653,15 @@ static void launch_tile2(ljgpu_sim* s, int guarded) {
     // static shared memory counts against the 48 KB default too: opt in well before the limit
     if (smem > 40 * 1024)
         CK(cudaFuncSetAttribute(tile_kernel<MODE, UNIT_SIGMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    TileArgs a{s->pos, s->nl, s->nl_count, s->f[0], s->f[1], s->f[2], s->partial_epot, s->ctrl, s->capq,
+    TileArgs a{s->pos, s->nl, s->nl_count, s->prune_skin > 0.0 ? s->nl_in : nullptr, s->nl_in_count,
+               s->f[0], s->f[1], s->f[2], s->partial_epot, s->ctrl, s->capq,
                s->slab.p2p ? s->slab.mail : nullptr, s->slab.halo_seq};
     tile_kernel<MODE, UNIT_SIGMA><<<s->nblocks_tile, s->tile_threads, smem, s->st>>>(s->c, s->tile_grid(), a, guarded);
     s->check_launch("tile_kernel");
 }
 template <int MODE>
 static void launch_tile(ljgpu_sim* s, int guarded) {
-    if (MODE == TILE_FORCE_LIST && s->c.sigma2 == 1.0) launch_tile2<MODE, true>(s, guarded);
+    if ((MODE == TILE_FORCE_LIST || MODE == TILE_FORCE_PRUNE) && s->c.sigma2 == 1.0) launch_tile2<MODE, true>(s, guarded);
     else launch_tile2<MODE, false>(s, guarded);
 }
 
@@ -679,8 +694,9 @@ void ljgpu_sim::build_list() {
         }
         const size_t need = (size_t)ntiles * capq * 32 * 4;
         if (need > nl_alloc) {
-            dfree(nl);
+            dfree(nl); dfree(nl_in);
             CK(cudaMalloc(&nl, need * 4));
+            if (prune_skin > 0.0) CK(cudaMalloc(&nl_in, need * 4));
             nl_alloc = need;
         }
         launch_tile<TILE_LIST_FILL>(this, 0);
@@ -752,6 +768,7 @@ void ljgpu_sim::launch_predict(double dt) {
 void ljgpu_sim::enqueue_step(unsigned step, double dt) {
     const double a = 0.5 * dt / p.mass;                                  // .cpp:339
     c.dt_over_tau = dt / p.tau;                                          // .cpp:375
+    c.dt = dt;
     cudaEvent_t ev = stage_begin();
     if (list_mode())
         kick_drift_kernel<true><<<nb_atoms(), kBlock, 0, st>>>(c, dt, a, ctrl, pos, dij[0], dij[1], dij[2],
@@ -762,7 +779,21 @@ void ljgpu_sim::enqueue_step(unsigned step, double dt) {
     check_launch("kick_drift");
     stage_end(ST_KICK_DRIFT, ev);
     if (slab.on) halo_exchange();
-    launch_force(true);
+    bool prune_now = false;
+    if (prune_skin > 0.0) {
+        prune_now = since_prune >= prune_interval;      // this step's force pass walks the outer list and emits the inner one
+        if (prune_now) since_prune = 0;
+        ++since_prune;
+    }
+    if (prune_now) {
+        cudaEvent_t pv = stage_begin();
+        launch_tile<TILE_FORCE_PRUNE>(this, 1);
+        prune_commit_kernel<<<1, 1, 0, st>>>(ctrl);
+        check_launch("prune_commit");
+        stage_end(ST_GHOST, pv);                        // reported as ms_ghost / n_ghost: force passes that also pruned
+    } else {
+        launch_force(true);
+    }
     ev = stage_begin();
     kick2_kernel<<<nb_atoms(), kBlock, 0, st>>>(c, a, ctrl, v[0], v[1], v[2], f[0], f[1], f[2], partial_ekin, partial_pred);
     check_launch("kick2");
@@ -793,6 +824,8 @@ void ljgpu_sim::run_steps(unsigned first, unsigned nsteps, double dt) {
         for (unsigned k = 0; k < batch; ++k) enqueue_step(step + k, dt);
         fetch_ctrl();
         const unsigned done = h_ctrl->steps_done;
+        if (prune_skin > 0.0 && h_ctrl->vmax_last > 0.0)     // steps until the fastest atom has covered s_in/2, with margin
+            prune_interval = std::max(1u, (unsigned)(0.85 * c.prune_half / (h_ctrl->vmax_last * dt)));
         step += done; remaining -= done; steps += done; since_rebuild += done;
         if (done) dirty_since_rebuild = true;
         if (h_ctrl->stop) rebuild();
@@ -1171,7 +1204,7 @@ int ljgpu_get_layout(ljgpu_sim* s, int32_t* force_kernel, uint32_t* cells_per_ax
         if (force_kernel) *force_kernel = s->mode;
         if (cells_per_axis) *cells_per_axis = s->nc;
         if (list_capacity) *list_capacity = 8 * s->capq;
-        if (n_ghosts) *n_ghosts = 0;      // no ghost atoms in this layout: periodic images are resolved per pair
+        if (n_ghosts) { s->fetch_ctrl(); *n_ghosts = s->h_ctrl->inner_used; }   // steps served by the pruned inner list (no ghost atoms exist in this layout)
     });
 }
 

@@ -109,12 +109,15 @@ __device__ __forceinline__ size_t nl16_index(unsigned i, unsigned k, unsigned ca
     return ((((size_t)(i >> 5) * capq + (k >> 3)) * 32 + (i & 31u)) * 8) + (k & 7u);
 }
 
-enum { TILE_FORCE_LIST = 0, TILE_FORCE_CELL = 1, TILE_LIST_COUNT = 2, TILE_LIST_FILL = 3 };
+enum { TILE_FORCE_LIST = 0, TILE_FORCE_CELL = 1, TILE_LIST_COUNT = 2, TILE_LIST_FILL = 3, TILE_PRUNE = 4,
+       TILE_FORCE_PRUNE = 5 /* force pass over the outer list that also emits the pruned inner list */ };
 
 struct TileArgs {
     const double4* __restrict__ pos;
     uint32_t* __restrict__ nl32;           // list words (fill: written as uint16 halves)
     uint32_t* __restrict__ nl_count;
+    uint32_t* __restrict__ in32;           // pruned inner list, same layout (null: none)
+    uint32_t* __restrict__ in_count;
     double* __restrict__ fx; double* __restrict__ fy; double* __restrict__ fz;
     double* __restrict__ partial_epot;     // one per CTA
     StepCtrl* ctrl;
@@ -183,6 +186,15 @@ tile_kernel(LJConst c, TileGrid g, TileArgs a, int guarded) {
 
     const unsigned hn = s_hstart[kHomeRowsMax];
     const int far2_hi = __double2hiint(c.far2);
+    // Pruned inner list (entries within rcut + s_in at the last pruning): usable while no pair can have come
+    // closer than s_in since, i.e. while the summed per-step maximum displacement stays below s_in / 2.
+    // Same decision in every block: the inputs were final before this launch.
+    bool use_inner = false;
+    if (MODE == TILE_FORCE_LIST && a.in32 != nullptr) {   // (TILE_FORCE_PRUNE always walks the outer list)
+        const double bound = a.ctrl->drift_bound + sqrt(__longlong_as_double((long long)a.ctrl->vmax2)) * c.dt;
+        use_inner = a.ctrl->inner_valid != 0u && bound <= c.prune_half;
+        if (use_inner && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&a.ctrl->inner_used, 1u);
+    }
     double etot = 0.0;
     unsigned maxcnt = 0;
 
@@ -200,6 +212,8 @@ tile_kernel(LJConst c, TileGrid g, TileArgs a, int guarded) {
         double ax = 0.0, ay = 0.0, az = 0.0, e = 0.0;
         unsigned nacc = 0, cnt = 0;
         uint4 quad = make_uint4(0u, 0u, 0u, 0u);
+        unsigned short* __restrict__ in16 = (MODE == TILE_FORCE_PRUNE)
+            ? reinterpret_cast<unsigned short*>(a.in32) + (((size_t)(i >> 5) * a.capq) * 32 + (i & 31u)) * 8 : nullptr;
 
 #define LJ_TILE_PAIR(J)                                                                     \
         {                                                                                   \
@@ -218,7 +232,7 @@ tile_kernel(LJConst c, TileGrid g, TileArgs a, int guarded) {
             }                                                                               \
         }
 
-        if (MODE == TILE_FORCE_LIST) {
+        if (MODE == TILE_FORCE_LIST || MODE == TILE_FORCE_PRUNE) {
             // Branch-free groups of four entries: all twelve shared-memory loads and the four
             // distance evaluations are issued back to back and the Lennard-Jones term is evaluated
             // for every entry, accumulated under a predicate.  (With 32 lanes and ~60 % of the entries
@@ -226,8 +240,8 @@ tile_kernel(LJConst c, TileGrid g, TileArgs a, int guarded) {
             // without the branches the four dependent chains overlap.)  The only branch left is the
             // rare minimum-image fix-up for pairs that straddle the box.  List quads (8 entries) are
             // fetched one iteration ahead with a single 128-bit load.
-            const unsigned n = a.nl_count[i];
-            const uint4* __restrict__ row = reinterpret_cast<const uint4*>(a.nl32) + ((size_t)(i >> 5) * a.capq) * 32 + (i & 31u);
+            const unsigned n = use_inner ? a.in_count[i] : a.nl_count[i];
+            const uint4* __restrict__ row = reinterpret_cast<const uint4*>(use_inner ? a.in32 : a.nl32) + ((size_t)(i >> 5) * a.capq) * 32 + (i & 31u);
             const unsigned nq = (n + 7) >> 3;
             const uint32_t selfw = li | (li << 16);
             uint4 cur = make_uint4(selfw, selfw, selfw, selfw);
@@ -280,10 +294,57 @@ tile_kernel(LJConst c, TileGrid g, TileArgs a, int guarded) {
                         e += t;
                         ax = fma(fr, dx[u], ax); ay = fma(fr, dy[u], ay); az = fma(fr, dz[u], az);
                         nacc += in ? 1u : 0u;
+                        if (MODE == TILE_FORCE_PRUNE) {
+                            // by-product: the entries still within rcut + s_in form the inner list of the coming steps
+                            if (d2[u] <= c.prune_cut2 && jj[u] != li) {
+                                in16[(size_t)(cnt >> 3) * 256 + (cnt & 7u)] = (unsigned short)jj[u];   // quad stride: 32 lanes x 8 entries
+                                ++cnt;
+                            }
+                        }
                     }
                 }
                 cur = nxt;
             }
+        } else if (MODE == TILE_PRUNE) {
+            // inner list = the outer-list entries that are within rcut + s_in right now
+            const unsigned n = a.nl_count[i];
+            const uint4* __restrict__ row = reinterpret_cast<const uint4*>(a.nl32) + ((size_t)(i >> 5) * a.capq) * 32 + (i & 31u);
+            uint4* __restrict__ orow = reinterpret_cast<uint4*>(a.in32) + ((size_t)(i >> 5) * a.capq) * 32 + (i & 31u);
+            const unsigned nq = (n + 7) >> 3;
+            for (unsigned q = 0; q < nq; ++q) {
+                const uint4 cur = __ldg(row + (size_t)q * 32);
+                const uint32_t w[4] = {cur.x, cur.y, cur.z, cur.w};
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const unsigned j = (w[u >> 1] >> ((u & 1) * 16)) & 0xffffu;
+                    const double* pj = sm + 3 * (size_t)j;
+                    double dx = pix - pj[0], dy = piy - pj[1], dz = piz - pj[2];
+                    double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
+                    if (maybe_wrapped(d2, far2_hi)) {
+                        dx = min_image(dx, c.L, c.halfL); dy = min_image(dy, c.L, c.halfL); dz = min_image(dz, c.L, c.halfL);
+                        d2 = fma(dz, dz, fma(dy, dy, dx * dx));
+                    }
+                    if (d2 <= c.prune_cut2 && j != li && q * 8 + u < n) {
+                        const unsigned slot = cnt & 7u;
+                        const uint32_t val = j << ((slot & 1u) * 16);
+                        const unsigned wsel = slot >> 1;
+                        quad.x |= wsel == 0 ? val : 0u; quad.y |= wsel == 1 ? val : 0u;
+                        quad.z |= wsel == 2 ? val : 0u; quad.w |= wsel == 3 ? val : 0u;
+                        if (slot == 7u) { orow[(size_t)(cnt >> 3) * 32] = quad; quad = make_uint4(0u, 0u, 0u, 0u); }
+                        ++cnt;
+                    }
+                }
+            }
+            if (cnt & 7u) {
+                for (unsigned slot = cnt & 7u; slot < 8u; ++slot) {
+                    const uint32_t val = li << ((slot & 1u) * 16);
+                    const unsigned wsel = slot >> 1;
+                    quad.x |= wsel == 0 ? val : 0u; quad.y |= wsel == 1 ? val : 0u;
+                    quad.z |= wsel == 2 ? val : 0u; quad.w |= wsel == 3 ? val : 0u;
+                }
+                orow[(size_t)(cnt >> 3) * 32] = quad;
+            }
+            a.in_count[i] = cnt;
         } else {
             // home cell of this atom along x, then the 3x3 x-rows around it: 3 consecutive tile cells each
             unsigned h = 0;
@@ -345,9 +406,15 @@ tile_kernel(LJConst c, TileGrid g, TileArgs a, int guarded) {
         }
 #undef LJ_TILE_PAIR
 
-        if (MODE == TILE_FORCE_LIST || MODE == TILE_FORCE_CELL) {
+        if (MODE == TILE_FORCE_PRUNE) {
+            for (unsigned k = cnt; k & 7u; ++k)               // the unused tail of the last quad points at the atom itself
+                in16[(size_t)(k >> 3) * 256 + (k & 7u)] = (unsigned short)li;
+            a.in_count[i] = cnt;
+        }
+        if (MODE == TILE_FORCE_LIST || MODE == TILE_FORCE_CELL || MODE == TILE_FORCE_PRUNE) {
             a.fx[i] = ax * c.prefctr; a.fy[i] = ay * c.prefctr; a.fz[i] = az * c.prefctr;
             etot += fma(-(double)nacc, c.ecut, e);
+        } else if (MODE == TILE_PRUNE) {
         } else {
             if (MODE == TILE_LIST_FILL && (cnt & 7u) && (cnt >> 3) < a.capq) {
                 // flush the last, partial quad; its unused tail points at the atom itself
@@ -364,7 +431,7 @@ tile_kernel(LJConst c, TileGrid g, TileArgs a, int guarded) {
         }
     }
 
-    if (MODE == TILE_FORCE_LIST || MODE == TILE_FORCE_CELL) {
+    if (MODE == TILE_FORCE_LIST || MODE == TILE_FORCE_CELL || MODE == TILE_FORCE_PRUNE) {
         // one partial per CTA without a block barrier (a finished warp frees its issue slots at once): every
         // warp parks its sum in shared memory, the last one to arrive adds them in warp order (fixed order
         // => reproducible) and writes the CTA's partial
@@ -380,7 +447,7 @@ tile_kernel(LJConst c, TileGrid g, TileArgs a, int guarded) {
                 a.partial_epot[blockIdx.x] = tot;
             }
         }
-    } else {
+    } else if (MODE != TILE_PRUNE) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) maxcnt = max(maxcnt, __shfl_xor_sync(0xffffffffu, maxcnt, o));
         if ((threadIdx.x & 31) == 0 && maxcnt) {

@@ -18,7 +18,7 @@ def run(n, kernel, steps, rho=0.8, kT=1.0, warm=200):
     t5 = time.time(); g.integrate_n(warm + steps + 1, steps, 0.001); e = g.get_energies(); t6 = time.time()
     print(f"N={n} kernel={kernel} layout={g.get_layout()} init {t1-t0:.2f}s create {t2-t1:.2f}s")
     print(f"  profiled: {n*steps/(t4-t3):.3e} atom-steps/s   unprofiled: {n*steps/(t6-t5):.3e} atom-steps/s  ({(t6-t5)/steps*1e6:.1f} us/step)")
-    for k in ("predict", "kick_drift", "force", "kick2", "rebuild"):
+    for k in ("predict", "kick_drift", "ghost", "force", "kick2", "rebuild"):
         ms, c = tm["ms_" + k], tm["n_" + k]
         if c: print(f"  {k:10s} {ms:9.3f} ms total  {c:6d} calls  {ms/c*1e3:9.2f} us/call   {ms/ (t4-t3)/10:.1f}% of wall")
     print("  energies", e, "rebuilds", tm["rebuilds"], "launches", tm["kernel_launches"])
