@@ -217,3 +217,24 @@ def test_rejects_small_boxes_and_bad_arguments(lj):
         g.get_speed_histogram(0, 10.0)
     with pytest.raises(lj.LJGpuError):
         g.set_param("cell_length", 20.0)
+
+
+def test_pruned_inner_list_is_bit_identical_to_outer_list(lj, monkeypatch):
+    """The pruned inner list only drops entries that are outside the cutoff anyway (they contribute exact
+    zeros), so a run with pruning must equal a run without it bit for bit - across prunings and re-binnings."""
+    cfg = ol.config(16384)
+    o = equilibrated_state(cfg, 150)
+    st = o.state()
+    params = lj.LennardJonesParameters(**cfg)
+    monkeypatch.setenv("LJGPU_PRUNE_SKIN", "0")
+    a = lj.LennardJonesSimulation(params, st, force_kernel=3)
+    monkeypatch.setenv("LJGPU_PRUNE_SKIN", "0.12")
+    b = lj.LennardJonesSimulation(params, st, force_kernel=3)
+    a.integrate_n(1, 120, DT)
+    b.integrate_n(1, 120, DT)
+    assert b.get_layout()["n_ghosts"] > 60          # most steps were served by the inner list
+    assert a.get_layout()["n_ghosts"] == 0
+    assert a.get_energies() == b.get_energies()
+    for u, v in zip(a.get_forces_soa() + a.get_positions_soa(), b.get_forces_soa() + b.get_positions_soa()):
+        assert np.array_equal(u, v)
+    assert b.get_timers()["rebuilds"] >= 2
