@@ -83,6 +83,8 @@ struct StepCtrl {
     unsigned long long maxdisp2;  // bits of max_i |dij_i|^2 of the current step (when above the threshold)
     unsigned int stop;            // a re-binning is due: remaining steps of the batch do nothing
     unsigned int steps_done;      // steps completed in the current batch
+    unsigned int next_step;       // the `step` argument of the integrate() call being executed (history, log cadence)
+    unsigned int pad0;
     unsigned int overflow;        // list capacity exceeded during a build
     unsigned int max_count;       // max list length seen by the last build
     unsigned int max_tile;        // largest shared-memory tile (atoms) over all home blocks

@@ -166,17 +166,38 @@ force_allpairs_kernel(LJConst c, const StepCtrl* __restrict__ ctrl, const double
         if (jl < j1) { const double4 q = pos[jl]; sx[threadIdx.x] = q.x; sy[threadIdx.x] = q.y; sz[threadIdx.x] = q.z; }
         __syncthreads();
         const unsigned cnt = min((unsigned)kApTile, j1 - jb);
-        if (active) {
-#pragma unroll 4
-            for (unsigned jj = 0; jj < cnt; ++jj) {
-                const double dx = min_image(xsub(pi.x, sx[jj]), c.L, c.halfL);
-                const double dy = min_image(xsub(pi.y, sy[jj]), c.L, c.halfL);
-                const double dz = min_image(xsub(pi.z, sz[jj]), c.L, c.halfL);
-                const double d2 = xnorm2(dx, dy, dz);
-                if (d2 < c.rc2 && (jb + jj) != i) {
-                    const double fr = lj_pair(d2, c.sigma2, e);
-                    ax = fma(fr, dx, ax); ay = fma(fr, dy, ay); az = fma(fr, dz, az);
-                    ++nacc;
+        // Four j per round, branch-free: the reference's one-shot minimum image (.cpp:295-302) as a selected
+        // shift (d + s with s in {-L, 0, +L} is the same rounded value as d - L / d + L / d), d2 formed
+        // without contraction exactly like .cpp:304; the Lennard-Jones term is evaluated only when some lane
+        // of the warp has an in-cutoff pair (1.3 % of all pairs are), and merged with selects.
+        for (unsigned jj0 = 0; jj0 < cnt; jj0 += 4) {
+            double dx[4], dy[4], dz[4], d2[4];
+            bool in[4];
+            bool any = false;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const unsigned jj = min(jj0 + u, cnt - 1);
+                double ex = xsub(pi.x, sx[jj]), ey = xsub(pi.y, sy[jj]), ez = xsub(pi.z, sz[jj]);
+                ex = xadd(ex, ex >= c.halfL ? -c.L : (ex < -c.halfL ? c.L : 0.0));
+                ey = xadd(ey, ey >= c.halfL ? -c.L : (ey < -c.halfL ? c.L : 0.0));
+                ez = xadd(ez, ez >= c.halfL ? -c.L : (ez < -c.halfL ? c.L : 0.0));
+                dx[u] = ex; dy[u] = ey; dz[u] = ez;
+                d2[u] = xnorm2(ex, ey, ez);
+                in[u] = active && d2[u] < c.rc2 && (jb + jj0 + u) != i && (jj0 + u) < cnt;
+                any = any || in[u];
+            }
+            if (__any_sync(0xffffffffu, any)) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const double inv = fast_rcp(in[u] ? d2[u] : 1.0);
+                    const double s2 = c.sigma2 * inv;
+                    const double s6 = s2 * s2 * s2;
+                    const double t0 = fma(s6, s6, -s6);
+                    const double fr0 = fma(s6, s6, t0) * inv;
+                    const double t = in[u] ? t0 : 0.0, fr = in[u] ? fr0 : 0.0;
+                    e += t;
+                    ax = fma(fr, dx[u], ax); ay = fma(fr, dy[u], ay); az = fma(fr, dz[u], az);
+                    nacc += in[u] ? 1u : 0u;
                 }
             }
         }
@@ -316,7 +337,7 @@ kick2_kernel(LJConst c, double a, const StepCtrl* __restrict__ ctrl,
 
 // Final reductions in fixed order, energies (.cpp:95-96, :327-329, :361), history, rebuild flag.
 __global__ void __launch_bounds__(kFinalizeThreads)
-step_finalize_kernel(LJConst c, StepCtrl* __restrict__ ctrl, HistEntry* __restrict__ hist, unsigned step,
+step_finalize_kernel(LJConst c, StepCtrl* __restrict__ ctrl, HistEntry* __restrict__ hist,
                      const double* __restrict__ partial_epot, unsigned nb_epot,
                      const double* __restrict__ partial_ekin, const double* __restrict__ partial_pred,
                      unsigned nb_kick) {
@@ -333,7 +354,8 @@ step_finalize_kernel(LJConst c, StepCtrl* __restrict__ ctrl, HistEntry* __restri
         ctrl->pred_sum = sp;
         ctrl->ekin = ekin; ctrl->epot = epot; ctrl->etot = xadd(ekin, epot);
         HistEntry& h = hist[ctrl->hist_head % kHistCap];
-        h.ekin = ekin; h.epot = epot; h.step = step; h.pad = 0;
+        h.ekin = ekin; h.epot = epot; h.step = ctrl->next_step; h.pad = 0;
+        ctrl->next_step += 1;
         ctrl->hist_head += 1;
         ctrl->steps_done += 1;
         if (__longlong_as_double((long long)ctrl->maxdisp2) > c.disp_thresh) ctrl->stop = 1;
@@ -508,7 +530,7 @@ halo_push_kernel(const StepCtrl* __restrict__ ctrl, const double4* __restrict__ 
 // Local reductions + all-reduce through the mailboxes + publication, one launch.
 //   what: 0 = full step, 1 = constructor (epot only), 2 = predict (pred_sum only)
 __global__ void __launch_bounds__(kFinalizeThreads)
-slab_exchange_kernel(LJConst c, StepCtrl* __restrict__ ctrl, HistEntry* __restrict__ hist, unsigned step, int what,
+slab_exchange_kernel(LJConst c, StepCtrl* __restrict__ ctrl, HistEntry* __restrict__ hist, int what,
                      const double* __restrict__ partial_epot, unsigned nb_epot,
                      const double* __restrict__ partial_ekin, const double* __restrict__ partial_pred, unsigned nb_kick,
                      Mailbox* mine, Mailbox* const* __restrict__ peers, int rank, int world, unsigned long long seq) {
@@ -555,7 +577,8 @@ slab_exchange_kernel(LJConst c, StepCtrl* __restrict__ ctrl, HistEntry* __restri
         ctrl->pred_sum = g[2];
         ctrl->ekin = ekin; ctrl->epot = epot; ctrl->etot = xadd(ekin, epot);
         HistEntry& h = hist[ctrl->hist_head % kHistCap];
-        h.ekin = ekin; h.epot = epot; h.step = step; h.pad = 0;
+        h.ekin = ekin; h.epot = epot; h.step = ctrl->next_step; h.pad = 0;
+        ctrl->next_step += 1;
         ctrl->hist_head += 1;
         ctrl->steps_done += 1;
         if (g[3] > 0.0) ctrl->stop = 1;
@@ -563,7 +586,7 @@ slab_exchange_kernel(LJConst c, StepCtrl* __restrict__ ctrl, HistEntry* __restri
 }
 
 // what: 0 = full step (energies, history, rebuild flag), 1 = constructor (epot only), 2 = predict (pred_sum only)
-__global__ void slab_publish_kernel(LJConst c, StepCtrl* __restrict__ ctrl, HistEntry* __restrict__ hist, unsigned step, int what) {
+__global__ void slab_publish_kernel(LJConst c, StepCtrl* __restrict__ ctrl, HistEntry* __restrict__ hist, int what) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     if (what == 2) { ctrl->pred_sum = ctrl->red[2]; return; }
     const double se = ctrl->red[0];
@@ -575,7 +598,8 @@ __global__ void slab_publish_kernel(LJConst c, StepCtrl* __restrict__ ctrl, Hist
     ctrl->pred_sum = ctrl->red[2];
     ctrl->ekin = ekin; ctrl->epot = epot; ctrl->etot = xadd(ekin, epot);
     HistEntry& h = hist[ctrl->hist_head % kHistCap];
-    h.ekin = ekin; h.epot = epot; h.step = step; h.pad = 0;
+    h.ekin = ekin; h.epot = epot; h.step = ctrl->next_step; h.pad = 0;
+        ctrl->next_step += 1;
     ctrl->hist_head += 1;
     ctrl->steps_done += 1;
     if (ctrl->red[3] > 0.0) ctrl->stop = 1;

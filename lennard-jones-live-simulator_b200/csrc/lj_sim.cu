@@ -81,6 +81,8 @@ struct Slab {
 
 } // namespace
 
+static void set_tile_attributes(size_t smem);
+
 struct ljgpu_sim {
     std::mutex mu;
     ljgpu_params p{};
@@ -113,6 +115,7 @@ struct ljgpu_sim {
 
     // shared-memory tiles (lj_tile.cuh) and the Verlet list of 16-bit tile indices
     uint32_t *tsrc = nullptr, *toff = nullptr;
+    unsigned bxd = kTileBX, byd = kTileBY, bzd = kTileBZ;      // brick size in cells
     unsigned nbx = 0, nby = 0, nbz = 0, nblocks_tile = 0, tcap = 0, tile_threads = 128;
     uint32_t* nl = nullptr; uint32_t* nl_count = nullptr; unsigned capq = 0; size_t nl_alloc = 0;
     // pruned inner list (single-device Verlet path)
@@ -129,6 +132,12 @@ struct ljgpu_sim {
 
     // staging for queries
     double* out3 = nullptr; uint32_t* out_u32 = nullptr; unsigned long long* hist_counts = nullptr;
+
+    // CUDA graphs of one step (plain / pruning), re-captured after every re-binning or dt change
+    struct StepGraph { cudaGraphExec_t exec = nullptr; uint64_t kernels = 0; uint64_t cnt[ST_COUNT] = {0}; };
+    StepGraph graphs[2];
+    uint64_t graph_epoch = ~0ull; double graph_dt = 0.0;
+    unsigned* h_scalar = nullptr;     // pinned scratch for 4-byte uploads
 
     // stepping bookkeeping
     bool pred_valid = false; double pred_dt = 0.0;
@@ -175,7 +184,14 @@ struct ljgpu_sim {
         }
         pending.clear();
     }
-    void sync() { CK(cudaStreamSynchronize(st)); resolve_pending(); }
+    // Busy-wait on the stream instead of a blocking synchronize: the step loop syncs a few times per
+    // re-binning and a sleeping host thread that is slow to wake up costs more than the spin.
+    void sync() {
+        cudaError_t e;
+        while ((e = cudaStreamQuery(st)) == cudaErrorNotReady) { }
+        if (e != cudaSuccess) throw LjError(LJGPU_ECUDA, std::string("stream: ") + cudaGetErrorString(e));
+        resolve_pending();
+    }
     void check_launch(const char* what) {
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) throw LjError(LJGPU_ECUDA, std::string(what) + " launch: " + cudaGetErrorString(e));
@@ -186,7 +202,7 @@ struct ljgpu_sim {
     unsigned nb_atoms() const { return std::max(1u, cdiv(n, kBlock)); }
     TileGrid tile_grid() const {
         return TileGrid{nc, ncz, slab.on ? 0u : 1u, slab.on ? 1u : 0u, slab.on ? slab.nzl : nc,
-                        nbx, nby, nbz, nblocks_tile, tsrc, toff};
+                        bxd, byd, bzd, nbx, nby, nbz, nblocks_tile, tsrc, toff};
     }
 
     void setup_constants();
@@ -199,14 +215,16 @@ struct ljgpu_sim {
     void halo_exchange();
     void allreduce_red();
     void setup_p2p();
-    void slab_finalize(int what, unsigned step, unsigned nb_epot, const double* pekin, unsigned nb_kick);
+    void slab_finalize(int what, unsigned nb_epot, const double* pekin, unsigned nb_kick);
     void rebuild();
     void build_list();
     void launch_force(bool timed);
     void initial_forces();
     void finalize_epot_only();
     void launch_predict(double dt);
-    void enqueue_step(unsigned step, double dt);
+    void enqueue_step(bool prune_now, double dt);
+    void launch_step(double dt);
+    void drop_graphs();
     void run_steps(unsigned first, unsigned nsteps, double dt);
     void fetch_ctrl() {
         CK(cudaMemcpyAsync(h_ctrl, ctrl, sizeof(StepCtrl), cudaMemcpyDeviceToHost, st));
@@ -236,6 +254,8 @@ ljgpu_sim::~ljgpu_sim() {
     dfree(slab.mail); dfree(slab.d_peer_mail); dfree(slab.push_ticket);
     if (slab.h_xchg) cudaFreeHost(slab.h_xchg);
     if (h_ctrl) cudaFreeHost(h_ctrl);
+    if (h_scalar) cudaFreeHost(h_scalar);
+    for (auto& g : graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     sort_scratch_free(scr);
     for (auto& q : pending) { cudaEventDestroy(q.a); cudaEventDestroy(q.b); }
     for (auto e : pool) cudaEventDestroy(e);
@@ -298,6 +318,7 @@ void ljgpu_sim::allocate() {
     CK(cudaMalloc(&orig, A * 4));
     CK(cudaMalloc(&ctrl, sizeof(StepCtrl))); CK(cudaMemset(ctrl, 0, sizeof(StepCtrl)));
     CK(cudaMallocHost(&h_ctrl, sizeof(StepCtrl))); std::memset(h_ctrl, 0, sizeof(StepCtrl));
+    CK(cudaMallocHost(&h_scalar, 64));
     CK(cudaMalloc(&hist, sizeof(HistEntry) * kHistCap)); CK(cudaMemset(hist, 0, sizeof(HistEntry) * kHistCap));
     CK(cudaMalloc(&out3, 3 * N * 8));
     CK(cudaMalloc(&out_u32, N * 4));
@@ -316,8 +337,15 @@ void ljgpu_sim::allocate() {
         CK(cudaMalloc(&nl_count, A * 4));
         if (prune_skin > 0.0) CK(cudaMalloc(&nl_in_count, A * 4));
         const unsigned nhz = slab.on ? slab.nzl : nc;
-        nbx = cdiv(nc, kTileBX); nby = cdiv(nc, kTileBY); nbz = cdiv(nhz, kTileBZ);
-        nblocks_tile = nbx * nby * nbz;
+        // brick = 3x2x2 cells when there are plenty of them; small systems (and thin slabs) get smaller bricks
+        // so that the grid still covers the 148 SMs several times over
+        bxd = kTileBX; byd = kTileBY; bzd = kTileBZ;
+        auto count_blocks = [&] { nbx = cdiv(nc, bxd); nby = cdiv(nc, byd); nbz = cdiv(nhz, bzd); nblocks_tile = nbx * nby * nbz; };
+        count_blocks();
+        while (nblocks_tile < 6u * 148u && bxd * byd * bzd > 1) {
+            if (bxd > 1 && bxd >= byd && bxd >= bzd) --bxd; else if (byd > 1 && byd >= bzd) --byd; else --bzd;
+            count_blocks();
+        }
         CK(cudaMalloc(&tsrc, (size_t)nblocks_tile * kTileCellsMax * 4));
         CK(cudaMalloc(&toff, (size_t)nblocks_tile * (kTileCellsMax + 1) * 4));
         nb_force = nblocks_tile;                                   // one partial per CTA
@@ -550,10 +578,10 @@ void ljgpu_sim::allreduce_red() {
 
 // Slab path: local sums -> global sums -> publication.  Over peer memory this is ONE kernel (mailbox
 // all-reduce inside); on the NCCL fallback it is reduce kernel + ncclAllReduce + publish kernel.
-void ljgpu_sim::slab_finalize(int what, unsigned step, unsigned nb_epot, const double* pekin, unsigned nb_kick) {
+void ljgpu_sim::slab_finalize(int what, unsigned nb_epot, const double* pekin, unsigned nb_kick) {
     if (slab.p2p) {
         ++slab.red_seq;
-        slab_exchange_kernel<<<1, kFinalizeThreads, 0, st>>>(c, ctrl, hist, step, what, partial_epot, nb_epot, pekin, partial_pred, nb_kick,
+        slab_exchange_kernel<<<1, kFinalizeThreads, 0, st>>>(c, ctrl, hist, what, partial_epot, nb_epot, pekin, partial_pred, nb_kick,
                                                              slab.mail, slab.d_peer_mail, slab.rank, slab.world, slab.red_seq);
         check_launch("slab_exchange");
         return;
@@ -561,7 +589,7 @@ void ljgpu_sim::slab_finalize(int what, unsigned step, unsigned nb_epot, const d
     slab_reduce_kernel<<<1, kFinalizeThreads, 0, st>>>(c, ctrl, partial_epot, nb_epot, pekin, partial_pred, nb_kick);
     check_launch("slab_reduce");
     allreduce_red();
-    slab_publish_kernel<<<1, 32, 0, st>>>(c, ctrl, hist, step, what);
+    slab_publish_kernel<<<1, 32, 0, st>>>(c, ctrl, hist, what);
     check_launch("slab_publish");
 }
 
@@ -631,11 +659,13 @@ void ljgpu_sim::rebuild() {
     check_launch("tile_table");
     fetch_ctrl();
     tcap = ((h_ctrl->max_tile + 15) / 16) * 16;
-    tile_threads = std::min((unsigned)LJ_TILE_MAXTHREADS, std::max(64u, ((h_ctrl->max_home + 31) / 32) * 32));
+    tile_threads = std::min((unsigned)LJ_TILE_MAXTHREADS, std::max(32u, ((h_ctrl->max_home + 31) / 32) * 32));
     nb_force = nblocks_tile;
     if ((size_t)tcap * 24 > 200 * 1024)
         throw LjError(LJGPU_ESTATE, "a cell neighbourhood does not fit in shared memory (density too inhomogeneous)");
     if (h_ctrl->max_tile > 65535) throw LjError(LJGPU_ESTATE, "tile too large for 16-bit list indices");
+    set_tile_attributes((size_t)tcap * 24);
+    drop_graphs();                                   // buffers were swapped, launch shapes may have changed
 
     lap("tile_table");
     if (mode == LJGPU_KERNEL_VERLET) build_list();
@@ -650,15 +680,25 @@ void ljgpu_sim::rebuild() {
 template <int MODE, bool UNIT_SIGMA>
 static void launch_tile2(ljgpu_sim* s, int guarded) {
     const size_t smem = (size_t)s->tcap * 24;
-    // static shared memory counts against the 48 KB default too: opt in well before the limit
-    if (smem > 40 * 1024)
-        CK(cudaFuncSetAttribute(tile_kernel<MODE, UNIT_SIGMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     TileArgs a{s->pos, s->nl, s->nl_count, s->prune_skin > 0.0 ? s->nl_in : nullptr, s->nl_in_count,
                s->f[0], s->f[1], s->f[2], s->partial_epot, s->ctrl, s->capq,
                s->slab.p2p ? s->slab.mail : nullptr, s->slab.halo_seq};
     tile_kernel<MODE, UNIT_SIGMA><<<s->nblocks_tile, s->tile_threads, smem, s->st>>>(s->c, s->tile_grid(), a, guarded);
     s->check_launch("tile_kernel");
 }
+// Static shared memory counts against the 48 KB default too: opt in well before the limit.  Done at
+// re-binning time (never inside a stream capture).
+template <int MODE, bool US>
+static void tile_attr(size_t smem) {
+    CK(cudaFuncSetAttribute(tile_kernel<MODE, US>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+}
+static void set_tile_attributes(size_t smem) {
+    if (smem <= 40 * 1024) return;
+    tile_attr<TILE_FORCE_LIST, true>(smem); tile_attr<TILE_FORCE_LIST, false>(smem);
+    tile_attr<TILE_FORCE_PRUNE, true>(smem); tile_attr<TILE_FORCE_PRUNE, false>(smem);
+    tile_attr<TILE_FORCE_CELL, false>(smem); tile_attr<TILE_LIST_COUNT, false>(smem); tile_attr<TILE_LIST_FILL, false>(smem);
+}
+
 template <int MODE>
 static void launch_tile(ljgpu_sim* s, int guarded) {
     if ((MODE == TILE_FORCE_LIST || MODE == TILE_FORCE_PRUNE) && s->c.sigma2 == 1.0) launch_tile2<MODE, true>(s, guarded);
@@ -735,7 +775,7 @@ void ljgpu_sim::launch_force(bool timed) {
 
 void ljgpu_sim::finalize_epot_only() {
     if (slab.on) {
-        slab_finalize(1, 0, nb_force, nullptr, 0);
+        slab_finalize(1, nb_force, nullptr, 0);
     } else {
         init_finalize_kernel<<<1, kFinalizeThreads, 0, st>>>(c, ctrl, partial_epot, nb_force);
         check_launch("init_finalize");
@@ -756,7 +796,7 @@ void ljgpu_sim::launch_predict(double dt) {
     predict_kernel<<<nb_atoms(), kBlock, 0, st>>>(n, a, v[0], v[1], v[2], f[0], f[1], f[2], partial_pred);
     check_launch("predict");
     if (slab.on) {
-        slab_finalize(2, 0, 0, nullptr, nb_atoms());
+        slab_finalize(2, 0, nullptr, nb_atoms());
     } else {
         predict_finalize_kernel<<<1, kFinalizeThreads, 0, st>>>(ctrl, partial_pred, nb_atoms());
         check_launch("predict_finalize");
@@ -765,7 +805,8 @@ void ljgpu_sim::launch_predict(double dt) {
     pred_valid = true; pred_dt = dt;
 }
 
-void ljgpu_sim::enqueue_step(unsigned step, double dt) {
+// The kernels of one integrate() call (no host decisions inside: capturable into a CUDA graph).
+void ljgpu_sim::enqueue_step(bool prune_now, double dt) {
     const double a = 0.5 * dt / p.mass;                                  // .cpp:339
     c.dt_over_tau = dt / p.tau;                                          // .cpp:375
     c.dt = dt;
@@ -779,13 +820,7 @@ void ljgpu_sim::enqueue_step(unsigned step, double dt) {
     check_launch("kick_drift");
     stage_end(ST_KICK_DRIFT, ev);
     if (slab.on) halo_exchange();
-    bool prune_now = false;
-    if (prune_skin > 0.0) {
-        prune_now = since_prune >= prune_interval;      // this step's force pass walks the outer list and emits the inner one
-        if (prune_now) since_prune = 0;
-        ++since_prune;
-    }
-    if (prune_now) {
+    if (prune_now) {       // this step's force pass walks the outer list and emits the inner one
         cudaEvent_t pv = stage_begin();
         launch_tile<TILE_FORCE_PRUNE>(this, 1);
         prune_commit_kernel<<<1, 1, 0, st>>>(ctrl);
@@ -798,13 +833,50 @@ void ljgpu_sim::enqueue_step(unsigned step, double dt) {
     kick2_kernel<<<nb_atoms(), kBlock, 0, st>>>(c, a, ctrl, v[0], v[1], v[2], f[0], f[1], f[2], partial_ekin, partial_pred);
     check_launch("kick2");
     if (slab.on) {
-        slab_finalize(0, step, nb_force, partial_ekin, nb_atoms());
+        slab_finalize(0, nb_force, partial_ekin, nb_atoms());
     } else {
-        step_finalize_kernel<<<1, kFinalizeThreads, 0, st>>>(c, ctrl, hist, step, partial_epot, nb_force,
+        step_finalize_kernel<<<1, kFinalizeThreads, 0, st>>>(c, ctrl, hist, partial_epot, nb_force,
                                                              partial_ekin, partial_pred, nb_atoms());
         check_launch("step_finalize");
     }
     stage_end(ST_KICK2, ev);
+}
+
+void ljgpu_sim::drop_graphs() {
+    for (auto& g : graphs) { if (g.exec) cudaGraphExecDestroy(g.exec); g = StepGraph(); }
+    graph_epoch = ~0ull;
+}
+
+// One integrate() call: decides on the host whether this step also prunes, then replays the matching
+// CUDA graph (single device, not profiling) or launches the kernels one by one.
+void ljgpu_sim::launch_step(double dt) {
+    bool prune_now = false;
+    if (prune_skin > 0.0) {
+        prune_now = since_prune >= prune_interval;
+        if (prune_now) since_prune = 0;
+        ++since_prune;
+    }
+    static const bool no_graph = std::getenv("LJGPU_NO_GRAPH") != nullptr;
+    if (prof || slab.on || no_graph) { enqueue_step(prune_now, dt); return; }
+    if (graph_epoch != rebuilds || graph_dt != dt) { drop_graphs(); graph_epoch = rebuilds; graph_dt = dt; }
+    StepGraph& g = graphs[prune_now ? 1 : 0];
+    if (!g.exec) {
+        uint64_t cnt0[ST_COUNT]; std::memcpy(cnt0, cnt, sizeof cnt0);
+        const uint64_t l0 = launches;
+        CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        cudaGraph_t graph = nullptr;
+        try { enqueue_step(prune_now, dt); }
+        catch (...) { cudaStreamEndCapture(st, &graph); if (graph) cudaGraphDestroy(graph); throw; }
+        CK(cudaStreamEndCapture(st, &graph));
+        CK(cudaGraphInstantiate(&g.exec, graph, 0));
+        cudaGraphDestroy(graph);
+        g.kernels = launches - l0;
+        for (int k = 0; k < ST_COUNT; ++k) { g.cnt[k] = cnt[k] - cnt0[k]; cnt[k] = cnt0[k]; }
+        launches = l0;
+    }
+    CK(cudaGraphLaunch(g.exec, st));
+    launches += g.kernels;
+    for (int k = 0; k < ST_COUNT; ++k) cnt[k] += g.cnt[k];
 }
 
 // n integrate() calls.  Steps are enqueued in batches without host round trips; once a step finds a
@@ -821,7 +893,9 @@ void ljgpu_sim::run_steps(unsigned first, unsigned nsteps, double dt) {
         else batch = 2;
         batch = std::min(std::min(batch, remaining), 256u);
         CK(cudaMemsetAsync(&ctrl->steps_done, 0, sizeof(unsigned), st));
-        for (unsigned k = 0; k < batch; ++k) enqueue_step(step + k, dt);
+        h_scalar[0] = step;                              // integrate(step, dt): the device counts on from here
+        CK(cudaMemcpyAsync(&ctrl->next_step, h_scalar, sizeof(unsigned), cudaMemcpyHostToDevice, st));
+        for (unsigned k = 0; k < batch; ++k) launch_step(dt);
         fetch_ctrl();
         const unsigned done = h_ctrl->steps_done;
         if (prune_skin > 0.0 && h_ctrl->vmax_last > 0.0)     // steps until the fastest atom has covered s_in/2, with margin
@@ -1022,6 +1096,7 @@ int ljgpu_update_params(ljgpu_sim* s, const ljgpu_params* p) {
         s->setup_constants();
         s->c.dt_over_tau = dto;
         s->pred_valid = false;                         // mass enters the kick factor
+        s->drop_graphs();                              // constants are baked into the captured launches
         if (force_changed) {                           // forces of the current positions under the new potential
             if (s->slab.on) s->halo_exchange();
             s->launch_force(false);

@@ -35,6 +35,7 @@ struct TileGrid {
     unsigned ncz;                // cell layers of the local table (nc, or owned layers + 2 halo layers on a slab)
     unsigned zper;               // z periodic within this table (single device) or bounded by halo layers (slab)
     unsigned hz0, nhz;           // first home layer and number of home layers
+    unsigned bxd, byd, bzd;      // brick size in cells (<= kTileBX, kTileBY, kTileBZ; smaller for small systems)
     unsigned nbx, nby, nbz;      // home blocks per axis
     unsigned nblocks;
     const uint32_t* __restrict__ tsrc;   // [nblocks][kTileCellsMax]     first global slot of each tile cell
@@ -51,10 +52,10 @@ __device__ __forceinline__ TileGeom tile_geometry(unsigned b, const TileGrid& g)
     unsigned bz = b / (g.nbx * g.nby);
     if (!g.zper && g.nbz > 2)        // slab: the two bricks that touch halo layers are scheduled last (they wait for the neighbours)
         bz = bz < g.nbz - 2 ? bz + 1 : (bz == g.nbz - 2 ? 0u : g.nbz - 1);
-    t.x0 = bx * kTileBX; t.y0 = by * kTileBY; t.z0 = g.hz0 + bz * kTileBZ;
-    t.bw = min((unsigned)kTileBX, g.nc - t.x0);
-    t.bh = min((unsigned)kTileBY, g.nc - t.y0);
-    t.bd = min((unsigned)kTileBZ, g.hz0 + g.nhz - t.z0);
+    t.x0 = bx * g.bxd; t.y0 = by * g.byd; t.z0 = g.hz0 + bz * g.bzd;
+    t.bw = min(g.bxd, g.nc - t.x0);
+    t.bh = min(g.byd, g.nc - t.y0);
+    t.bd = min(g.bzd, g.hz0 + g.nhz - t.z0);
     t.W = t.bw + 2; t.H = t.bh + 2;
     return t;
 }
