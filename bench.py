@@ -178,6 +178,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--atoms", type=int, default=1048576, help="atoms of the whole system (strong scaling over --gpus)")
     ap.add_argument("--atoms-per-gpu", type=int, default=0, help="weak scaling instead: this many atoms per device")
+    ap.add_argument("--rho", type=float, default=RHO, help="reduced density (0.84 with --kT 0.72 = triple point, BASELINE configs[4])")
+    ap.add_argument("--kT", type=float, default=KT)
     ap.add_argument("--equil", type=int, default=2000, help="untimed equilibration steps before the warm-up")
     ap.add_argument("--kernel", type=int, default=3, help="LJGPU_KERNEL_* (3 = Verlet list)")
     ap.add_argument("--e2e-steps", type=int, default=200)
@@ -206,7 +208,7 @@ def main():
     lj = importlib.import_module(PKG)
     weak = args.atoms_per_gpu > 0
     n = args.atoms_per_gpu * world if weak else args.atoms
-    cfg = params_dict(n)
+    cfg = params_dict(n, args.rho, args.kT)
     params = lj.LennardJonesParameters(**cfg)
     lj.host_rng_reset()
     state = lj.host_initialize(params)           # every rank builds the same start state (same generator, same seed)
@@ -294,7 +296,7 @@ def main():
     # every force launch: plain passes (inner or outer list) + the passes that also prune
     nf = max(1, timers["n_force"] + timers["n_ghost"])
     force_us = (timers["ms_force"] + timers["ms_ghost"]) / nf * 1e3
-    n_rc = 65.45 * RHO                               # ordered in-cutoff neighbours per atom, SURVEY 8(a)/(d)
+    n_rc = 65.45 * args.rho                          # ordered in-cutoff neighbours per atom, SURVEY 8(a)/(d)
     if layout["force_kernel"] == 3:
         bytes_per_atom = 24 + 24 + 4 * (mean_len + 1)    # x,y,z in + f out + the atom's list
     else:
@@ -320,7 +322,7 @@ def main():
         "metric": "atom-steps/s fp64", "value": value, "unit": "atom-steps/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
         "higher_is_better": True, "scaling": "weak" if weak else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"N={n} LJ liquid rho*=0.8 kT=1 rc=2.5 shell=0.4 tau=0.5 dt=0.001 (BASELINE configs[3])",
+        "config": {"workload": f"N={n} LJ liquid rho*={args.rho:g} kT={args.kT:g} rc=2.5 shell=0.4 tau=0.5 dt=0.001 (BASELINE configs[3])",
                    "force_kernel": {1: "allpairs", 2: "cell", 3: "verlet"}[layout["force_kernel"]],
                    "cells_per_axis": layout["cells_per_axis"], "list_capacity": layout["list_capacity"],
                    "mean_list_length": mean_len, "equilibration_steps": args.equil,

@@ -112,7 +112,6 @@ struct Mailbox {
 constexpr int kHistCap = 4096;    // entries in the energy history ring
 struct HistEntry { double ekin, epot; unsigned int step; unsigned int pad; };
 
-constexpr int kMaxPartials = 1 << 16;   // upper bound on per-block partial sums
 
 // ---------------------------------------------------------------------------------------------
 // Deterministic block reduction (fixed shape => fixed summation order).

@@ -106,9 +106,6 @@ tile_table_kernel(TileGrid g, const uint32_t* __restrict__ cstart, const uint32_
 // one warp-wide 128-bit load fetches 512 contiguous bytes: quad q of slot i starts at 32-bit word
 // (((i>>5)*capq + q)*32 + (i&31))*4.  Entry k of slot i is half-word k&7 of quad k>>3.
 // Replaces the reference's flat [offsets][entries..., sentinel] vector (.cpp:543-550).
-__device__ __forceinline__ size_t nl16_index(unsigned i, unsigned k, unsigned capq) {
-    return ((((size_t)(i >> 5) * capq + (k >> 3)) * 32 + (i & 31u)) * 8) + (k & 7u);
-}
 
 enum { TILE_FORCE_LIST = 0, TILE_FORCE_CELL = 1, TILE_LIST_COUNT = 2, TILE_LIST_FILL = 3, TILE_PRUNE = 4,
        TILE_FORCE_PRUNE = 5 /* force pass over the outer list that also emits the pruned inner list */ };

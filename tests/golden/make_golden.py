@@ -60,6 +60,9 @@ def one(name):
     out = {"config": cfg, "dt": DT, "steps": steps}
     ek, ep, et = sim.energies()
     out["energies"] = [{"step": 0, "ekin": hx(ek), "epot": hx(ep), "etot": hx(et)}]
+    # yardstick: the same pair terms accumulated in long double (oracle/lj_oracle.c, ljo_epot_long_double) -
+    # on the perfect start lattice the reference's single running double sum is measurably off from it
+    out["epot_step0_long_double"] = hx(ol.Oracle(cfg, state=sim.state()).epot_long_double())
     out["list_size_step0"] = sim.list_size()
     cells, dims = sim.cell_ids()
     counts = sim.neighbor_counts()

@@ -1,6 +1,10 @@
 """GPU parity tests: the CUDA integrator (through the C ABI) against the CPU oracle on the same
 seeded inputs.  Tolerances follow BASELINE.json's north_star: integer outputs bit-exact; forces and
 energies within 1e-12 relative over 10-step windows."""
+import json
+import os
+import zlib
+
 import numpy as np
 import pytest
 
@@ -238,3 +242,78 @@ def test_pruned_inner_list_is_bit_identical_to_outer_list(lj, monkeypatch):
     for u, v in zip(a.get_forces_soa() + a.get_positions_soa(), b.get_forces_soa() + b.get_positions_soa()):
         assert np.array_equal(u, v)
     assert b.get_timers()["rebuilds"] >= 2
+
+
+def _crc(a):
+    return zlib.crc32(np.ascontiguousarray(a).tobytes()) & 0xFFFFFFFF
+
+
+def test_full_size_n1048576_against_reference_golden_vectors(lj):
+    """BASELINE configs[3] at full size, without running the oracle here: the golden vectors were
+    written by the reference's own code (tests/golden/make_golden.py).  Integer outputs bit-exact; energies
+    of steps 1-3 to 1e-11; at step 0 (perfect lattice) the reference's single running sum over 5.5e7 pair
+    terms is itself 6e-10 from the exact sum (see check_step), so there the GPU is held to 1e-12 of the
+    long-double re-summation of the same terms and to 2e-9 of the reference's value."""
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_vectors.json")) as fh:
+        g = json.load(fh)["n1048576_rho0.8"]
+    cfg = g["config"]
+    params = lj.LennardJonesParameters(**cfg)
+    lj.host_rng_reset()
+    st = lj.host_initialize(params)
+    assert [_crc(a) for a in st[:3]] == g["step0"]["crc_positions"]
+    assert [_crc(a) for a in st[3:]] == g["step0"]["crc_velocities"]
+    sim = lj.LennardJonesSimulation(params, st)
+    assert sim.get_layout()["force_kernel"] == 3
+    cells, dims = sim.get_cell_ids()
+    assert list(dims) == g["step0"]["cell_dims"] and _crc(cells) == g["step0"]["crc_cell_ids"]
+    counts = sim.get_neighbor_counts(cfg["rcut"] + cfg["shell"], True)
+    assert int(counts.sum()) == g["step0"]["sum_neighbor_counts"] and _crc(counts) == g["step0"]["crc_neighbor_counts"]
+    assert int(counts.sum()) + 2 * cfg["nr_particles"] == g["list_size_step0"]
+    incut = sim.get_neighbor_counts(cfg["rcut"], False)
+    assert int(incut.sum()) == g["step0"]["sum_incutoff_counts"] and _crc(incut) == g["step0"]["crc_incutoff_counts"]
+    for rec in g["energies"]:
+        if rec["step"] > 0:
+            sim.integrate(rec["step"], g["dt"])
+        ek, ep, _ = sim.get_energies()
+        if rec["step"] == 0:
+            # the reference's own running sum is 6e-10 off the exact sum here; the GPU matches the exact sum
+            assert rel(ep, float.fromhex(g["epot_step0_long_double"])) < 1e-12
+            assert rel(ep, float.fromhex(rec["epot"])) < 2e-9
+        else:
+            assert rel(ep, float.fromhex(rec["epot"])) < 1e-11, rec["step"]
+            assert rel(ek, float.fromhex(rec["ekin"])) < 1e-11, rec["step"]
+    assert _crc(sim.get_cell_ids()[0]) == g["final"]["crc_cell_ids"]
+    v = sim.get_velocities_copy()
+    assert np.abs(v.sum(axis=0)).max() < 1e-6            # the reference removes the mean velocity; both kicks keep it
+    x = sim.get_positions_soa()[0]
+    assert np.max(np.abs(x[:8] - np.array([float.fromhex(h) for h in g["final"]["first8"]["x"]]))) < 1e-12
+
+
+def test_nve_energy_conservation_and_thermostat(lj):
+    """Physics checks valid for both implementations (SURVEY.md section 4): Berendsen pulls T to kT;
+    with tau = 1e300 lambda rounds to exactly 1 (NVE through the unchanged API) and the total energy is
+    conserved to the level the reference shows (sigma(Etot)/N of a few 1e-6)."""
+    cfg = ol.config(4096)
+    n = cfg["nr_particles"]
+    _, g = make_pair(lj, cfg, 3)
+    g.integrate_n(1, 3000, DT)
+    t_kin = 2.0 * g.get_ekin() / (3.0 * (n - 1))
+    assert abs(t_kin - cfg["kT"]) < 0.05
+    g.set_param("tau", 1e300)
+    g.integrate_n(3001, 2000, DT)
+    steps, ek, ep = g.get_energy_history(2000)
+    etot = (ek + ep) / n
+    assert etot.std() < 2e-5 and abs(etot[-1] - etot[0]) < 1e-4
+    # speed distribution against Maxwell-Boltzmann at the measured temperature (graphwidget.cpp:55-73)
+    temp = 2.0 * ek.mean() / (3.0 * (n - 1))
+    hist = g.get_speed_histogram(100, 10.0).astype(np.float64)
+    edges = np.linspace(0.0, 10.0, 101)
+    from math import erf, exp, pi, sqrt
+
+    def cdf(v):
+        a = sqrt(temp)
+        return erf(v / (sqrt(2) * a)) - sqrt(2 / pi) * v * exp(-v * v / (2 * a * a)) / a
+    expected = n * np.diff([cdf(e) for e in edges])
+    mask = expected > 5
+    chi2 = float(((hist[mask] - expected[mask]) ** 2 / expected[mask]).sum() / mask.sum())
+    assert chi2 < 2.5 and hist.argmax() in (12, 13, 14, 15)
