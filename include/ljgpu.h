@@ -172,6 +172,8 @@ int ljgpu_write_movie_frame(ljgpu_sim* s, const char* path, int create);
 
 /* ---- introspection --------------------------------------------------------------------------- */
 
+/* enabled = 0 off; 1 = every step timed stage by stage; k > 1 = every k-th step timed (the others run as
+ * CUDA-graph replays), stage times scaled by k so that ms_* / n_* stay per-launch averages. */
 int ljgpu_set_profiling(ljgpu_sim* s, int enabled);
 int ljgpu_get_timers(ljgpu_sim* s, ljgpu_timers* out);
 int ljgpu_reset_timers(ljgpu_sim* s);

@@ -332,7 +332,8 @@ class LennardJonesSimulation:
 
     # -- introspection -------------------------------------------------------------------------
     def set_profiling(self, on):
-        _check(self._lib, self._lib.ljgpu_set_profiling(self._h, 1 if on else 0))
+        """False/0 off, True/1 every step, k > 1 every k-th step (others replay the CUDA graph)."""
+        _check(self._lib, self._lib.ljgpu_set_profiling(self._h, int(on)))
 
     def get_timers(self):
         t = LJTimers()

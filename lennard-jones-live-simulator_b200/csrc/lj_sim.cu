@@ -146,7 +146,10 @@ struct ljgpu_sim {
 
     // profiling
     bool prof = false;
-    struct Pending { int stage; cudaEvent_t a, b; };
+    unsigned prof_every = 1;        // profile every k-th step (the others replay the CUDA graph); stage times are scaled by k
+    unsigned prof_tick = 0;
+    bool prof_this_step = true;
+    struct Pending { int stage; cudaEvent_t a, b; double weight; };
     std::vector<Pending> pending;
     std::vector<cudaEvent_t> pool;
     double ms[ST_COUNT] = {0};
@@ -162,7 +165,7 @@ struct ljgpu_sim {
     }
     // stage timers nest (a re-binning contains halo exchanges): the caller keeps its start event
     cudaEvent_t stage_begin() {
-        if (!prof) return nullptr;
+        if (!prof || !prof_this_step) return nullptr;
         cudaEvent_t a = get_event();
         CK(cudaEventRecord(a, st));
         return a;
@@ -172,13 +175,15 @@ struct ljgpu_sim {
         if (prof && a) {
             cudaEvent_t b = get_event();
             CK(cudaEventRecord(b, st));
-            pending.push_back({stage, a, b});
+            // step stages are sampled every prof_every-th step; re-binning / halo stages are always timed
+            const bool sampled = stage != ST_REBUILD && !(stage == ST_HALO && !slab.on);
+            pending.push_back({stage, a, b, sampled && !slab.on ? (double)prof_every : 1.0});
         }
     }
     void resolve_pending() {      // stream must be idle
         for (auto& q : pending) {
             float t = 0.f;
-            if (cudaEventElapsedTime(&t, q.a, q.b) == cudaSuccess) ms[q.stage] += t;
+            if (cudaEventElapsedTime(&t, q.a, q.b) == cudaSuccess) ms[q.stage] += t * q.weight;
             else cudaGetLastError();
             pool.push_back(q.a); pool.push_back(q.b);
         }
@@ -857,7 +862,14 @@ void ljgpu_sim::launch_step(double dt) {
         ++since_prune;
     }
     static const bool no_graph = std::getenv("LJGPU_NO_GRAPH") != nullptr;
-    if (prof || slab.on || no_graph) { enqueue_step(prune_now, dt); return; }
+    bool timed_step = false;
+    if (prof) { timed_step = slab.on || (prof_tick++ % prof_every) == 0; }
+    if (timed_step || slab.on || no_graph) {
+        prof_this_step = true;
+        enqueue_step(prune_now, dt);
+        return;
+    }
+    prof_this_step = false;          // graph replay (and its capture) carries no event records
     if (graph_epoch != rebuilds || graph_dt != dt) { drop_graphs(); graph_epoch = rebuilds; graph_dt = dt; }
     StepGraph& g = graphs[prune_now ? 1 : 0];
     if (!g.exec) {
@@ -877,6 +889,7 @@ void ljgpu_sim::launch_step(double dt) {
     CK(cudaGraphLaunch(g.exec, st));
     launches += g.kernels;
     for (int k = 0; k < ST_COUNT; ++k) cnt[k] += g.cnt[k];
+    prof_this_step = true;
 }
 
 // n integrate() calls.  Steps are enqueued in batches without host round trips; once a step finds a
@@ -1250,7 +1263,9 @@ int ljgpu_write_movie_frame(ljgpu_sim* s, const char* path, int create) {
 }
 
 int ljgpu_set_profiling(ljgpu_sim* s, int enabled) {
-    return with_sim(s, [&] { s->sync(); s->prof = enabled != 0; });
+    // enabled == 1: every step is timed stage by stage (plain launches); enabled == k > 1: every k-th step is,
+    // the others replay the CUDA graph, and the sampled stage times are scaled by k
+    return with_sim(s, [&] { s->sync(); s->prof = enabled != 0; s->prof_every = enabled > 1 ? (unsigned)enabled : 1u; s->prof_tick = 0; });
 }
 
 int ljgpu_get_timers(ljgpu_sim* s, ljgpu_timers* out) {
