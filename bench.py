@@ -183,7 +183,7 @@ def main():
     ap.add_argument("--equil", type=int, default=2000, help="untimed equilibration steps before the warm-up")
     ap.add_argument("--kernel", type=int, default=3, help="LJGPU_KERNEL_* (3 = Verlet list)")
     ap.add_argument("--e2e-steps", type=int, default=200)
-    ap.add_argument("--profile-every", type=int, default=8,
+    ap.add_argument("--profile-every", type=int, default=5,
                     help="CUDA-event stage timing on every k-th step of the timed region (1 = every step, no graph replay)")
     ap.add_argument("--cpu-steps", type=int, default=20)
     ap.add_argument("--no-cpu", action="store_true")
