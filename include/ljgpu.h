@@ -71,6 +71,7 @@ typedef struct ljgpu_sim ljgpu_sim;   /* opaque */
  * while profiling is enabled (ljgpu_set_profiling), measured with CUDA events on the
  * integrator's own stream. Milliseconds and launch counts. */
 typedef struct ljgpu_timers {
+    /* ms_ghost / n_ghost: force passes that also emitted the pruned inner list (no ghost atoms exist) */
     double   ms_predict, ms_kick_drift, ms_ghost, ms_force, ms_kick2, ms_rebuild, ms_halo;
     uint64_t n_predict, n_kick_drift, n_ghost, n_force, n_kick2, n_rebuild, n_halo;
     uint64_t steps;            /* integrate steps completed                         */
@@ -177,7 +178,9 @@ int ljgpu_write_movie_frame(ljgpu_sim* s, const char* path, int create);
 int ljgpu_set_profiling(ljgpu_sim* s, int enabled);
 int ljgpu_get_timers(ljgpu_sim* s, ljgpu_timers* out);
 int ljgpu_reset_timers(ljgpu_sim* s);
-/* Force path actually in use (LJGPU_KERNEL_*), cells per axis, current list capacity per atom. */
+/* Force path actually in use (LJGPU_KERNEL_*), cells per axis, current list capacity per atom, and - in the
+ * last argument, historically named n_ghosts; this layout has no ghost atoms - the number of steps whose force
+ * pass was served by the pruned inner list. */
 int ljgpu_get_layout(ljgpu_sim* s, int32_t* force_kernel, uint32_t* cells_per_axis,
                      uint32_t* list_capacity, uint64_t* n_ghosts);
 
