@@ -107,7 +107,7 @@ tile_table_kernel(TileGrid g, const uint32_t* __restrict__ cstart, const uint32_
 // (((i>>5)*capq + q)*32 + (i&31))*4.  Entry k of slot i is half-word k&7 of quad k>>3.
 // Replaces the reference's flat [offsets][entries..., sentinel] vector (.cpp:543-550).
 
-enum { TILE_FORCE_LIST = 0, TILE_FORCE_CELL = 1, TILE_LIST_COUNT = 2, TILE_LIST_FILL = 3, TILE_PRUNE = 4,
+enum { TILE_FORCE_LIST = 0, TILE_FORCE_CELL = 1, TILE_LIST_COUNT = 2, TILE_LIST_FILL = 3,
        TILE_FORCE_PRUNE = 5 /* force pass over the outer list that also emits the pruned inner list */ };
 
 struct TileArgs {
@@ -209,9 +209,11 @@ tile_kernel(LJConst c, TileGrid g, TileArgs a, int guarded) {
         const double pix = pi[0], piy = pi[1], piz = pi[2];
         double ax = 0.0, ay = 0.0, az = 0.0, e = 0.0;
         unsigned nacc = 0, cnt = 0;
-        uint4 quad = make_uint4(0u, 0u, 0u, 0u);
+        // entry k of slot i is half-word k&7 of quad k>>3; quads of one slot are 32 lanes x 8 half-words apart
         unsigned short* __restrict__ in16 = (MODE == TILE_FORCE_PRUNE)
             ? reinterpret_cast<unsigned short*>(a.in32) + (((size_t)(i >> 5) * a.capq) * 32 + (i & 31u)) * 8 : nullptr;
+        unsigned short* __restrict__ fill16 = (MODE == TILE_LIST_FILL)
+            ? reinterpret_cast<unsigned short*>(a.nl32) + (((size_t)(i >> 5) * a.capq) * 32 + (i & 31u)) * 8 : nullptr;
 
 #define LJ_TILE_PAIR(J)                                                                     \
         {                                                                                   \
@@ -303,46 +305,6 @@ tile_kernel(LJConst c, TileGrid g, TileArgs a, int guarded) {
                 }
                 cur = nxt;
             }
-        } else if (MODE == TILE_PRUNE) {
-            // inner list = the outer-list entries that are within rcut + s_in right now
-            const unsigned n = a.nl_count[i];
-            const uint4* __restrict__ row = reinterpret_cast<const uint4*>(a.nl32) + ((size_t)(i >> 5) * a.capq) * 32 + (i & 31u);
-            uint4* __restrict__ orow = reinterpret_cast<uint4*>(a.in32) + ((size_t)(i >> 5) * a.capq) * 32 + (i & 31u);
-            const unsigned nq = (n + 7) >> 3;
-            for (unsigned q = 0; q < nq; ++q) {
-                const uint4 cur = __ldg(row + (size_t)q * 32);
-                const uint32_t w[4] = {cur.x, cur.y, cur.z, cur.w};
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const unsigned j = (w[u >> 1] >> ((u & 1) * 16)) & 0xffffu;
-                    const double* pj = sm + 3 * (size_t)j;
-                    double dx = pix - pj[0], dy = piy - pj[1], dz = piz - pj[2];
-                    double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
-                    if (maybe_wrapped(d2, far2_hi)) {
-                        dx = min_image(dx, c.L, c.halfL); dy = min_image(dy, c.L, c.halfL); dz = min_image(dz, c.L, c.halfL);
-                        d2 = fma(dz, dz, fma(dy, dy, dx * dx));
-                    }
-                    if (d2 <= c.prune_cut2 && j != li && q * 8 + u < n) {
-                        const unsigned slot = cnt & 7u;
-                        const uint32_t val = j << ((slot & 1u) * 16);
-                        const unsigned wsel = slot >> 1;
-                        quad.x |= wsel == 0 ? val : 0u; quad.y |= wsel == 1 ? val : 0u;
-                        quad.z |= wsel == 2 ? val : 0u; quad.w |= wsel == 3 ? val : 0u;
-                        if (slot == 7u) { orow[(size_t)(cnt >> 3) * 32] = quad; quad = make_uint4(0u, 0u, 0u, 0u); }
-                        ++cnt;
-                    }
-                }
-            }
-            if (cnt & 7u) {
-                for (unsigned slot = cnt & 7u; slot < 8u; ++slot) {
-                    const uint32_t val = li << ((slot & 1u) * 16);
-                    const unsigned wsel = slot >> 1;
-                    quad.x |= wsel == 0 ? val : 0u; quad.y |= wsel == 1 ? val : 0u;
-                    quad.z |= wsel == 2 ? val : 0u; quad.w |= wsel == 3 ? val : 0u;
-                }
-                orow[(size_t)(cnt >> 3) * 32] = quad;
-            }
-            a.in_count[i] = cnt;
         } else {
             // home cell of this atom along x, then the 3x3 x-rows around it: 3 consecutive tile cells each
             unsigned h = 0;
@@ -382,19 +344,8 @@ tile_kernel(LJConst c, TileGrid g, TileArgs a, int guarded) {
                         for (int u = 0; u < 4; ++u) {
                             const unsigned j = jb + u;
                             if (j < j1 && d2[u] <= c.list_cut2 && j != li) {
-                                if (MODE == TILE_LIST_FILL) {
-                                    // entries are collected in registers and leave as whole 16-byte quads
-                                    const unsigned slot = cnt & 7u;
-                                    const uint32_t val = j << ((slot & 1u) * 16);
-                                    const unsigned wsel = slot >> 1;
-                                    quad.x |= wsel == 0 ? val : 0u; quad.y |= wsel == 1 ? val : 0u;
-                                    quad.z |= wsel == 2 ? val : 0u; quad.w |= wsel == 3 ? val : 0u;
-                                    if (slot == 7u) {
-                                        if ((cnt >> 3) < a.capq)
-                                            reinterpret_cast<uint4*>(a.nl32)[((size_t)(i >> 5) * a.capq + (cnt >> 3)) * 32 + (i & 31u)] = quad;
-                                        quad = make_uint4(0u, 0u, 0u, 0u);
-                                    }
-                                }
+                                if (MODE == TILE_LIST_FILL && cnt < 8 * a.capq)     // plain 16-bit stores: measured cheaper than packing quads in registers
+                                    fill16[(size_t)(cnt >> 3) * 256 + (cnt & 7u)] = (unsigned short)j;
                                 ++cnt;
                             }
                         }
@@ -412,18 +363,9 @@ tile_kernel(LJConst c, TileGrid g, TileArgs a, int guarded) {
         if (MODE == TILE_FORCE_LIST || MODE == TILE_FORCE_CELL || MODE == TILE_FORCE_PRUNE) {
             a.fx[i] = ax * c.prefctr; a.fy[i] = ay * c.prefctr; a.fz[i] = az * c.prefctr;
             etot += fma(-(double)nacc, c.ecut, e);
-        } else if (MODE == TILE_PRUNE) {
         } else {
-            if (MODE == TILE_LIST_FILL && (cnt & 7u) && (cnt >> 3) < a.capq) {
-                // flush the last, partial quad; its unused tail points at the atom itself
-                for (unsigned slot = cnt & 7u; slot < 8u; ++slot) {
-                    const uint32_t val = li << ((slot & 1u) * 16);
-                    const unsigned wsel = slot >> 1;
-                    quad.x |= wsel == 0 ? val : 0u; quad.y |= wsel == 1 ? val : 0u;
-                    quad.z |= wsel == 2 ? val : 0u; quad.w |= wsel == 3 ? val : 0u;
-                }
-                reinterpret_cast<uint4*>(a.nl32)[((size_t)(i >> 5) * a.capq + (cnt >> 3)) * 32 + (i & 31u)] = quad;
-            }
+            if (MODE == TILE_LIST_FILL)                      // the unused tail of the last quad points at the atom itself
+                for (unsigned k = min(cnt, 8 * a.capq); k & 7u; ++k) fill16[(size_t)(k >> 3) * 256 + (k & 7u)] = (unsigned short)li;
             a.nl_count[i] = MODE == TILE_LIST_FILL ? min(cnt, 8 * a.capq) : cnt;
             maxcnt = max(maxcnt, cnt);
         }
@@ -445,7 +387,7 @@ tile_kernel(LJConst c, TileGrid g, TileArgs a, int guarded) {
                 a.partial_epot[blockIdx.x] = tot;
             }
         }
-    } else if (MODE != TILE_PRUNE) {
+    } else {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) maxcnt = max(maxcnt, __shfl_xor_sync(0xffffffffu, maxcnt, o));
         if ((threadIdx.x & 31) == 0 && maxcnt) {
