@@ -105,6 +105,7 @@ struct Mailbox {
     unsigned long long halo_flag[2];                 // [0]: written by my lower neighbour, [1]: by my upper; value = step sequence
     unsigned long long red_flag[2][kMaxPeers];       // [parity][source rank] = sequence number of the deposited sums
     double red[2][kMaxPeers][4];                     // [parity][source rank]{epot_sum, ekin_sum, pred_sum, rebuild vote}
+    double nb_vmax2[2];                              // max |v|^2 of this step's drift on my lower [0] / upper [1] neighbour (pushed with the halo)
     unsigned int error;                              // a wait timed out (peer gone): results are invalid
     unsigned int pad;
 };

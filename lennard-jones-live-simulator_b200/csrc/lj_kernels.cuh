@@ -520,6 +520,10 @@ halo_push_kernel(const StepCtrl* __restrict__ ctrl, const double4* __restrict__ 
     if (threadIdx.x == 0) {
         if (atomicAdd(ticket, 1u) == gridDim.x - 1) {          // last block: every store of every block is fenced
             *ticket = 0;
+            // my fastest atom of this step travels with the halo: it bounds how far my boundary atoms moved
+            const double v2 = __longlong_as_double((long long)ctrl->vmax2);
+            down_mail->nb_vmax2[1] = v2;
+            up_mail->nb_vmax2[0] = v2;
             __threadfence_system();
             st_sys_u64(&down_mail->halo_flag[1], seq);          // I am my lower neighbour's upper neighbour
             st_sys_u64(&up_mail->halo_flag[0], seq);
@@ -536,6 +540,7 @@ slab_exchange_kernel(LJConst c, StepCtrl* __restrict__ ctrl, HistEntry* __restri
                      Mailbox* mine, Mailbox* const* __restrict__ peers, int rank, int world, unsigned long long seq) {
     __shared__ double red[32];
     __shared__ double tot[4];
+    __shared__ double nbv2;
     if (what == 0 && ctrl->stop) return;
     double se = strided_sum(partial_epot, nb_epot);
     double sk = partial_ekin ? strided_sum(partial_ekin, nb_kick) : 0.0;
@@ -548,6 +553,9 @@ slab_exchange_kernel(LJConst c, StepCtrl* __restrict__ ctrl, HistEntry* __restri
         tot[0] = se; tot[1] = sk; tot[2] = sp;
         tot[3] = (__longlong_as_double((long long)ctrl->maxdisp2) > c.disp_thresh) ? 1.0 : 0.0;
         ctrl->maxdisp2 = 0ull;
+        // the neighbours' fastest-atom values of this step arrived with the halo the force kernel waited for;
+        // read them before my deposit releases the neighbours into the next step's push
+        nbv2 = fmax(ld_sys_f64(&mine->nb_vmax2[0]), ld_sys_f64(&mine->nb_vmax2[1]));
     }
     __syncthreads();
     // thread r deposits my four sums in peer r's mailbox (its own included), fences, raises the flag
@@ -582,6 +590,12 @@ slab_exchange_kernel(LJConst c, StepCtrl* __restrict__ ctrl, HistEntry* __restri
         ctrl->hist_head += 1;
         ctrl->steps_done += 1;
         if (g[3] > 0.0) ctrl->stop = 1;
+        // pruned inner list: pairs of this device involve its own atoms and the two neighbours' boundary
+        // atoms, so the displacement bound advances by the fastest atom among the three devices
+        const double vmax = sqrt(fmax(__longlong_as_double((long long)ctrl->vmax2), nbv2));
+        ctrl->vmax_last = vmax;
+        ctrl->drift_bound += vmax * c.dt;
+        ctrl->vmax2 = 0ull;
     }
 }
 

@@ -286,7 +286,8 @@ void ljgpu_sim::setup_constants() {
     {   // inner-list skin: LJGPU_PRUNE_SKIN (in sigma units of length; 0 disables), default 0.12, never beyond the shell
         const char* e = std::getenv("LJGPU_PRUNE_SKIN");
         prune_skin = e ? std::atof(e) : 0.12;
-        if (prune_skin >= p.shell || slab.on || mode != LJGPU_KERNEL_VERLET) prune_skin = 0.0;
+        // on slabs only the peer-memory step loop carries the neighbours' speeds (NCCL fallback: no pruning)
+        if (prune_skin >= p.shell || (slab.on && !slab.p2p) || mode != LJGPU_KERNEL_VERLET) prune_skin = 0.0;
         c.prune_cut2 = (p.rcut + prune_skin) * (p.rcut + prune_skin);
         c.prune_half = 0.5 * prune_skin;
         c.dt = 0.0;
@@ -340,7 +341,7 @@ void ljgpu_sim::allocate() {
         CK(cudaMalloc(&keys, A * 4)); CK(cudaMalloc(&vals, A * 4));
         CK(cudaMalloc(&cstart, (size_t)ncell * 4)); CK(cudaMalloc(&cend, (size_t)ncell * 4)); CK(cudaMalloc(&ccount, (size_t)ncell * 4));
         CK(cudaMalloc(&nl_count, A * 4));
-        if (prune_skin > 0.0) CK(cudaMalloc(&nl_in_count, A * 4));
+        if (mode == LJGPU_KERNEL_VERLET) CK(cudaMalloc(&nl_in_count, A * 4));
         const unsigned nhz = slab.on ? slab.nzl : nc;
         // brick = 3x2x2 cells when there are plenty of them; small systems (and thin slabs) get smaller bricks
         // so that the grid still covers the 148 SMs several times over
@@ -741,7 +742,7 @@ void ljgpu_sim::build_list() {
         if (need > nl_alloc) {
             dfree(nl); dfree(nl_in);
             CK(cudaMalloc(&nl, need * 4));
-            if (prune_skin > 0.0) CK(cudaMalloc(&nl_in, need * 4));
+            if (mode == LJGPU_KERNEL_VERLET) CK(cudaMalloc(&nl_in, need * 4));
             nl_alloc = need;
         }
         launch_tile<TILE_LIST_FILL>(this, 0);
@@ -1033,7 +1034,7 @@ static int create_common(const ljgpu_params* p, int rank, int world, const void*
         s->n = 0;
         s->setup_constants();
         s->allocate();
-        if (s->slab.on) s->setup_p2p();
+        if (s->slab.on) { s->setup_p2p(); s->setup_constants(); }      // pruning is decided once the step loop is known
         s->upload_state(x, y, z, vx, vy, vz);
         s->initial_forces();
     });

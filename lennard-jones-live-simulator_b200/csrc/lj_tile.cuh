@@ -189,7 +189,12 @@ tile_kernel(LJConst c, TileGrid g, TileArgs a, int guarded) {
     // Same decision in every block: the inputs were final before this launch.
     bool use_inner = false;
     if (MODE == TILE_FORCE_LIST && a.in32 != nullptr) {   // (TILE_FORCE_PRUNE always walks the outer list)
-        const double bound = a.ctrl->drift_bound + sqrt(__longlong_as_double((long long)a.ctrl->vmax2)) * c.dt;
+        double v2 = __longlong_as_double((long long)a.ctrl->vmax2);
+        if (a.mail) {   // slab: a brick that reaches a halo layer also sees that neighbour's atoms (value pushed with the halo)
+            if (tg.z0 == g.hz0) v2 = fmax(v2, ld_sys_f64(&a.mail->nb_vmax2[0]));
+            if (tg.z0 + tg.bd == g.hz0 + g.nhz) v2 = fmax(v2, ld_sys_f64(&a.mail->nb_vmax2[1]));
+        }
+        const double bound = a.ctrl->drift_bound + sqrt(v2) * c.dt;
         use_inner = a.ctrl->inner_valid != 0u && bound <= c.prune_half;
         if (use_inner && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&a.ctrl->inner_used, 1u);
     }

@@ -93,9 +93,41 @@ def main():
     v = g.get_velocities_copy()
     assert np.abs(v.sum(axis=0)).max() < 1e-8
     dist.barrier()
-    if rank == 0:
-        print(f"SLAB OK world={world} N={n_atoms} rebuilds={t['rebuilds']} info={g.slab_info()}")
+    info = g.slab_info()
     g.close()
+
+    # the pruned inner list (peer-memory step loop) must not change a single bit of the trajectory
+    def variant(skin):
+        if skin is None:
+            os.environ.pop("LJGPU_PRUNE_SKIN", None)
+        else:
+            os.environ["LJGPU_PRUNE_SKIN"] = skin
+        vid = [lj.slab_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(vid, src=0)
+        s = lj.LennardJonesSimulation(params, state, force_kernel=lj.KERNEL_VERLET, device=local,
+                                      slab=(rank, world, vid[0]))
+        s.integrate_n(1, long_steps, DT)
+        out = (s.get_energies(), s.get_positions_soa(), s.get_velocities_soa(), s.get_layout()["n_ghosts"])
+        dist.barrier()
+        s.close()
+        return out
+
+    keep = os.environ.get("LJGPU_PRUNE_SKIN")
+    e1, x1, v1, used1 = variant(keep)
+    e0, x0, v0, used0 = variant("0")
+    if keep is None:
+        os.environ.pop("LJGPU_PRUNE_SKIN", None)
+    else:
+        os.environ["LJGPU_PRUNE_SKIN"] = keep
+    assert used0 == 0
+    assert e1 == e0, (e1, e0)
+    for a, b in zip(x1 + v1, x0 + v0):
+        assert np.array_equal(a, b)
+    if not os.environ.get("LJGPU_SLAB_NCCL") and keep is None:
+        assert used1 > 0, "inner list never used on the peer-memory path"
+    dist.barrier()
+    if rank == 0:
+        print(f"SLAB OK world={world} N={n_atoms} rebuilds={t['rebuilds']} inner_steps={used1} info={info}")
     dist.destroy_process_group()
 
 
