@@ -352,6 +352,13 @@ void ljgpu_sim::allocate() {
             if (bxd > 1 && bxd >= byd && bxd >= bzd) --bxd; else if (byd > 1 && byd >= bzd) --byd; else --bzd;
             count_blocks();
         }
+        if (const char* e = std::getenv("LJGPU_BRICK")) {          // tuning knob: "bx,by,bz" in cells, within the compiled maxima
+            unsigned ex = 0, ey = 0, ez = 0;
+            if (std::sscanf(e, "%u,%u,%u", &ex, &ey, &ez) == 3 && ex >= 1 && ey >= 1 && ez >= 1 &&
+                ex <= (unsigned)kTileBX && ey <= (unsigned)kTileBY && ez <= (unsigned)kTileBZ) {
+                bxd = ex; byd = ey; bzd = ez; count_blocks();
+            }
+        }
         CK(cudaMalloc(&tsrc, (size_t)nblocks_tile * kTileCellsMax * 4));
         CK(cudaMalloc(&toff, (size_t)nblocks_tile * (kTileCellsMax + 1) * 4));
         nb_force = nblocks_tile;                                   // one partial per CTA

@@ -163,16 +163,34 @@ tile_kernel(LJConst c, TileGrid g, TileArgs a, int guarded) {
         for (; q <= kHomeRowsMax; ++q) s_hstart[q] = run;
     }
 
-    // stage the neighbourhood: one warp per tile cell, asynchronous global->shared copies (LDGSTS), so
-    // no thread waits on a load before issuing the next; x,y,z of an atom are 24 contiguous bytes of the
-    // 32-byte global record and go to the 24-byte shared record as three 8-byte copies
+    // stage the neighbourhood: one warp per tile x-row (W consecutive tile cells, ~100 atoms at liquid
+    // density), lanes stride over the row's atoms.  An atom's global slot is its tile index plus the
+    // (source - offset) difference of its cell, picked by comparing against the row's W-1 inner cell
+    // offsets held in registers (a per-cell loop cost ~4x the instructions: 21 of 32 lanes busy and the
+    // loop set-up once per cell).  Asynchronous global->shared copies (LDGSTS), so no thread waits on a
+    // load before issuing the next; x,y,z of an atom are 24 contiguous bytes of the 32-byte global
+    // record and go to the 24-byte shared record as three 8-byte copies.
     {
+        constexpr int kW = kTileBX + 2;
         const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-        for (unsigned t = w; t < ntc; t += nw) {
-            const unsigned o = s_off[t], cnt = s_off[t + 1] - o, src = s_src[t];
-            for (unsigned k = lane; k < cnt; k += 32) {
-                const double* gp = reinterpret_cast<const double*>(a.pos + src + k);
-                const unsigned sp = (unsigned)__cvta_generic_to_shared(sm + 3 * (size_t)(o + k));
+        const unsigned nrows = H * (tg.bd + 2);
+        for (unsigned r = w; r < nrows; r += nw) {
+            const unsigned t0 = r * W;
+            unsigned offk[kW], delk[kW];
+#pragma unroll
+            for (int k = 0; k < kW; ++k) {
+                const bool on = (unsigned)k < W;
+                const unsigned o = on ? s_off[t0 + k] : 0xffffffffu;
+                offk[k] = o;
+                delk[k] = on ? s_src[t0 + k] - o : 0u;      // modulo 2^32: li + delk = source slot
+            }
+            const unsigned o1 = s_off[t0 + W];
+            for (unsigned li = offk[0] + lane; li < o1; li += 32) {
+                unsigned d = delk[0];
+#pragma unroll
+                for (int k = 1; k < kW; ++k) d = (li >= offk[k]) ? delk[k] : d;
+                const double* gp = reinterpret_cast<const double*>(a.pos + (li + d));
+                const unsigned sp = (unsigned)__cvta_generic_to_shared(sm + 3 * (size_t)li);
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(sp), "l"(gp) : "memory");
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(sp + 8), "l"(gp + 1) : "memory");
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(sp + 16), "l"(gp + 2) : "memory");
@@ -290,12 +308,13 @@ tile_kernel(LJConst c, TileGrid g, TileArgs a, int guarded) {
                     for (int u = 0; u < 4; ++u) {
                         // padding entries point at the atom itself (d2 == 0): excluded by index
                         const bool in = (d2[u] < c.rc2) && (jj[u] != li);
-                        const double inv = fast_rcp(d2[u]);
+                        // one select, not a divergent branch: a rejected entry gets 1/d2 := 0, which turns both
+                        // terms below into exact +0 (same bits as selecting them afterwards, half the selects)
+                        const double inv = in ? fast_rcp(d2[u]) : 0.0;
                         const double s2 = UNIT_SIGMA ? inv : c.sigma2 * inv;
                         const double s6 = s2 * s2 * s2;
-                        const double t0 = fma(s6, s6, -s6);         // s12 - s6
-                        const double fr0 = fma(s6, s6, t0) * inv;   // (2 s12 - s6) / d2
-                        const double t = in ? t0 : 0.0, fr = in ? fr0 : 0.0;     // selects, not a divergent branch
+                        const double t = fma(s6, s6, -s6);          // s12 - s6
+                        const double fr = fma(s6, s6, t) * inv;     // (2 s12 - s6) / d2
                         e += t;
                         ax = fma(fr, dx[u], ax); ay = fma(fr, dy[u], ay); az = fma(fr, dz[u], az);
                         nacc += in ? 1u : 0u;
