@@ -83,6 +83,34 @@ struct Slab {
 
 static void set_tile_attributes(size_t smem);
 
+// LJGPU_TRACE_HOST=1: wall-clock spent by the stepping thread per host section (totals, maxima and every
+// event above 2 ms), printed when the simulation is destroyed.  Adds no synchronisation.
+struct HostTrace {
+    enum { ENQUEUE, CAPTURE, GRAPH_LAUNCH, FETCH, REBUILD, NSEC };
+    bool on = std::getenv("LJGPU_TRACE_HOST") != nullptr;
+    double tot[NSEC] = {}, mx[NSEC] = {};
+    uint64_t cnt[NSEC] = {};
+    std::vector<std::pair<int, double>> slow;
+    struct Scope {
+        HostTrace& t; int sec; std::chrono::steady_clock::time_point t0;
+        Scope(HostTrace& tr, int s) : t(tr), sec(s) { if (t.on) t0 = std::chrono::steady_clock::now(); }
+        ~Scope() {
+            if (!t.on) return;
+            const double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+            t.tot[sec] += us; t.mx[sec] = std::max(t.mx[sec], us); ++t.cnt[sec];
+            if (us > 2000.0 && t.slow.size() < 64) t.slow.emplace_back(sec, us);
+        }
+    };
+    void report(int rank) const {
+        if (!on) return;
+        static const char* names[NSEC] = {"enqueue", "capture", "graph_launch", "fetch", "rebuild"};
+        for (int k = 0; k < NSEC; ++k)
+            if (cnt[k]) std::fprintf(stderr, "[ljgpu host r%d] %-12s n=%8llu total %10.1f us  max %9.1f us\n", rank, names[k],
+                                     (unsigned long long)cnt[k], tot[k], mx[k]);
+        for (auto& e : slow) std::fprintf(stderr, "[ljgpu host r%d]   slow %-12s %9.1f us\n", rank, names[e.first], e.second);
+    }
+};
+
 struct ljgpu_sim {
     std::mutex mu;
     ljgpu_params p{};
@@ -116,7 +144,7 @@ struct ljgpu_sim {
     // shared-memory tiles (lj_tile.cuh) and the Verlet list of 16-bit tile indices
     uint32_t *tsrc = nullptr, *toff = nullptr;
     unsigned bxd = kTileBX, byd = kTileBY, bzd = kTileBZ;      // brick size in cells
-    unsigned nbx = 0, nby = 0, nbz = 0, nblocks_tile = 0, tcap = 0, tile_threads = 128;
+    unsigned nbx = 0, nby = 0, nbz = 0, nblocks_tile = 0, tcap = 0, tile_threads = 128, tile_threads_min = 32;
     uint32_t* nl = nullptr; uint32_t* nl_count = nullptr; unsigned capq = 0; size_t nl_alloc = 0;
     // pruned inner list (single-device Verlet path)
     uint32_t* nl_in = nullptr; uint32_t* nl_in_count = nullptr;
@@ -134,9 +162,17 @@ struct ljgpu_sim {
     double* out3 = nullptr; uint32_t* out_u32 = nullptr; unsigned long long* hist_counts = nullptr;
 
     // CUDA graphs of one step (plain / pruning), re-captured after every re-binning or dt change
-    struct StepGraph { cudaGraphExec_t exec = nullptr; uint64_t kernels = 0; uint64_t cnt[ST_COUNT] = {0}; };
-    StepGraph graphs[2];
-    uint64_t graph_epoch = ~0ull; double graph_dt = 0.0;
+    // Captured steps, keyed by everything a launch bakes in (buffer pointers alternate between two sets from
+    // one re-binning to the next, launch shapes only grow): after a few re-binnings every step replays a cached
+    // graph and nothing is instantiated any more (an instantiation now and then took tens of milliseconds).
+    struct GraphKey {
+        const void* ptr[16]; unsigned shape[6]; double dt; uint64_t gen; int prune;
+        bool operator==(const GraphKey& o) const { return std::memcmp(this, &o, sizeof(GraphKey)) == 0; }
+    };
+    struct StepGraph { cudaGraphExec_t exec = nullptr; uint64_t kernels = 0; uint64_t cnt[ST_COUNT] = {0}; GraphKey key; uint64_t used = 0; };
+    std::vector<StepGraph> graphs;
+    uint64_t graph_gen = 0, graph_clock = 0;          // gen: bumped when constants change (all cached graphs are stale)
+    GraphKey graph_key(bool prune_now, double dt) const;
     unsigned* h_scalar = nullptr;     // pinned scratch for 4-byte uploads
 
     // stepping bookkeeping
@@ -156,6 +192,7 @@ struct ljgpu_sim {
     uint64_t cnt[ST_COUNT] = {0};
     uint64_t steps = 0, rebuilds = 0, launches = 0;
 
+    HostTrace htrace;
     ~ljgpu_sim();
 
     // ---- helpers ------------------------------------------------------------------------------
@@ -242,6 +279,7 @@ struct ljgpu_sim {
 };
 
 ljgpu_sim::~ljgpu_sim() {
+    htrace.report(slab.on ? slab.rank : 0);
     cudaSetDevice(device);
     if (st) cudaStreamSynchronize(st);
     // after a failure the peers may be inside a collective this rank will never join: abort, do not wait
@@ -671,14 +709,16 @@ void ljgpu_sim::rebuild() {
     tile_table_kernel<<<cdiv(nblocks_tile, 4), 128, 0, st>>>(tile_grid(), cstart, ccount, tsrc, toff, ctrl);
     check_launch("tile_table");
     fetch_ctrl();
-    tcap = ((h_ctrl->max_tile + 15) / 16) * 16;
-    tile_threads = std::min((unsigned)LJ_TILE_MAXTHREADS, std::max(32u, ((h_ctrl->max_home + 31) / 32) * 32));
+    // launch shapes only grow (a few spare shared-memory records cost nothing; a changed shape costs a graph capture)
+    tcap = std::max(tcap, ((h_ctrl->max_tile + 63) / 64) * 64);
+    tile_threads = std::max(tile_threads_min,
+                            std::min((unsigned)LJ_TILE_MAXTHREADS, std::max(32u, ((h_ctrl->max_home + 31) / 32) * 32)));
+    tile_threads_min = tile_threads;
     nb_force = nblocks_tile;
-    if ((size_t)tcap * 24 > 200 * 1024)
+    if ((size_t)tcap * kTileRecBytes > 200 * 1024)
         throw LjError(LJGPU_ESTATE, "a cell neighbourhood does not fit in shared memory (density too inhomogeneous)");
     if (h_ctrl->max_tile > 65535) throw LjError(LJGPU_ESTATE, "tile too large for 16-bit list indices");
-    set_tile_attributes((size_t)tcap * 24);
-    drop_graphs();                                   // buffers were swapped, launch shapes may have changed
+    set_tile_attributes((size_t)tcap * kTileRecBytes);
 
     lap("tile_table");
     if (mode == LJGPU_KERNEL_VERLET) build_list();
@@ -692,7 +732,7 @@ void ljgpu_sim::rebuild() {
 
 template <int MODE, bool UNIT_SIGMA>
 static void launch_tile2(ljgpu_sim* s, int guarded) {
-    const size_t smem = (size_t)s->tcap * 24;
+    const size_t smem = (size_t)s->tcap * kTileRecBytes;
     TileArgs a{s->pos, s->nl, s->nl_count, s->prune_skin > 0.0 ? s->nl_in : nullptr, s->nl_in_count,
                s->f[0], s->f[1], s->f[2], s->partial_epot, s->ctrl, s->capq,
                s->slab.p2p ? s->slab.mail : nullptr, s->slab.halo_seq};
@@ -746,11 +786,13 @@ void ljgpu_sim::build_list() {
             note("capacity agreed");
         }
         const size_t need = (size_t)ntiles * capq * 32 * 4;
-        if (need > nl_alloc) {
+        if (need > nl_alloc) {      // two spare quads per atom: the longest list creeps up by an entry now and then,
+            const size_t want = (size_t)ntiles * (capq + 2) * 32 * 4;   // and freeing + allocating 2 x 250 MB took up to 170 ms
             dfree(nl); dfree(nl_in);
-            CK(cudaMalloc(&nl, need * 4));
-            if (mode == LJGPU_KERNEL_VERLET) CK(cudaMalloc(&nl_in, need * 4));
-            nl_alloc = need;
+            CK(cudaMalloc(&nl, want * 4));
+            if (mode == LJGPU_KERNEL_VERLET) CK(cudaMalloc(&nl_in, want * 4));
+            nl_alloc = want;
+            ++graph_gen;            // (cached graphs hold the old pointers; the key would catch it too)
         }
         launch_tile<TILE_LIST_FILL>(this, 0);
         fetch_ctrl();
@@ -855,9 +897,21 @@ void ljgpu_sim::enqueue_step(bool prune_now, double dt) {
     stage_end(ST_KICK2, ev);
 }
 
+ljgpu_sim::GraphKey ljgpu_sim::graph_key(bool prune_now, double dt) const {
+    GraphKey k;
+    std::memset(&k, 0, sizeof k);                      // padding included: keys are compared bytewise
+    const void* ptrs[16] = {pos, v[0], v[1], v[2], f[0], f[1], f[2], dij[0], dij[1], dij[2],
+                            nl, nl_in, nl_count, nl_in_count, tsrc, toff};
+    std::memcpy(k.ptr, ptrs, sizeof ptrs);
+    k.shape[0] = n; k.shape[1] = tile_threads; k.shape[2] = tcap; k.shape[3] = capq; k.shape[4] = nblocks_tile; k.shape[5] = nb_force;
+    k.dt = dt; k.gen = graph_gen; k.prune = prune_now ? 1 : 0;
+    return k;
+}
+
 void ljgpu_sim::drop_graphs() {
-    for (auto& g : graphs) { if (g.exec) cudaGraphExecDestroy(g.exec); g = StepGraph(); }
-    graph_epoch = ~0ull;
+    for (auto& g : graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+    graphs.clear();
+    ++graph_gen;
 }
 
 // One integrate() call: decides on the host whether this step also prunes, then replays the matching
@@ -873,14 +927,30 @@ void ljgpu_sim::launch_step(double dt) {
     bool timed_step = false;
     if (prof) { timed_step = slab.on || (prof_tick++ % prof_every) == 0; }
     if (timed_step || slab.on || no_graph) {
+        HostTrace::Scope hs(htrace, HostTrace::ENQUEUE);
         prof_this_step = true;
         enqueue_step(prune_now, dt);
         return;
     }
     prof_this_step = false;          // graph replay (and its capture) carries no event records
-    if (graph_epoch != rebuilds || graph_dt != dt) { drop_graphs(); graph_epoch = rebuilds; graph_dt = dt; }
-    StepGraph& g = graphs[prune_now ? 1 : 0];
+    const GraphKey key = graph_key(prune_now, dt);
+    StepGraph* hit = nullptr;
+    for (auto& e : graphs) if (e.key == key) { hit = &e; break; }
+    if (!hit) {
+        if (graphs.size() >= 12) {                    // evict the least recently used
+            size_t lru = 0;
+            for (size_t k = 1; k < graphs.size(); ++k) if (graphs[k].used < graphs[lru].used) lru = k;
+            cudaGraphExecDestroy(graphs[lru].exec);
+            graphs.erase(graphs.begin() + (long)lru);
+        }
+        graphs.emplace_back();
+        hit = &graphs.back();
+        hit->key = key;
+    }
+    StepGraph& g = *hit;
+    g.used = ++graph_clock;
     if (!g.exec) {
+        HostTrace::Scope hs(htrace, HostTrace::CAPTURE);
         uint64_t cnt0[ST_COUNT]; std::memcpy(cnt0, cnt, sizeof cnt0);
         const uint64_t l0 = launches;
         CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
@@ -894,7 +964,10 @@ void ljgpu_sim::launch_step(double dt) {
         for (int k = 0; k < ST_COUNT; ++k) { g.cnt[k] = cnt[k] - cnt0[k]; cnt[k] = cnt0[k]; }
         launches = l0;
     }
-    CK(cudaGraphLaunch(g.exec, st));
+    {
+        HostTrace::Scope hs(htrace, HostTrace::GRAPH_LAUNCH);
+        CK(cudaGraphLaunch(g.exec, st));
+    }
     launches += g.kernels;
     for (int k = 0; k < ST_COUNT; ++k) cnt[k] += g.cnt[k];
     prof_this_step = true;
@@ -917,13 +990,16 @@ void ljgpu_sim::run_steps(unsigned first, unsigned nsteps, double dt) {
         h_scalar[0] = step;                              // integrate(step, dt): the device counts on from here
         CK(cudaMemcpyAsync(&ctrl->next_step, h_scalar, sizeof(unsigned), cudaMemcpyHostToDevice, st));
         for (unsigned k = 0; k < batch; ++k) launch_step(dt);
-        fetch_ctrl();
+        {
+            HostTrace::Scope hs(htrace, HostTrace::FETCH);
+            fetch_ctrl();
+        }
         const unsigned done = h_ctrl->steps_done;
         if (prune_skin > 0.0 && h_ctrl->vmax_last > 0.0)     // steps until the fastest atom has covered s_in/2, with margin
             prune_interval = std::max(1u, (unsigned)(0.85 * c.prune_half / (h_ctrl->vmax_last * dt)));
         step += done; remaining -= done; steps += done; since_rebuild += done;
         if (done) dirty_since_rebuild = true;
-        if (h_ctrl->stop) rebuild();
+        if (h_ctrl->stop) { HostTrace::Scope hs(htrace, HostTrace::REBUILD); rebuild(); }
         else if (done != batch) throw LjError(LJGPU_ESTATE, "step batch ended early without a rebuild request");
     }
 }

@@ -30,6 +30,32 @@ constexpr int kTileRowsMax = (kTileBY + 2) * (kTileBZ + 2);           // x-rows 
 constexpr int kTileCellsMax = (kTileBX + 2) * kTileRowsMax;           // tile cells per CTA
 constexpr int kHomeRowsMax = kTileBY * kTileBZ;
 
+// Shared-memory record of a tile atom.  The list walk is a random gather, and the shared-memory data pipe is
+// its busiest unit (ncu: 72 % of cycles, 6.5 wavefronts per 64-bit load where 2 would be conflict-free - 16
+// random lanes over 16 bank pairs).  LJ_TILE_REC32: 32-byte records, (x,y) fetched with one 128-bit load
+// (quarter-warps over 8 bank quads) and z with a 64-bit load; the two 16-byte halves of a record swap places
+// with bit 4 of the atom index so that the (x,y) halves spread over all eight quads.  Otherwise 24-byte
+// records and three 64-bit loads.  Measured at N = 2^20: 237 us per force pass with 32-byte records against
+// 227 us with 24-byte ones (fewer loads, but not fewer wavefronts, and two more integer instructions per
+// entry) - so 24 bytes stay the default.
+#ifndef LJ_TILE_REC32
+#define LJ_TILE_REC32 0
+#endif
+constexpr unsigned kTileRecBytes = LJ_TILE_REC32 ? 32u : 24u;
+
+__device__ __forceinline__ void tile_ld(const double* sm, unsigned j, double& x, double& y, double& z) {
+#if LJ_TILE_REC32
+    const char* b = reinterpret_cast<const char*>(sm);
+    const unsigned a = j * 32u, s = j & 16u;
+    const double2 xy = *reinterpret_cast<const double2*>(b + (a + s));
+    z = *reinterpret_cast<const double*>(b + (a + 16u - s));
+    x = xy.x; y = xy.y;
+#else
+    const double* p = sm + 3 * (size_t)j;
+    x = p[0]; y = p[1]; z = p[2];
+#endif
+}
+
 struct TileGrid {
     unsigned nc;                 // cells per axis in x and y (periodic)
     unsigned ncz;                // cell layers of the local table (nc, or owned layers + 2 halo layers on a slab)
@@ -129,7 +155,7 @@ struct TileArgs {
 template <int MODE, bool UNIT_SIGMA>
 __global__ void __launch_bounds__(LJ_TILE_MAXTHREADS, LJ_TILE_MINBLOCKS)
 tile_kernel(LJConst c, TileGrid g, TileArgs a, int guarded) {
-    extern __shared__ double sm[];                      // tile positions, 3 doubles per atom (stride 24 B)
+    extern __shared__ __align__(16) double sm[];        // tile positions, one record per atom (tile_ld)
     __shared__ uint32_t s_off[kTileCellsMax + 1];
     __shared__ uint32_t s_src[kTileCellsMax];
     __shared__ uint32_t s_hstart[kHomeRowsMax + 1];     // prefix of home atoms per home x-row
@@ -174,6 +200,7 @@ tile_kernel(LJConst c, TileGrid g, TileArgs a, int guarded) {
         constexpr int kW = kTileBX + 2;
         const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
         const unsigned nrows = H * (tg.bd + 2);
+        const unsigned smem_base = (unsigned)__cvta_generic_to_shared(sm);
         for (unsigned r = w; r < nrows; r += nw) {
             const unsigned t0 = r * W;
             unsigned offk[kW], delk[kW];
@@ -190,10 +217,16 @@ tile_kernel(LJConst c, TileGrid g, TileArgs a, int guarded) {
 #pragma unroll
                 for (int k = 1; k < kW; ++k) d = (li >= offk[k]) ? delk[k] : d;
                 const double* gp = reinterpret_cast<const double*>(a.pos + (li + d));
-                const unsigned sp = (unsigned)__cvta_generic_to_shared(sm + 3 * (size_t)li);
+#if LJ_TILE_REC32
+                const unsigned sp = smem_base + li * 32u, sw = li & 16u;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(sp + sw), "l"(gp) : "memory");
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(sp + 16u - sw), "l"(gp + 2) : "memory");
+#else
+                const unsigned sp = smem_base + li * 24u;
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(sp), "l"(gp) : "memory");
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(sp + 8), "l"(gp + 1) : "memory");
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(sp + 16), "l"(gp + 2) : "memory");
+#endif
             }
         }
         asm volatile("cp.async.wait_all;" ::: "memory");
@@ -228,8 +261,8 @@ tile_kernel(LJConst c, TileGrid g, TileArgs a, int guarded) {
         const unsigned rbase = (hz * H + hy) * W;                 // tile cell index of (tx=0, hy, hz)
         const unsigned li = s_off[rbase + 1] + (t - s_hstart[q]);
         const unsigned i = s_src[rbase + 1] + (t - s_hstart[q]);
-        const double* pi = sm + 3 * (size_t)li;
-        const double pix = pi[0], piy = pi[1], piz = pi[2];
+        double pix, piy, piz;
+        tile_ld(sm, li, pix, piy, piz);
         double ax = 0.0, ay = 0.0, az = 0.0, e = 0.0;
         unsigned nacc = 0, cnt = 0;
         // entry k of slot i is half-word k&7 of quad k>>3; quads of one slot are 32 lanes x 8 half-words apart
@@ -240,8 +273,9 @@ tile_kernel(LJConst c, TileGrid g, TileArgs a, int guarded) {
 
 #define LJ_TILE_PAIR(J)                                                                     \
         {                                                                                   \
-            const double* pj = sm + 3 * (size_t)(J);                                        \
-            double dx = pix - pj[0], dy = piy - pj[1], dz = piz - pj[2];                    \
+            double dx, dy, dz;                                                              \
+            tile_ld(sm, (J), dx, dy, dz);                                                   \
+            dx = pix - dx; dy = piy - dy; dz = piz - dz;                                    \
             double d2 = fma(dz, dz, fma(dy, dy, dx * dx));                                  \
             if (maybe_wrapped(d2, far2_hi)) {                                               \
                 dx = min_image(dx, c.L, c.halfL); dy = min_image(dy, c.L, c.halfL);         \
@@ -289,8 +323,8 @@ tile_kernel(LJConst c, TileGrid g, TileArgs a, int guarded) {
                         const double fake = __hiloint2double(0x3ff00000 + (int)(jj[u] << 8), 0);
                         dx[u] = fake; dy[u] = fake * 0.5; dz[u] = fake * 0.25;
 #else
-                        const double* pj = sm + 3 * (size_t)jj[u];
-                        dx[u] = pix - pj[0]; dy[u] = piy - pj[1]; dz[u] = piz - pj[2];
+                        tile_ld(sm, jj[u], dx[u], dy[u], dz[u]);
+                        dx[u] = pix - dx[u]; dy[u] = piy - dy[u]; dz[u] = piz - dz[u];
 #endif
                         d2[u] = fma(dz[u], dz[u], fma(dy[u], dy[u], dx[u] * dx[u]));
                         far = max(far, __double2hiint(d2[u]));
@@ -348,8 +382,9 @@ tile_kernel(LJConst c, TileGrid g, TileArgs a, int guarded) {
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
                             const unsigned j = min(jb + u, j1 - 1);
-                            const double* pj = sm + 3 * (size_t)j;
-                            const double dx = pix - pj[0], dy = piy - pj[1], dz = piz - pj[2];
+                            double dx, dy, dz;
+                            tile_ld(sm, j, dx, dy, dz);
+                            dx = pix - dx; dy = piy - dy; dz = piz - dz;
                             d2[u] = fma(dz, dz, fma(dy, dy, dx * dx));
                             far = max(far, __double2hiint(d2[u]));
                         }
@@ -358,9 +393,10 @@ tile_kernel(LJConst c, TileGrid g, TileArgs a, int guarded) {
                             for (int u = 0; u < 4; ++u)
                                 if (maybe_wrapped(d2[u], far2_hi)) {
                                     const unsigned j = min(jb + u, j1 - 1);
-                                    const double* pj = sm + 3 * (size_t)j;
-                                    const double dx = min_image(pix - pj[0], c.L, c.halfL), dy = min_image(piy - pj[1], c.L, c.halfL);
-                                    const double dz = min_image(piz - pj[2], c.L, c.halfL);
+                                    double dx, dy, dz;
+                                    tile_ld(sm, j, dx, dy, dz);
+                                    dx = min_image(pix - dx, c.L, c.halfL); dy = min_image(piy - dy, c.L, c.halfL);
+                                    dz = min_image(piz - dz, c.L, c.halfL);
                                     d2[u] = fma(dz, dz, fma(dy, dy, dx * dx));
                                 }
                         }
