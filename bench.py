@@ -14,9 +14,9 @@ One JSON line is printed by rank 0:
             stream), max over ranks; re-binning, per-step energy reductions and the per-1000-step speed
             histogram (threadintegrate.cpp:57-62 cadence) are inside the timed region
   e2e       the same metric through the drop-in call pattern of the reference: one integrate() per
-            call (host sync each step) followed by a device->host read of the published positions and
-            energies into pinned host buffers, what get_render_x/y/z + get_ekin/epot expose after
-            every step of the reference
+            call (host sync each step) that also publishes the step's positions into pinned host buffers
+            (ljgpu_step_publish: what get_render_x/y/z expose after every step of the reference; the
+            transfer of step k overlaps the computation of step k+1) and an energy read-back per step
   roofline  the dominant kernel (Verlet-list force kernel) against the measured HBM peak, plus its
             FP64 view; cpu_baseline: the reference's own integrator timed on this box's host cores.
 """
@@ -265,19 +265,26 @@ def main():
     dbg(f"value {value:.4e}")
 
     # ---- timed region 2: end to end through the drop-in call pattern --------------------------------
-    pinned = [torch.empty(n, dtype=torch.float64, pin_memory=True) for _ in range(3)]
-    ptrs = [p.data_ptr() for p in pinned]
-    for _ in range(3):
-        sim.integrate(step, DT); step += 1
-        sim.get_positions_into(*ptrs); sim.get_energies()
+    # integrate() + publish_state() every step, as the reference does (lennardjonessimulation.cpp:70-98): host call per
+    # step (12 bytes of arguments in), energies read back, and this step's positions delivered into one of two pinned
+    # host buffer sets (the reference's double buffer); the delivery of step k overlaps the computation of step k+1 and
+    # the last one is waited for inside the timed region.
+    pinned = [[torch.empty(n, dtype=torch.float64, pin_memory=True) for _ in range(3)] for _ in range(2)]
+    ptrs = [[p.data_ptr() for p in set_] for set_ in pinned]
+    for _ in range(4):
+        sim.integrate_publish(step, DT, *ptrs[step & 1]); step += 1
+        sim.get_energies()
+    sim.publish_wait()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.e2e_steps):
-        sim.integrate(step, DT); step += 1
-        sim.get_positions_into(*ptrs)
+        sim.integrate_publish(step, DT, *ptrs[step & 1]); step += 1
         ek, ep, et = sim.get_energies()
+    sim.publish_wait()
     barrier()
     e2e_s = time.perf_counter() - t0
+    last = pinned[(step - 1) & 1]
+    assert all(bool(torch.isfinite(p).all()) for p in last), "published positions are not finite"
     if world > 1:
         t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -333,7 +340,7 @@ def main():
                    f"{world} z-slabs, NCCL halo exchange + 4-double all-reduce per step, migration at re-binning"},
         "e2e": {"value": e2e_value, "unit": "atom-steps/s", "h2d_bytes_per_step": 12, "d2h_bytes_per_step": 24 * n + 24,
                 "steps": args.e2e_steps, "ms_per_step": e2e_s / args.e2e_steps * 1e3,
-                "pattern": "integrate(step, dt) + positions (3 x f64 x N, pinned) + energies read back after every step"},
+                "pattern": "ljgpu_step_publish(step, dt) every step: integrate + positions (3 x f64 x N) delivered into alternating pinned host buffers, transfer of step k overlapping step k+1, last delivery waited for; energies read back after every step"},
         "gpu_launches": int(timers["kernel_launches"]),
         "clocks": clocks,
         "roofline": {"kernel": "tile_kernel<TILE_FORCE_LIST> (Verlet-list force)" if layout["force_kernel"] == 3 else "force kernel",

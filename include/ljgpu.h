@@ -134,6 +134,19 @@ int ljgpu_step_n(ljgpu_sim* s, uint32_t first, uint32_t n, double dt);
  * with CUDA events recorded on the integrator's own stream around the whole batch. */
 int ljgpu_step_n_timed(ljgpu_sim* s, uint32_t first, uint32_t n, double dt, double* device_ms);
 
+/* integrate(step, dt) followed by publish_state() (lennardjonessimulation.cpp:70-98 and :574-576: every
+ * reference step ends by making the new positions the renderer's buffer).  The step is complete and its
+ * energies are final when the call returns; the positions of this step (original atom order, wrapped like
+ * ljgpu_get_positions) are on their way into x, y, z - the device->host transfer runs on a second stream while
+ * the caller's next step computes.  When the call returns, the delivery started by the PREVIOUS
+ * ljgpu_step_publish is complete; the one started by this call is complete after the next ljgpu_step_publish
+ * or ljgpu_publish_wait.  Alternate between two sets of buffers (pinned: ljgpu_alloc_host), exactly like the
+ * reference's double buffer.  On slabs the call is collective and delivers before returning. */
+int ljgpu_step_publish(ljgpu_sim* s, uint32_t step, double dt, double* x, double* y, double* z);
+
+/* Blocks until the delivery started by the last ljgpu_step_publish is complete (no-op if none is pending). */
+int ljgpu_publish_wait(ljgpu_sim* s);
+
 /* ---- queries (original atom order) --------------------------------------------------------- */
 
 /* get_positions_copy / get_render_x,y,z (lennardjonessimulation.h:131-143, .cpp:159-171):

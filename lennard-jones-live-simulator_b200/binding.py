@@ -21,11 +21,37 @@ EXPORTED_SYMBOLS = [
     "ljgpu_write_movie_frame", "ljgpu_set_profiling", "ljgpu_get_timers", "ljgpu_reset_timers",
     "ljgpu_get_layout", "ljgpu_step_n_timed", "ljgpu_get_list_stats", "ljgpu_alloc_host", "ljgpu_free_host",
     "ljgpu_slab_layers", "ljgpu_slab_unique_id", "ljgpu_create_slab", "ljgpu_slab_info",
+    "ljgpu_step_publish", "ljgpu_publish_wait",
 ]
 
 
 class LJGpuError(RuntimeError):
     pass
+
+
+class HostBuffer:
+    """Page-locked host memory from ljgpu_alloc_host viewed as a float64 numpy array (freed on close / gc)."""
+
+    def __init__(self, count):
+        self._lib = load_library()
+        p = C.c_void_p()
+        rc = self._lib.ljgpu_alloc_host(C.c_size_t(count * 8), C.byref(p))
+        if rc != 0:
+            raise LJGpuError(self._lib.ljgpu_last_error().decode())
+        self.ptr = p.value
+        self.array = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_double)), shape=(count,))
+
+    def close(self):
+        if self.ptr:
+            self.array = None
+            self._lib.ljgpu_free_host(C.c_void_p(self.ptr))
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class LJParams(C.Structure):
@@ -92,6 +118,8 @@ def load_library():
                                      C.POINTER(C.c_uint64)]
     lib.ljgpu_step_n_timed.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_double, dp]
     lib.ljgpu_get_list_stats.argtypes = [vp, dp, C.POINTER(C.c_uint32)]
+    lib.ljgpu_step_publish.argtypes = [vp, C.c_uint32, C.c_double, vp, vp, vp]
+    lib.ljgpu_publish_wait.argtypes = [vp]
     lib.ljgpu_alloc_host.argtypes = [C.c_size_t, C.POINTER(vp)]
     lib.ljgpu_free_host.argtypes = [vp]
     lib.ljgpu_slab_layers.argtypes = [C.c_uint32, C.c_int, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
@@ -231,6 +259,14 @@ class LennardJonesSimulation:
 
     def integrate_n(self, first, n, dt):
         _check(self._lib, self._lib.ljgpu_step_n(self._h, first, n, dt))
+
+    def integrate_publish(self, step, dt, px, py, pz):
+        """integrate() + publish_state(): the step is complete on return, its positions are in flight into the
+        caller's (pinned) buffers given as raw addresses; the previous call's delivery is complete."""
+        _check(self._lib, self._lib.ljgpu_step_publish(self._h, step, dt, px, py, pz))
+
+    def publish_wait(self):
+        _check(self._lib, self._lib.ljgpu_publish_wait(self._h))
 
     def integrate_n_timed(self, first, n, dt):
         """integrate_n + device milliseconds (CUDA events on the integrator's stream)."""

@@ -160,6 +160,13 @@ struct ljgpu_sim {
 
     // staging for queries
     double* out3 = nullptr; uint32_t* out_u32 = nullptr; unsigned long long* hist_counts = nullptr;
+    // asynchronous publication of positions (ljgpu_step_publish): staging buffers, copy stream, events
+    double* pub3[2] = {nullptr, nullptr};
+    cudaStream_t st_copy = nullptr;
+    cudaEvent_t ev_pub_ready[2] = {nullptr, nullptr}, ev_pub_done[2] = {nullptr, nullptr};
+    int pub_cur = 0; bool pub_pending = false; uint32_t pub_step = 0;
+    void step_publish(unsigned step, double dt, double* x, double* y, double* z);
+    void publish_wait();
 
     // CUDA graphs of one step (plain / pruning), re-captured after every re-binning or dt change
     // Captured steps, keyed by everything a launch bakes in (buffer pointers alternate between two sets from
@@ -291,6 +298,12 @@ ljgpu_sim::~ljgpu_sim() {
     dfree(nl); dfree(nl_count); dfree(nl_in); dfree(nl_in_count); dfree(tsrc); dfree(toff);
     dfree(partial_epot); dfree(partial_ekin); dfree(partial_pred);
     dfree(ctrl); dfree(hist); dfree(out3); dfree(out_u32); dfree(hist_counts);
+    if (st_copy) { cudaStreamSynchronize(st_copy); cudaStreamDestroy(st_copy); }
+    for (int b = 0; b < 2; ++b) {
+        dfree(pub3[b]);
+        if (ev_pub_ready[b]) cudaEventDestroy(ev_pub_ready[b]);
+        if (ev_pub_done[b]) cudaEventDestroy(ev_pub_done[b]);
+    }
     for (int k = 0; k < 2; ++k) { dfree(slab.sendbuf[k]); dfree(slab.recvbuf[k]); dfree(slab.hcount[k]); dfree(slab.hoff[k]); }
     dfree(slab.xchg);
     for (int k = 0; k < slab.n_ipc_opened; ++k) cudaIpcCloseMemHandle(slab.ipc_opened[k]);
@@ -1024,6 +1037,42 @@ void ljgpu_sim::export3(int what, double* a, double* b, double* cc) {
     sync();
 }
 
+// integrate() + publish_state() (.cpp:70-98, :574-576) without stalling the integrator on the transfer: the step
+// runs (and is waited for: the energies are final on return), its positions are gathered into original order on
+// the integrator's stream, and the device->host copies go out on a second stream while the caller's next step
+// computes.  On return the PREVIOUS delivery is complete; the current one is in flight.
+void ljgpu_sim::step_publish(unsigned step, double dt, double* x, double* y, double* z) {
+    run_steps(step, 1, dt);
+    if (slab.on) { export3(0, x, y, z); return; }          // slabs: every rank assembles the whole system (collective), synchronous
+    const size_t N = nglobal;
+    if (!st_copy) {
+        CK(cudaStreamCreateWithFlags(&st_copy, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; ++b) {
+            CK(cudaMalloc(&pub3[b], 3 * N * 8));
+            CK(cudaEventCreateWithFlags(&ev_pub_ready[b], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&ev_pub_done[b], cudaEventDisableTiming));
+        }
+    }
+    const int b = pub_cur ^ 1;                               // its last delivery (two calls ago) was waited for one call ago
+    double* o = pub3[b];
+    export_positions_kernel<<<nb_atoms(), kBlock, 0, st>>>(c, pos, orig, o, o + N, o + 2 * N);
+    check_launch("export");
+    CK(cudaEventRecord(ev_pub_ready[b], st));
+    CK(cudaStreamWaitEvent(st_copy, ev_pub_ready[b], 0));
+    CK(cudaMemcpyAsync(x, o, N * 8, cudaMemcpyDeviceToHost, st_copy));
+    CK(cudaMemcpyAsync(y, o + N, N * 8, cudaMemcpyDeviceToHost, st_copy));
+    CK(cudaMemcpyAsync(z, o + 2 * N, N * 8, cudaMemcpyDeviceToHost, st_copy));
+    CK(cudaEventRecord(ev_pub_done[b], st_copy));
+    if (pub_pending) CK(cudaEventSynchronize(ev_pub_done[pub_cur]));
+    pub_cur = b; pub_pending = true; pub_step = step;
+}
+
+void ljgpu_sim::publish_wait() {
+    if (!pub_pending) return;
+    CK(cudaEventSynchronize(ev_pub_done[pub_cur]));
+    pub_pending = false;
+}
+
 // =================================================================================================
 // C ABI
 // =================================================================================================
@@ -1205,6 +1254,15 @@ int ljgpu_update_params(ljgpu_sim* s, const ljgpu_params* p) {
 
 int ljgpu_step(ljgpu_sim* s, uint32_t step, double dt) {
     return with_sim(s, [&] { s->run_steps(step, 1, dt); });
+}
+
+int ljgpu_step_publish(ljgpu_sim* s, uint32_t step, double dt, double* x, double* y, double* z) {
+    if (!x || !y || !z) return fail(LJGPU_EINVAL, "null argument");
+    return with_sim(s, [&] { s->step_publish(step, dt, x, y, z); });
+}
+
+int ljgpu_publish_wait(ljgpu_sim* s) {
+    return with_sim(s, [&] { s->publish_wait(); });
 }
 
 int ljgpu_step_n(ljgpu_sim* s, uint32_t first, uint32_t n, double dt) {

@@ -45,7 +45,7 @@ LennardJonesSimulation::LennardJonesSimulation(const std::shared_ptr<LennardJone
         throw std::runtime_error("ljgpu_host_initialize: invalid parameters");
     if (ljgpu_create(&s, &st[0], &st[n], &st[2 * n], &st[3 * n], &st[4 * n], &st[5 * n], &sim) != LJGPU_OK)
         fail("ljgpu_create");
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < kMirrors; ++b) {
         void* p = nullptr;
         if (ljgpu_alloc_host(3 * n * sizeof(double), &p) != LJGPU_OK) { ljgpu_destroy(sim); sim = nullptr; fail("ljgpu_alloc_host"); }
         mirror_buf[b] = static_cast<double*>(p);
@@ -57,7 +57,7 @@ LennardJonesSimulation::LennardJonesSimulation(const std::shared_ptr<LennardJone
 
 LennardJonesSimulation::~LennardJonesSimulation() {
     if (sim) ljgpu_destroy(sim);
-    for (int b = 0; b < 2; ++b) if (mirror_buf[b]) ljgpu_free_host(mirror_buf[b]);
+    for (int b = 0; b < kMirrors; ++b) if (mirror_buf[b]) ljgpu_free_host(mirror_buf[b]);
 }
 
 void LennardJonesSimulation::refresh_energies() {
@@ -68,13 +68,20 @@ void LennardJonesSimulation::refresh_energies() {
     etot.store(t, std::memory_order_relaxed);
 }
 
-// Copies the published positions into the buffer the readers are NOT looking at, then flips the
-// index with release semantics: the protocol of .h:76-84 / .cpp:574-576.
+// Makes the newest positions the readers' buffer: completes a delivery that is in flight, or copies the
+// published positions into a buffer the readers are NOT looking at; then flips the index with release
+// semantics: the protocol of .h:76-84 / .cpp:574-576.
 void LennardJonesSimulation::refresh_mirror() const {
     std::lock_guard<std::mutex> lk(mirror_mu);
     const uint64_t now = steps_done.load(std::memory_order_acquire);
+    if (inflight_idx >= 0) {
+        if (ljgpu_publish_wait(sim) != LJGPU_OK) fail("ljgpu_publish_wait");
+        render_idx.store(inflight_idx, std::memory_order_release);
+        mirrored_step.store(inflight_step, std::memory_order_relaxed);
+        inflight_idx = -1;
+    }
     if (mirrored_step.load(std::memory_order_relaxed) == now) return;
-    const int w = 1 - render_idx.load(std::memory_order_relaxed);
+    const int w = (render_idx.load(std::memory_order_relaxed) + 1) % kMirrors;
     double* b = mirror_buf[w];
     if (ljgpu_get_positions(sim, b, b + n, b + 2 * n) != LJGPU_OK) fail("ljgpu_get_positions");
     render_idx.store(w, std::memory_order_release);
@@ -82,10 +89,26 @@ void LennardJonesSimulation::refresh_mirror() const {
 }
 
 void LennardJonesSimulation::integrate(unsigned int step, double dt) {
-    if (ljgpu_step(sim, step, dt) != LJGPU_OK) fail("ljgpu_step");
-    steps_done.fetch_add(1, std::memory_order_release);
+    if (mirror == Mirror::Eager) {
+        // .cpp:98 publish_state: this step's positions start travelling into the free buffer and arrive while the
+        // next step computes; the delivery of the previous step is complete when the call returns
+        std::lock_guard<std::mutex> lk(mirror_mu);
+        const int vis = render_idx.load(std::memory_order_relaxed), fly = inflight_idx;
+        int tgt = 0;
+        while (tgt == vis || tgt == fly) ++tgt;
+        double* b = mirror_buf[tgt];
+        if (ljgpu_step_publish(sim, step, dt, b, b + n, b + 2 * n) != LJGPU_OK) fail("ljgpu_step_publish");
+        const uint64_t now = steps_done.fetch_add(1, std::memory_order_release) + 1;
+        if (fly >= 0) {
+            render_idx.store(fly, std::memory_order_release);
+            mirrored_step.store(inflight_step, std::memory_order_relaxed);
+        }
+        inflight_idx = tgt; inflight_step = now;
+    } else {
+        if (ljgpu_step(sim, step, dt) != LJGPU_OK) fail("ljgpu_step");
+        steps_done.fetch_add(1, std::memory_order_release);
+    }
     refresh_energies();                                                   // .cpp:95-96
-    if (mirror == Mirror::Eager) refresh_mirror();                        // .cpp:98
     if (step % 1000 == 0 && std::getenv("LJGPU_VERBOSE")) {               // .cpp:100-113
         const auto end = std::chrono::system_clock::now();
         const std::chrono::duration<double> el = end - ttime;
@@ -104,7 +127,7 @@ void LennardJonesSimulation::integrate_n(unsigned int first_step, unsigned int c
 }
 
 int LennardJonesSimulation::get_render_index() const {
-    if (mirror == Mirror::Lazy) refresh_mirror();
+    refresh_mirror();          // lazy: copy on demand; eager: wait for the delivery in flight, so the newest step shows
     return render_idx.load(std::memory_order_acquire);
 }
 const double* LennardJonesSimulation::get_render_x() const { return mirror_buf[get_render_index()]; }

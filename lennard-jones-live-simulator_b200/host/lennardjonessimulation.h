@@ -24,7 +24,9 @@ public:
     using dvec3 = ljgpu_host::dvec3;
 
     // When the host mirror of the published positions (get_render_x/y/z) is refreshed:
-    //   Eager - after every integrate(), exactly the reference's publish_state semantics;
+    //   Eager - every integrate() publishes (the reference's publish_state): the transfer of step k overlaps the
+    //           computation of step k+1 (ljgpu_step_publish); a reader that asks earlier waits for it, so
+    //           get_render_*() after integrate(k) always shows step k;
     //   Lazy  - on get_render_index() / get_positions_copy(), i.e. once per rendered frame;
     // The default is Eager up to 131072 atoms (GUI scale) and Lazy above.
     enum class Mirror { Eager, Lazy };
@@ -81,9 +83,14 @@ private:
     ljgpu_sim* sim = nullptr;
     int kernel_choice = 0, device_choice = -1;
 
-    // host mirror of the published positions: two page-locked SoA buffers + atomic index (.h:76-84)
-    mutable double* mirror_buf[2] = {nullptr, nullptr};
+    // host mirror of the published positions: page-locked SoA buffers + atomic index (.h:76-84).  Three rather
+    // than the reference's two: one is visible to the readers, one may be receiving the positions of the last
+    // step (ljgpu_step_publish delivers while the next step computes), one is free for the next delivery.
+    static constexpr int kMirrors = 3;
+    mutable double* mirror_buf[kMirrors] = {nullptr, nullptr, nullptr};
     mutable std::atomic<int> render_idx{0};
+    mutable int inflight_idx = -1;                     // buffer with a delivery in flight (guarded by mirror_mu)
+    mutable uint64_t inflight_step = 0;                // steps_done value that delivery carries
     mutable std::atomic<uint64_t> mirrored_step{~0ull};
     mutable std::mutex mirror_mu;
     std::atomic<uint64_t> steps_done{0};

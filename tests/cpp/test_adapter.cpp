@@ -97,6 +97,24 @@ int main(int argc, char** argv) {
     ljo_get_energies(o, &ek, &ep, &et);
     CHECK(rel(sim->get_ekin(), ek) < 1e-12);
 
+    // publication: after every integrate() the render buffers show that very step, in both mirror modes
+    // (eager: the delivery in flight is completed on demand and rotates through three buffers; lazy: copied on demand)
+    for (int mode = 0; mode < 2; ++mode) {
+        sim->set_mirror_mode(mode ? LennardJonesSimulation::Mirror::Lazy : LennardJonesSimulation::Mirror::Eager);
+        for (unsigned s = 12 + 5 * mode; s < 17 + 5 * mode; ++s) {
+            sim->integrate(s, dt); ljo_integrate(o, s, dt);
+            ljo_get_positions(o, ox.data(), oy.data(), oz.data());
+            const double* px = sim->get_render_x();
+            const double* py = sim->get_render_y();
+            const double* pz = sim->get_render_z();
+            double md = 0;
+            for (size_t i = 0; i < n; ++i)
+                md = std::fmax(md, std::fmax(std::fabs(px[i] - ox[i]), std::fmax(std::fabs(py[i] - oy[i]), std::fabs(pz[i] - oz[i]))));
+            CHECK(md < 1e-11);
+        }
+    }
+    sim->set_mirror_mode(LennardJonesSimulation::Mirror::Eager);
+
     // movie file: header + one frame
     sim->write_to_movie_file("/tmp/ljgpu_adapter_movie.bin", true);
     FILE* fp = std::fopen("/tmp/ljgpu_adapter_movie.bin", "rb");

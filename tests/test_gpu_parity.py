@@ -200,6 +200,41 @@ def test_changing_dt_and_tau_between_steps(lj):
         check_step(o, g, what=f"dt/tau step {s}")
 
 
+@pytest.mark.parametrize("n_atoms,kernel", [(1000, 1), (20000, 3)])
+def test_step_publish_delivers_every_step(lj, n_atoms, kernel):
+    """ljgpu_step_publish: the positions of step k are complete in the caller's buffers once the call for step
+    k+1 (or ljgpu_publish_wait) returned, bit-identical to integrate() + get_positions on a twin simulation."""
+    cfg = ol.config(n_atoms)
+    o = ol.Oracle(cfg)
+    st = o.state()
+    params = lj.LennardJonesParameters(**cfg)
+    a = lj.LennardJonesSimulation(params, st, force_kernel=kernel)
+    b = lj.LennardJonesSimulation(params, st, force_kernel=kernel)
+    bufs = [[lj.HostBuffer(n_atoms) for _ in range(3)] for _ in range(2)]       # two pinned x/y/z sets
+    expected = []
+    steps = 45 if kernel == 3 else 8                                            # across a re-binning on the list path
+    for s in range(1, steps + 1):
+        a.integrate(s, DT)
+        expected.append((a.get_positions_soa(), a.get_energies()))
+        cur = bufs[s & 1]
+        b.integrate_publish(s, DT, *[h.ptr for h in cur])
+        assert b.get_energies() == expected[-1][1]                              # the step itself is complete on return
+        if s > 1:                                                               # ... and so is the previous delivery
+            prev = bufs[(s - 1) & 1]
+            for got, want in zip(prev, expected[-2][0]):
+                assert np.array_equal(got.array, want)
+    b.publish_wait()
+    for got, want in zip(bufs[steps & 1], expected[-1][0]):
+        assert np.array_equal(got.array, want)
+    b.publish_wait()                                                            # idempotent
+    x, y, z = b.get_positions_soa()
+    assert np.array_equal(x, expected[-1][0][0])
+    for set_ in bufs:
+        for h in set_:
+            h.close()
+    a.close(); b.close()
+
+
 def test_momentum_is_conserved(lj):
     cfg = ol.config(4096)
     _, g = make_pair(lj, cfg, 3)
