@@ -235,6 +235,30 @@ def test_step_publish_delivers_every_step(lj, n_atoms, kernel):
     a.close(); b.close()
 
 
+def test_movie_frames_match_the_reference_writer(lj, tmp_path):
+    """write_to_movie_file (.cpp:121-157): the start frame is byte-identical to the reference writer's (same
+    positions, velocities and speed expression); later frames agree to the parity tolerance."""
+    cfg = ol.DEFAULT
+    o, g = make_pair(lj, cfg, 0)
+    n, L = cfg["nr_particles"], cfg["cell_length"]
+    po, pg = str(tmp_path / "oracle.bin"), str(tmp_path / "gpu.bin")
+    o.write_movie(po, True); g.write_to_movie_file(pg, True)
+    assert open(po, "rb").read() == open(pg, "rb").read()
+    for s in range(1, 4):
+        o.integrate(s, DT); g.integrate(s, DT)
+    o.write_movie(po, False); g.write_to_movie_file(pg, False)
+    ro, rg = open(po, "rb").read(), open(pg, "rb").read()
+    assert len(ro) == len(rg) == 4 + 2 * (24 + n * 56)
+    fo = np.frombuffer(ro[4 + 24 + n * 56:], dtype=np.float64)
+    fg = np.frombuffer(rg[4 + 24 + n * 56:], dtype=np.float64)
+    assert np.array_equal(fo[:3], fg[:3])
+    a, b = fo[3:].reshape(n, 7), fg[3:].reshape(n, 7)
+    d = np.abs(a[:, :3] - b[:, :3]); d = np.minimum(d, L - d)
+    assert d.max() < 1e-11
+    assert np.abs(a[:, 3:] - b[:, 3:]).max() < 1e-11
+    g.close()
+
+
 def test_momentum_is_conserved(lj):
     cfg = ol.config(4096)
     _, g = make_pair(lj, cfg, 3)
