@@ -3,6 +3,7 @@
 // Path replaced: class LennardJonesSimulation, /root/reference/src/simulator/lennardjonessimulation.{h,cpp}
 // (".cpp"/".h" below).  No CPU fallback: every entry point fails with LJGPU_ECUDA when there is no device.
 #include "lj_tile.cuh"
+#include "lj_pair.cuh"
 #include "lj_nccl.h"
 #include "../../include/ljgpu.h"
 
@@ -148,6 +149,16 @@ struct ljgpu_sim {
     uint32_t* nl = nullptr; uint32_t* nl_count = nullptr; unsigned capq = 0; size_t nl_alloc = 0;
     // pruned inner list (single-device Verlet path)
     uint32_t* nl_in = nullptr; uint32_t* nl_in_count = nullptr;
+    // EXPERIMENTAL pair path (lj_pair.cuh, LJGPU_PAIRLIST=1): one thread per two home atoms, union lists per slot
+    bool pairlist = false;
+    unsigned pbx = 0, pby = 0, pbz = 0, pnbx = 0, pnby = 0, pnbz = 0, pnblocks = 0, ptcap = 0, pthreads = 32, pslots = 32, pcapq = 0;
+    uint32_t *ptsrc = nullptr, *ptoff = nullptr, *pl = nullptr, *pl_in = nullptr, *pl_count = nullptr, *pl_in_count = nullptr;
+    size_t pl_alloc = 0, pslots_alloc = 0;
+    TileGrid pair_grid() const {
+        return TileGrid{nc, ncz, 1u, 0u, nc, pbx, pby, pbz, pnbx, pnby, pnbz, pnblocks, ptsrc, ptoff};
+    }
+    void pair_tables();
+    void pair_build_list();
     double prune_skin = 0.0; unsigned prune_interval = 8, since_prune = 0;
 
     // reductions
@@ -173,7 +184,7 @@ struct ljgpu_sim {
     // one re-binning to the next, launch shapes only grow): after a few re-binnings every step replays a cached
     // graph and nothing is instantiated any more (an instantiation now and then took tens of milliseconds).
     struct GraphKey {
-        const void* ptr[16]; unsigned shape[6]; double dt; uint64_t gen; int prune;
+        const void* ptr[20]; unsigned shape[10]; double dt; uint64_t gen; int prune;
         bool operator==(const GraphKey& o) const { return std::memcmp(this, &o, sizeof(GraphKey)) == 0; }
     };
     struct StepGraph { cudaGraphExec_t exec = nullptr; uint64_t kernels = 0; uint64_t cnt[ST_COUNT] = {0}; GraphKey key; uint64_t used = 0; };
@@ -296,6 +307,7 @@ ljgpu_sim::~ljgpu_sim() {
     dfree(orig); dfree(orig_alt); dfree(keys); dfree(vals);
     dfree(cstart); dfree(cend); dfree(ccount);
     dfree(nl); dfree(nl_count); dfree(nl_in); dfree(nl_in_count); dfree(tsrc); dfree(toff);
+    dfree(ptsrc); dfree(ptoff); dfree(pl); dfree(pl_in); dfree(pl_count); dfree(pl_in_count);
     dfree(partial_epot); dfree(partial_ekin); dfree(partial_pred);
     dfree(ctrl); dfree(hist); dfree(out3); dfree(out_u32); dfree(hist_counts);
     if (st_copy) { cudaStreamSynchronize(st_copy); cudaStreamDestroy(st_copy); }
@@ -413,6 +425,17 @@ void ljgpu_sim::allocate() {
         CK(cudaMalloc(&tsrc, (size_t)nblocks_tile * kTileCellsMax * 4));
         CK(cudaMalloc(&toff, (size_t)nblocks_tile * (kTileCellsMax + 1) * 4));
         nb_force = nblocks_tile;                                   // one partial per CTA
+        // experimental pair path: bricks of 6x2x2 cells when that still gives the SMs a few waves of CTAs
+        pairlist = std::getenv("LJGPU_PAIRLIST") != nullptr && !slab.on && mode == LJGPU_KERNEL_VERLET;
+        if (pairlist) {
+            pbx = kPairBX; pby = kPairBY; pbz = kPairBZ;
+            pnbx = cdiv(nc, pbx); pnby = cdiv(nc, pby); pnbz = cdiv(nc, pbz); pnblocks = pnbx * pnby * pnbz;
+            if (pnblocks < 4u * 148u) pairlist = false;            // small systems stay on the per-atom path
+        }
+        if (pairlist) {
+            CK(cudaMalloc(&ptsrc, (size_t)pnblocks * kPairCellsMax * 4));
+            CK(cudaMalloc(&ptoff, (size_t)pnblocks * (kPairCellsMax + 1) * 4));
+        }
     } else {
         // j splits: enough blocks to fill 148 SMs a few times over, each split at least 64 atoms wide
         const unsigned nba = cdiv(N, kBlock);
@@ -734,8 +757,10 @@ void ljgpu_sim::rebuild() {
     set_tile_attributes((size_t)tcap * kTileRecBytes);
 
     lap("tile_table");
-    if (mode == LJGPU_KERNEL_VERLET) build_list();
+    if (pairlist) { pair_tables(); pair_build_list(); }
+    else if (mode == LJGPU_KERNEL_VERLET) build_list();
     lap("build_list");
+    if (pairlist) nb_force = pnblocks;                   // one epot partial per pair CTA
     stage_end(ST_REBUILD, ev);
     ++rebuilds;
     if (since_rebuild > 0) last_interval = since_rebuild;
@@ -769,6 +794,80 @@ template <int MODE>
 static void launch_tile(ljgpu_sim* s, int guarded) {
     if ((MODE == TILE_FORCE_LIST || MODE == TILE_FORCE_PRUNE) && s->c.sigma2 == 1.0) launch_tile2<MODE, true>(s, guarded);
     else launch_tile2<MODE, false>(s, guarded);
+}
+
+template <int MODE, bool UNIT_SIGMA>
+static void launch_pair2(ljgpu_sim* s, int guarded) {
+    const size_t smem = (size_t)s->ptcap * kTileRecBytes;
+    PairArgs a{s->pos, s->pl, s->pl_count, s->prune_skin > 0.0 ? s->pl_in : nullptr, s->pl_in_count, s->nl_count,
+               s->f[0], s->f[1], s->f[2], s->partial_epot, s->ctrl, s->pcapq, s->pslots};
+    pair_kernel<MODE, UNIT_SIGMA><<<s->pnblocks, s->pthreads, smem, s->st>>>(s->c, s->pair_grid(), a, guarded);
+    s->check_launch("pair_kernel");
+}
+template <int MODE>
+static void launch_pair(ljgpu_sim* s, int guarded) {
+    if ((MODE == TILE_FORCE_LIST || MODE == TILE_FORCE_PRUNE) && s->c.sigma2 == 1.0) launch_pair2<MODE, true>(s, guarded);
+    else launch_pair2<MODE, false>(s, guarded);
+}
+template <int MODE, bool US>
+static void pair_attr(size_t smem) {
+    CK(cudaFuncSetAttribute(pair_kernel<MODE, US>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+}
+
+// Pair path, re-binning part 1: tile tables of the 6x2x2 bricks, launch shapes (only ever growing).
+void ljgpu_sim::pair_tables() {
+    CK(cudaMemsetAsync(&ctrl->max_tile, 0, sizeof(unsigned), st));
+    CK(cudaMemsetAsync(&ctrl->max_home, 0, sizeof(unsigned), st));
+    pair_table_kernel<<<cdiv(pnblocks, 4), 128, 0, st>>>(pair_grid(), cstart, ccount, ptsrc, ptoff, ctrl);
+    check_launch("pair_table");
+    fetch_ctrl();
+    if (h_ctrl->max_tile > 65535) throw LjError(LJGPU_ESTATE, "pair tile too large for 16-bit list indices");
+    ptcap = std::max(ptcap, ((h_ctrl->max_tile + 63) / 64) * 64);
+    if ((size_t)ptcap * kTileRecBytes > 100 * 1024)
+        throw LjError(LJGPU_ESTATE, "a pair-brick neighbourhood does not fit in shared memory twice per SM");
+    pslots = std::max(pslots, ((h_ctrl->max_home + 31) / 32) * 32);
+    pthreads = std::min((unsigned)LJ_PAIR_MAXTHREADS, pslots);
+    const size_t smem = (size_t)ptcap * kTileRecBytes;
+    if (smem > 40 * 1024) {
+        pair_attr<TILE_FORCE_LIST, true>(smem); pair_attr<TILE_FORCE_LIST, false>(smem);
+        pair_attr<TILE_FORCE_PRUNE, true>(smem); pair_attr<TILE_FORCE_PRUNE, false>(smem);
+        pair_attr<TILE_LIST_COUNT, false>(smem); pair_attr<TILE_LIST_FILL, false>(smem);
+    }
+    const size_t slots = (size_t)pnblocks * pslots;
+    if (slots > pslots_alloc) {
+        dfree(pl_count); dfree(pl_in_count);
+        CK(cudaMalloc(&pl_count, slots * 4)); CK(cudaMalloc(&pl_in_count, slots * 4));
+        pslots_alloc = slots;
+        pl_alloc = 0;                                    // slot numbering changed: lists are re-sized below
+        ++graph_gen;
+    }
+}
+
+// Pair path, re-binning part 2: union lists (count once for the capacity, then fill; grow and refill on overflow).
+void ljgpu_sim::pair_build_list() {
+    const size_t ntiles = cdiv((unsigned)((size_t)pnblocks * pslots), 32);
+    for (int attempt = 0; attempt < 4; ++attempt) {
+        CK(cudaMemsetAsync(&ctrl->max_count, 0, sizeof(unsigned), st));
+        CK(cudaMemsetAsync(&ctrl->overflow, 0, sizeof(unsigned), st));
+        if (pcapq == 0) {
+            launch_pair<TILE_LIST_COUNT>(this, 0);
+            fetch_ctrl();
+            pcapq = (h_ctrl->max_count + 16 + 7) / 8;
+        }
+        const size_t need = ntiles * pcapq * 32 * 4;
+        if (need > pl_alloc) {
+            const size_t want = ntiles * (pcapq + 2) * 32 * 4;
+            dfree(pl); dfree(pl_in);
+            CK(cudaMalloc(&pl, want * 4)); CK(cudaMalloc(&pl_in, want * 4));
+            pl_alloc = want;
+            ++graph_gen;
+        }
+        launch_pair<TILE_LIST_FILL>(this, 0);
+        fetch_ctrl();
+        if (!h_ctrl->overflow) return;
+        pcapq = (h_ctrl->max_count + 16 + 7) / 8;
+    }
+    throw LjError(LJGPU_ESTATE, "pair list capacity did not converge");
 }
 
 void ljgpu_sim::build_list() {
@@ -835,6 +934,8 @@ void ljgpu_sim::launch_force(bool timed) {
         check_launch("allpairs_reduce");
     } else if (mode == LJGPU_KERNEL_CELL) {
         launch_tile<TILE_FORCE_CELL>(this, 1);
+    } else if (pairlist) {
+        launch_pair<TILE_FORCE_LIST>(this, 1);
     } else {
         launch_tile<TILE_FORCE_LIST>(this, 1);
     }
@@ -890,7 +991,8 @@ void ljgpu_sim::enqueue_step(bool prune_now, double dt) {
     if (slab.on) halo_exchange();
     if (prune_now) {       // this step's force pass walks the outer list and emits the inner one
         cudaEvent_t pv = stage_begin();
-        launch_tile<TILE_FORCE_PRUNE>(this, 1);
+        if (pairlist) launch_pair<TILE_FORCE_PRUNE>(this, 1);
+        else launch_tile<TILE_FORCE_PRUNE>(this, 1);
         prune_commit_kernel<<<1, 1, 0, st>>>(ctrl);
         check_launch("prune_commit");
         stage_end(ST_GHOST, pv);                        // reported as ms_ghost / n_ghost: force passes that also pruned
@@ -913,10 +1015,11 @@ void ljgpu_sim::enqueue_step(bool prune_now, double dt) {
 ljgpu_sim::GraphKey ljgpu_sim::graph_key(bool prune_now, double dt) const {
     GraphKey k;
     std::memset(&k, 0, sizeof k);                      // padding included: keys are compared bytewise
-    const void* ptrs[16] = {pos, v[0], v[1], v[2], f[0], f[1], f[2], dij[0], dij[1], dij[2],
-                            nl, nl_in, nl_count, nl_in_count, tsrc, toff};
+    const void* ptrs[20] = {pos, v[0], v[1], v[2], f[0], f[1], f[2], dij[0], dij[1], dij[2],
+                            nl, nl_in, nl_count, nl_in_count, tsrc, toff, pl, pl_in, pl_count, pl_in_count};
     std::memcpy(k.ptr, ptrs, sizeof ptrs);
     k.shape[0] = n; k.shape[1] = tile_threads; k.shape[2] = tcap; k.shape[3] = capq; k.shape[4] = nblocks_tile; k.shape[5] = nb_force;
+    k.shape[6] = pthreads; k.shape[7] = ptcap; k.shape[8] = pcapq; k.shape[9] = pslots;
     k.dt = dt; k.gen = graph_gen; k.prune = prune_now ? 1 : 0;
     return k;
 }
