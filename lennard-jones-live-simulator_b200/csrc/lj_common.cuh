@@ -4,7 +4,11 @@
 // /root/reference/src/simulator/lennardjonessimulation.cpp:70-576 (".cpp" in the comments below).
 #pragma once
 
+// LJ_EMUL: the same sources compiled by g++ against tests/cuda_emul/cuda_emul.h (threads of a block as host
+// threads) - test infrastructure for checking kernel logic without a GPU, never part of libljgpu.so.
+#ifndef LJ_EMUL
 #include <cuda_runtime.h>
+#endif
 #include <cstdint>
 #include <cstddef>
 
@@ -167,7 +171,11 @@ __device__ __forceinline__ double block_max(double v, double* smem32) {
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ double fast_rcp(double a) {
     double y;
+#ifdef LJ_EMUL
+    y = ljemul::rcp_seed(a);
+#else
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));     // MUFU.RCP64H: relative error e0 < 2^-20
+#endif
     // one third-order step: y (1 + e + e^2) with e = 1 - a y  ->  error e0^3 < 2^-60, three DFMA
     const double e = fma(-a, y, 1.0);
     const double p = fma(e, e, e);
@@ -191,18 +199,49 @@ __device__ __forceinline__ double lj_pair(double d2, double sigma2, double& e) {
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ double4 ld_pos(const double4* p) {
     double4 r;
+#ifdef LJ_EMUL
+    r = *p;
+#else
     asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+#endif
     return r;
 }
 // read-only path (positions are not written by the kernel that uses this)
 __device__ __forceinline__ double4 ld_pos_nc(const double4* p) {
     double4 r;
+#ifdef LJ_EMUL
+    r = *p;
+#else
     asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+#endif
     return r;
 }
 __device__ __forceinline__ void st_pos(double4* p, const double4& v) {
+#ifdef LJ_EMUL
+    *p = v;
+#else
     asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" :: "l"(p), "d"(v.x), "d"(v.y), "d"(v.z), "d"(v.w) : "memory");
+#endif
 }
+
+// Asynchronous global->shared copies (LDGSTS) behind helpers; shared addresses are 32-bit shared-window offsets.
+#ifdef LJ_EMUL
+#define LJ_DYNAMIC_SMEM(name) double* name = reinterpret_cast<double*>(ljemul::dynamic_smem())
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return ljemul::smem_offset(p); }
+__device__ __forceinline__ void cp_async8(unsigned saddr, const void* g) { ljemul::smem_copy(saddr, g, 8); }
+__device__ __forceinline__ void cp_async16(unsigned saddr, const void* g) { ljemul::smem_copy(saddr, g, 16); }
+__device__ __forceinline__ void cp_async_wait_all() {}
+#else
+#define LJ_DYNAMIC_SMEM(name) extern __shared__ __align__(16) double name[]
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async8(unsigned saddr, const void* g) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async16(unsigned saddr, const void* g) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // Device-wide primitives implemented in lj_sort.cu

@@ -481,15 +481,27 @@ slab_reduce_kernel(LJConst c, StepCtrl* __restrict__ ctrl,
 // ---- slab path over peer memory (NVLink loads/stores, no NCCL in the step loop) ----------------------
 __device__ __forceinline__ unsigned long long ld_sys_u64(const unsigned long long* p) {
     unsigned long long v;
+#ifdef LJ_EMUL
+    v = ljemul::atomic_load_u64(p);
+#else
     asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+#endif
     return v;
 }
 __device__ __forceinline__ void st_sys_u64(unsigned long long* p, unsigned long long v) {
+#ifdef LJ_EMUL
+    ljemul::atomic_store_u64(p, v);
+#else
     asm volatile("st.relaxed.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+#endif
 }
 __device__ __forceinline__ double ld_sys_f64(const double* p) {
     double v;
+#ifdef LJ_EMUL
+    v = ljemul::atomic_load_f64(p);
+#else
     asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+#endif
     return v;
 }
 // Spin until *flag >= seq; gives up after ~2 s (a peer died) so that no kernel can hang the device.

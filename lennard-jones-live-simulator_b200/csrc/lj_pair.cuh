@@ -98,7 +98,7 @@ struct PairArgs {
 template <int MODE, bool UNIT_SIGMA>
 __global__ void __launch_bounds__(LJ_PAIR_MAXTHREADS, LJ_PAIR_MINBLOCKS)
 pair_kernel(LJConst c, TileGrid g, PairArgs a, int guarded) {
-    extern __shared__ __align__(16) double sm[];
+    LJ_DYNAMIC_SMEM(sm);
     __shared__ uint32_t s_off[kPairCellsMax + 1];
     __shared__ uint32_t s_src[kPairCellsMax];
     __shared__ uint32_t s_pstart[kPairHomeRows + 1];    // prefix of pairs per home x-row
@@ -128,7 +128,7 @@ pair_kernel(LJConst c, TileGrid g, PairArgs a, int guarded) {
         constexpr int kW = kPairBX + 2;
         const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
         const unsigned nrows = H * (tg.bd + 2);
-        const unsigned smem_base = (unsigned)__cvta_generic_to_shared(sm);
+        const unsigned smem_base = smem_addr(sm);
         for (unsigned r = w; r < nrows; r += nw) {
             const unsigned t0 = r * W;
             unsigned offk[kW], delk[kW];
@@ -147,17 +147,17 @@ pair_kernel(LJConst c, TileGrid g, PairArgs a, int guarded) {
                 const double* gp = reinterpret_cast<const double*>(a.pos + (li + d));
 #if LJ_TILE_REC32
                 const unsigned sp = smem_base + li * 32u, sw = li & 16u;
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(sp + sw), "l"(gp) : "memory");
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(sp + 16u - sw), "l"(gp + 2) : "memory");
+                cp_async16(sp + sw, gp);
+                cp_async16(sp + 16u - sw, gp + 2);
 #else
                 const unsigned sp = smem_base + li * 24u;
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(sp), "l"(gp) : "memory");
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(sp + 8), "l"(gp + 1) : "memory");
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(sp + 16), "l"(gp + 2) : "memory");
+                cp_async8(sp, gp);
+                cp_async8(sp + 8, gp + 1);
+                cp_async8(sp + 16, gp + 2);
 #endif
             }
         }
-        asm volatile("cp.async.wait_all;" ::: "memory");
+        cp_async_wait_all();
     }
     __syncthreads();
 
