@@ -33,6 +33,10 @@ constexpr int kPairBZ = 2;
 constexpr int kPairRowsMax = (kPairBY + 2) * (kPairBZ + 2);
 constexpr int kPairCellsMax = (kPairBX + 2) * kPairRowsMax;
 constexpr int kPairHomeRows = kPairBY * kPairBZ;
+#ifndef LJ_PAIR_GROUP
+#define LJ_PAIR_GROUP 2                    // list entries evaluated together (x 2 atoms = independent chains): 1, 2 or 4
+#endif
+constexpr int kPairGroup = LJ_PAIR_GROUP;
 
 // Re-binning: tile tables of the pair bricks (strides kPairCellsMax); max_tile = atoms in the largest tile,
 // max_home = PAIRS in the fullest brick (sum over home x-rows of ceil(atoms / 2)).
@@ -207,13 +211,19 @@ pair_kernel(LJConst c, TileGrid g, PairArgs a, int guarded) {
                 if (qd + 1 < nq) nxt = __ldg(row + (size_t)(qd + 1) * 32);
                 const unsigned nvalid = n - 8u * qd;                 // entries of this quad that exist (tail: padding)
 #pragma unroll
-                for (int part = 0; part < 4; ++part) {               // two entries x two atoms = four chains in flight
-                    const uint32_t w = part == 0 ? cur.x : part == 1 ? cur.y : part == 2 ? cur.z : cur.w;
-                    const unsigned jj[2] = { w & 0xffffu, w >> 16 };
-                    double d1x[2], d1y[2], d1z[2], d2x[2], d2y[2], d2z[2], r1[2], r2[2];
+                for (int part = 0; part < 8 / kPairGroup; ++part) {  // kPairGroup entries x two atoms: chains in flight
+                    constexpr int G = kPairGroup;
+                    unsigned jj[G];
+#pragma unroll
+                    for (int u = 0; u < G; ++u) {
+                        const int k = part * G + u;                  // half-word k of the quad
+                        const uint32_t w = (k >> 1) == 0 ? cur.x : (k >> 1) == 1 ? cur.y : (k >> 1) == 2 ? cur.z : cur.w;
+                        jj[u] = (k & 1) ? (w >> 16) : (w & 0xffffu);
+                    }
+                    double d1x[G], d1y[G], d1z[G], d2x[G], d2y[G], d2z[G], r1[G], r2[G];
                     int far = 0;
 #pragma unroll
-                    for (int u = 0; u < 2; ++u) {
+                    for (int u = 0; u < G; ++u) {
                         double jx, jy, jz;
                         tile_ld(sm, jj[u], jx, jy, jz);
                         d1x[u] = p1x - jx; d1y[u] = p1y - jy; d1z[u] = p1z - jz;
@@ -224,7 +234,7 @@ pair_kernel(LJConst c, TileGrid g, PairArgs a, int guarded) {
                     }
                     if (far >= far2_hi) {
 #pragma unroll
-                        for (int u = 0; u < 2; ++u) {
+                        for (int u = 0; u < G; ++u) {
                             if (maybe_wrapped(r1[u], far2_hi)) {
                                 d1x[u] = min_image(d1x[u], c.L, c.halfL); d1y[u] = min_image(d1y[u], c.L, c.halfL);
                                 d1z[u] = min_image(d1z[u], c.L, c.halfL);
@@ -238,8 +248,8 @@ pair_kernel(LJConst c, TileGrid g, PairArgs a, int guarded) {
                         }
                     }
 #pragma unroll
-                    for (int u = 0; u < 2; ++u) {
-                        const bool valid = (unsigned)(2 * part + u) < nvalid;
+                    for (int u = 0; u < G; ++u) {
+                        const bool valid = (unsigned)(G * part + u) < nvalid;
                         const bool in1 = valid && (r1[u] < c.rc2) && (jj[u] != li1);
                         const bool in2 = valid && has2 && (r2[u] < c.rc2) && (jj[u] != li2);
                         {
