@@ -430,7 +430,7 @@ void ljgpu_sim::allocate() {
         if (pairlist) {
             pbx = kPairBX; pby = kPairBY; pbz = kPairBZ;
             pnbx = cdiv(nc, pbx); pnby = cdiv(nc, pby); pnbz = cdiv(nc, pbz); pnblocks = pnbx * pnby * pnbz;
-            if (pnblocks < 4u * 148u) pairlist = false;            // small systems stay on the per-atom path
+            if (pnblocks < 2u * 148u) pairlist = false;            // fewer bricks than one wave of CTAs: stay on the per-atom path
         }
         if (pairlist) {
             CK(cudaMalloc(&ptsrc, (size_t)pnblocks * kPairCellsMax * 4));

@@ -1,12 +1,14 @@
 // cuda_emul.h - TEST INFRASTRUCTURE ONLY.  A minimal CUDA-on-CPU shim: the device headers of
 // lennard-jones-live-simulator_b200/csrc are compiled by g++ with -DLJ_EMUL and their kernels run with the
-// threads of a block as host threads (one block at a time, std::barrier for __syncthreads / warp
-// collectives).  It exists to check kernel LOGIC (indexing, list layout, staging tables) where no GPU is
+// threads of a block as cooperatively scheduled fibers on one host thread (barriers and warp collectives yield to
+// the next fiber), blocks spread over a few host threads.  It exists to check kernel LOGIC (indexing, list layout, staging tables) where no GPU is
 // available; it is never linked into libljgpu.so and the product has no CPU path.
 #pragma once
 #include <algorithm>
 #include <atomic>
-#include <barrier>
+#include <cstdio>
+#include <functional>
+#include <sys/mman.h>
 #include <chrono>
 #include <cmath>
 #include <cstdint>
@@ -21,7 +23,7 @@
 #define __host__
 #define __forceinline__ inline
 #define __restrict__
-#define __shared__ static
+#define __shared__ static thread_local      /* one copy per host thread = per running block */
 #define __launch_bounds__(...)
 #define __align__(n) alignas(n)
 
@@ -35,31 +37,62 @@ inline uint4 make_uint4(unsigned a, unsigned b, unsigned c, unsigned d) { return
 inline double4 make_double4(double a, double b, double c, double d) { return double4{a, b, c, d}; }
 inline double2 make_double2(double a, double b) { return double2{a, b}; }
 
+inline thread_local uint3 threadIdx, blockIdx;
+inline thread_local dim3 blockDim, gridDim;
+
+// Minimal x86-64 context switch (callee-saved registers + stack pointer; no signal-mask system call like swapcontext).
+extern "C" void ljemul_switch(void** save_sp, void* load_sp);
+asm(R"(
+.text
+.weak ljemul_switch
+.type ljemul_switch, @function
+ljemul_switch:
+    pushq %rbp
+    pushq %rbx
+    pushq %r12
+    pushq %r13
+    pushq %r14
+    pushq %r15
+    movq %rsp, (%rdi)
+    movq %rsi, %rsp
+    popq %r15
+    popq %r14
+    popq %r13
+    popq %r12
+    popq %rbx
+    popq %rbp
+    ret
+.size ljemul_switch, .-ljemul_switch
+)");
+
 namespace ljemul {
 
-struct Warp {
-    std::barrier<> bar;
-    unsigned long long xch[32];
-    explicit Warp(int lanes) : bar(lanes) {}
-};
-struct Block {
-    unsigned nthreads;
-    std::barrier<> bar;
-    std::vector<std::unique_ptr<Warp>> warps;
+constexpr size_t kFiberStack = 128 * 1024;
+
+struct WarpState { unsigned live = 0, count = 0, gen = 0; unsigned long long xch[32]; };
+struct Fiber { void* sp = nullptr; bool done = false; unsigned tid = 0; };
+
+// One running block: its fibers, barrier state and dynamic shared memory.  Lives on the host thread that runs it.
+struct BlockRun {
+    unsigned nthreads = 0, live = 0, bar_count = 0, bar_gen = 0;
+    std::vector<WarpState> warps;
+    std::vector<Fiber> fibers;
     std::vector<char> dyn_storage;
     char* dyn = nullptr;
-    Block(unsigned nt, size_t smem) : nthreads(nt), bar((std::ptrdiff_t)nt), dyn_storage(smem + 64) {
-        for (unsigned w = 0; w < (nt + 31) / 32; ++w) warps.emplace_back(new Warp((int)std::min(32u, nt - 32 * w)));
-        dyn = dyn_storage.data();
-        dyn += (64 - (reinterpret_cast<uintptr_t>(dyn) & 63)) & 63;
-    }
+    char* stacks = nullptr;
+    size_t stacks_bytes = 0;
+    void* sched_sp = nullptr;
+    Fiber* cur = nullptr;
+    const std::function<void()>* kernel = nullptr;
+    unsigned long long progress = 0;
+    ~BlockRun() { if (stacks) munmap(stacks, stacks_bytes); }
 };
-inline thread_local Block* t_block = nullptr;
+inline thread_local BlockRun* t_run = nullptr;
 inline thread_local unsigned t_tid = 0;
 
-inline void* dynamic_smem() { return t_block->dyn; }
-inline unsigned smem_offset(const void* p) { return (unsigned)(static_cast<const char*>(p) - t_block->dyn); }
-inline void smem_copy(unsigned off, const void* g, unsigned bytes) { std::memcpy(t_block->dyn + off, g, bytes); }
+inline void* dynamic_smem() { return t_run->dyn; }
+inline unsigned smem_offset(const void* p) { return (unsigned)(static_cast<const char*>(p) - t_run->dyn); }
+inline void smem_copy(unsigned off, const void* g, unsigned bytes) { std::memcpy(t_run->dyn + off, g, bytes); }
 inline double rcp_seed(double a) { return (double)(1.0f / (float)a); }        // ~2^-23 relative error, like MUFU.RCP64H
 inline unsigned long long atomic_load_u64(const unsigned long long* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
 inline void atomic_store_u64(unsigned long long* p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
@@ -68,30 +101,103 @@ inline double atomic_load_f64(const double* p) {
     double d; std::memcpy(&d, &b, 8); return d;
 }
 
-inline Warp& warp() { return *t_block->warps[t_tid >> 5]; }
+inline void yield_fiber() {
+    BlockRun& r = *t_run;
+    Fiber* me = r.cur;
+    ljemul_switch(&me->sp, r.sched_sp);
+}
+inline void sync_block() {
+    BlockRun& r = *t_run;
+    const unsigned gen = r.bar_gen;
+    if (++r.bar_count == r.live) { r.bar_count = 0; ++r.bar_gen; ++r.progress; }
+    else while (r.bar_gen == gen) yield_fiber();
+}
+inline void sync_warp() {
+    BlockRun& r = *t_run;
+    WarpState& w = r.warps[t_tid >> 5];
+    const unsigned gen = w.gen;
+    if (++w.count == w.live) { w.count = 0; ++w.gen; ++r.progress; }
+    else while (w.gen == gen) yield_fiber();
+}
 template <class T>
 inline T warp_exchange(T v, int src_lane) {           // every live lane of the warp calls this together
     static_assert(sizeof(T) <= 8, "8-byte lanes");
-    Warp& w = warp();
+    WarpState& w = t_run->warps[t_tid >> 5];
     const int lane = (int)(t_tid & 31u);
     unsigned long long bits = 0;
     std::memcpy(&bits, &v, sizeof(T));
     w.xch[lane] = bits;
-    w.bar.arrive_and_wait();
+    sync_warp();
     const unsigned long long got = w.xch[(src_lane >= 0 && src_lane < 32) ? src_lane : lane];
-    w.bar.arrive_and_wait();
+    sync_warp();
     T r; std::memcpy(&r, &got, sizeof(T));
     return r;
 }
 
+inline void fiber_main() {
+    BlockRun& r = *t_run;
+    Fiber* me = r.cur;
+    (*r.kernel)();
+    // a finished thread no longer takes part in barriers: release the ones it was the last straggler of
+    me->done = true;
+    ++r.progress;
+    --r.live;
+    if (r.bar_count && r.bar_count == r.live) { r.bar_count = 0; ++r.bar_gen; }
+    WarpState& w = r.warps[me->tid >> 5];
+    --w.live;
+    if (w.count && w.count == w.live) { w.count = 0; ++w.gen; }
+    ljemul_switch(&me->sp, r.sched_sp);
+    std::abort();                                   // a finished fiber is never resumed
+}
+
+// Runs one block to completion on the calling host thread.
+inline void run_block(BlockRun& r, unsigned nthreads, size_t smem, uint3 bidx, dim3 grid, const std::function<void()>& kernel) {
+    r.nthreads = r.live = nthreads; r.bar_count = 0; r.kernel = &kernel; r.progress = 0;
+    r.warps.assign((nthreads + 31) / 32, WarpState());
+    for (unsigned w = 0; w < r.warps.size(); ++w) r.warps[w].live = std::min(32u, nthreads - 32 * w);
+    if (r.dyn_storage.size() < smem + 64) r.dyn_storage.resize(smem + 64);
+    r.dyn = r.dyn_storage.data();
+    r.dyn += (64 - (reinterpret_cast<uintptr_t>(r.dyn) & 63)) & 63;
+    if (r.stacks_bytes < (size_t)nthreads * kFiberStack) {
+        if (r.stacks) munmap(r.stacks, r.stacks_bytes);
+        r.stacks_bytes = (size_t)nthreads * kFiberStack;
+        r.stacks = static_cast<char*>(mmap(nullptr, r.stacks_bytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0));
+        if (r.stacks == MAP_FAILED) { std::fprintf(stderr, "ljemul: cannot map fiber stacks\n"); std::abort(); }
+    }
+    r.fibers.assign(nthreads, Fiber());
+    t_run = &r;
+    blockIdx = bidx; blockDim = dim3(nthreads); gridDim = grid;
+    for (unsigned t = 0; t < nthreads; ++t) {
+        Fiber& f = r.fibers[t];
+        f.tid = t;
+        // initial frame: six callee-saved registers, the entry point for `ret`, a null return address
+        char* top = r.stacks + (size_t)(t + 1) * kFiberStack;
+        void** sp = reinterpret_cast<void**>(top) - 8;
+        for (int k = 0; k < 6; ++k) sp[k] = nullptr;
+        sp[6] = reinterpret_cast<void*>(&fiber_main);
+        sp[7] = nullptr;
+        f.sp = sp;
+    }
+    unsigned long long seen = ~0ull;
+    while (r.live) {
+        if (seen == r.progress) { std::fprintf(stderr, "ljemul: deadlock in block (%u,%u): %u threads wait at a barrier nobody else reaches\n", bidx.x, bidx.y, r.live); std::abort(); }
+        seen = r.progress;
+        for (unsigned t = 0; t < nthreads; ++t) {
+            Fiber& f = r.fibers[t];
+            if (f.done) continue;
+            r.cur = &f; t_tid = t; threadIdx = uint3{t, 0, 0};
+            ljemul_switch(&r.sched_sp, f.sp);
+        }
+    }
+    t_run = nullptr;
+}
+
 }  // namespace ljemul
 
-inline thread_local uint3 threadIdx, blockIdx;
-inline thread_local dim3 blockDim, gridDim;
 
 // ---- synchronisation, warp collectives ------------------------------------------------------------------
-inline void __syncthreads() { ljemul::t_block->bar.arrive_and_wait(); }
-inline void __syncwarp(unsigned = 0xffffffffu) { ljemul::warp().bar.arrive_and_wait(); }
+inline void __syncthreads() { ljemul::sync_block(); }
+inline void __syncwarp(unsigned = 0xffffffffu) { ljemul::sync_warp(); }
 inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 inline void __threadfence_block() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 inline void __threadfence_system() { std::atomic_thread_fence(std::memory_order_seq_cst); }
@@ -103,6 +209,14 @@ inline int __any_sync(unsigned, int pred) {
     int any = 0;
     for (int l = 0; l < 32; ++l) any |= ljemul::warp_exchange(pred ? 1 : 0, l);
     return any;
+}
+
+inline int __ffs(unsigned v) { return v ? __builtin_ctz(v) + 1 : 0; }
+inline int __popc(unsigned v) { return __builtin_popcount(v); }
+template <class T> inline unsigned __match_any_sync(unsigned, T v) {
+    unsigned m = 0;
+    for (int l = 0; l < 32; ++l) if (ljemul::warp_exchange(v, l) == v) m |= 1u << l;
+    return m;
 }
 
 // ---- atomics ----------------------------------------------------------------------------------------------
@@ -133,7 +247,7 @@ inline unsigned __double2uint_rz(double d) { return d <= 0.0 ? 0u : (d >= 429496
 inline int __double2int_rz(double d) { return (int)d; }
 template <class T> inline T __ldg(const T* p) { return *p; }
 inline long long clock64() { return std::chrono::steady_clock::now().time_since_epoch().count(); }
-inline void __nanosleep(unsigned) { std::this_thread::yield(); }
+inline void __nanosleep(unsigned) { if (ljemul::t_run) ljemul::yield_fiber(); }
 using std::floor;
 using std::fma;
 using std::sqrt;
@@ -152,24 +266,31 @@ inline double max(double a, double b) { return a > b ? a : b; }
 
 namespace ljemul {
 
-// Runs `kernel()` for every block of the grid, one block at a time, one host thread per CUDA thread.
-template <class F>
-void launch(unsigned nblocks, unsigned nthreads, size_t smem, F&& kernel) {
-    for (unsigned b = 0; b < nblocks; ++b) {
-        Block blk(nthreads, smem);
-        std::vector<std::thread> th;
-        th.reserve(nthreads);
-        for (unsigned t = 0; t < nthreads; ++t)
-            th.emplace_back([&, t] {
-                t_block = &blk; t_tid = t;
-                threadIdx = uint3{t, 0, 0}; blockIdx = uint3{b, 0, 0};
-                blockDim = dim3(nthreads); gridDim = dim3(nblocks);
-                kernel();
-                blk.warps[t >> 5]->bar.arrive_and_drop();      // a finished thread no longer takes part in barriers
-                blk.bar.arrive_and_drop();
-            });
-        for (auto& x : th) x.join();
-    }
+// Runs `kernel()` for every block of the grid: blocks are handed to a few host threads, each runs its block's
+// threads as fibers.  grid may be an unsigned or a dim3 (x, y).
+template <class G, class F>
+void launch_grid(G grid, unsigned nthreads, size_t smem, F&& kernel) {
+    const dim3 g = dim3(grid);
+    const unsigned total = g.x * g.y;
+    const std::function<void()> fn = kernel;
+    static const unsigned hw = [] {
+        const char* e = std::getenv("LJEMUL_THREADS");
+        const unsigned n = e ? (unsigned)std::atoi(e) : std::thread::hardware_concurrency();
+        return std::max(1u, std::min(n, 32u));
+    }();
+    const unsigned nworkers = std::min(hw, total);
+    std::atomic<unsigned> next{0};
+    auto work = [&] {
+        BlockRun r;
+        for (unsigned b = next.fetch_add(1); b < total; b = next.fetch_add(1))
+            run_block(r, nthreads, smem, uint3{b % g.x, b / g.x, 0}, g, fn);
+    };
+    if (nworkers <= 1) { work(); return; }
+    std::vector<std::thread> th;
+    for (unsigned w = 0; w < nworkers; ++w) th.emplace_back(work);
+    for (auto& x : th) x.join();
 }
+template <class F>
+void launch(unsigned nblocks, unsigned nthreads, size_t smem, F&& kernel) { launch_grid(nblocks, nthreads, smem, kernel); }
 
 }  // namespace ljemul
