@@ -74,7 +74,8 @@ def build(force=False):
     srcs = [os.path.join(PKG, "csrc", f) for f in ("lj_sim.cu", "lj_sort.cu")]
     deps = srcs + [os.path.join(PKG, "csrc", f) for f in ("lj_common.cuh", "lj_kernels.cuh", "lj_tile.cuh", "lj_pair.cuh", "lj_nccl.h")]
     deps += [os.path.join(PKG, "host", "lj_host.cpp"), os.path.join(ROOT, "include", "ljgpu.h"),
-             os.path.join(HERE, "cuda_emul.h"), os.path.join(HERE, "cuda_runtime_emul.h"), os.path.abspath(__file__)]
+             os.path.join(HERE, "cuda_emul.h"), os.path.join(HERE, "cuda_runtime_emul.h"), os.path.join(HERE, "nccl_emul.cpp"),
+             os.path.abspath(__file__)]
     if not force and os.path.exists(OUT) and all(os.path.getmtime(d) <= os.path.getmtime(OUT) for d in deps):
         return OUT
     os.makedirs(os.path.join(SCRATCH, "csrc"), exist_ok=True)
@@ -95,6 +96,9 @@ def build(force=False):
     subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-ffp-contract=off", "-c", os.path.join(PKG, "host", "lj_host.cpp"),
                     "-o", hobj], check=True, timeout=300)
     subprocess.run(["g++", "-shared", "-pthread", "-o", OUT] + objs + [hobj, "-ldl"], check=True, timeout=300)
+    # stand-in NCCL for the slab path: ranks are threads of one process (found through LD_LIBRARY_PATH by lj_nccl.h)
+    subprocess.run(["g++", "-std=c++20", "-O1", "-fPIC", "-shared", "-pthread", "-o", os.path.join(SCRATCH, "libnccl.so.2"),
+                    os.path.join(HERE, "nccl_emul.cpp")], check=True, timeout=300)
     return OUT
 
 

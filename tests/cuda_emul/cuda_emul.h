@@ -247,7 +247,7 @@ inline unsigned __double2uint_rz(double d) { return d <= 0.0 ? 0u : (d >= 429496
 inline int __double2int_rz(double d) { return (int)d; }
 template <class T> inline T __ldg(const T* p) { return *p; }
 inline long long clock64() { return std::chrono::steady_clock::now().time_since_epoch().count(); }
-inline void __nanosleep(unsigned) { if (ljemul::t_run) ljemul::yield_fiber(); }
+inline void __nanosleep(unsigned) { if (ljemul::t_run) { ++ljemul::t_run->progress; ljemul::yield_fiber(); } }   // waiting for another "device" is not a deadlock
 using std::floor;
 using std::fma;
 using std::sqrt;

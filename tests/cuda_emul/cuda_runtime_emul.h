@@ -1,7 +1,7 @@
 // cuda_runtime_emul.h - TEST INFRASTRUCTURE ONLY.  The slice of the CUDA runtime API that lj_sim.cu / lj_sort.cu
 // use, implemented on host memory with synchronous semantics (every "stream" operation completes before the
-// call returns, which is one legal in-order execution).  Graph capture and IPC report "not supported": the
-// emulated library runs with plain launches on a single "device".
+// call returns, which is one legal in-order execution).  Graph capture reports "not supported" (plain launches);
+// "devices" are ranks of one process, so an IPC handle simply carries the pointer.
 #pragma once
 #include <chrono>
 #include <cstdlib>
@@ -29,7 +29,7 @@ inline const char* cudaGetErrorString(cudaError_t e) {
     }
 }
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }
-inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
+inline cudaError_t cudaGetDeviceCount(int* n) { *n = 16; return cudaSuccess; }   // "devices" are just ranks of one process
 inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
 inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 template <class T> inline cudaError_t cudaMalloc(T** p, size_t bytes) {
@@ -66,6 +66,7 @@ inline cudaError_t cudaGraphInstantiate(cudaGraphExec_t*, cudaGraph_t, unsigned 
 inline cudaError_t cudaGraphLaunch(cudaGraphExec_t, cudaStream_t) { return cudaErrorNotSupported; }
 inline cudaError_t cudaGraphDestroy(cudaGraph_t) { return cudaSuccess; }
 inline cudaError_t cudaGraphExecDestroy(cudaGraphExec_t) { return cudaSuccess; }
-inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t*, void*) { return cudaErrorNotSupported; }
-inline cudaError_t cudaIpcOpenMemHandle(void**, cudaIpcMemHandle_t, unsigned) { return cudaErrorNotSupported; }
+// all "devices" share one address space: the handle carries the pointer itself
+inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) { std::memset(h, 0, sizeof *h); std::memcpy(h->reserved, &p, sizeof p); return cudaSuccess; }
+inline cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned) { std::memcpy(p, h.reserved, sizeof *p); return cudaSuccess; }
 inline cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }

@@ -32,3 +32,25 @@ def test_gpu_parity_suite_against_the_emulated_library():
     out = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=1500)
     assert out.returncode == 0, out.stdout[-4000:] + out.stderr[-2000:]
     assert " passed" in out.stdout and "failed" not in out.stdout
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize("world,nccl_loop", [(2, False), (4, False), (2, True)], ids=["2-peer-memory", "4-peer-memory", "2-nccl-loop"])
+def test_slab_path_on_the_emulated_library(world, nccl_loop):
+    """The multi-device path with the "devices" as threads of one process (tests/slab_emul_worker.py): halo push and
+    mailbox all-reduce over "peer memory", migration through the stand-in NCCL, pruning, re-binnings - same checks as
+    the multi-GPU worker (tests/slab_worker.py).  With four devices the lower and upper neighbour are different ranks."""
+    import build_emul_lib
+    lib = build_emul_lib.build()
+    env = dict(os.environ, LJGPU_LIBRARY=lib, LJGPU_NO_GRAPH="1",
+               LD_LIBRARY_PATH=os.path.join(HERE, "cuda_emul", "_build") + os.pathsep + os.environ.get("LD_LIBRARY_PATH", ""))
+    env.pop("LJGPU_PRUNE_SKIN", None)
+    if nccl_loop:
+        env["LJGPU_SLAB_NCCL"] = "1"
+    else:
+        env.pop("LJGPU_SLAB_NCCL", None)
+    cmd = [sys.executable, os.path.join(HERE, "slab_emul_worker.py"), str(world), "32768", "5", "80", "200", "2"]
+    out = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=1200)
+    assert out.returncode == 0 and "SLAB EMUL OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
