@@ -152,8 +152,13 @@ struct TileArgs {
 };
 
 // UNIT_SIGMA: sigma == 1 exactly (reduced units): s2 = sigma^2/d2 needs no multiply.
+// The pruning pass carries the list emission on top of the force walk and spills at the common register budget;
+// LJ_TILE_PRUNE_MINBLOCKS lets it trade occupancy for registers on its own (tuning knob, default: same budget).
+#ifndef LJ_TILE_PRUNE_MINBLOCKS
+#define LJ_TILE_PRUNE_MINBLOCKS LJ_TILE_MINBLOCKS
+#endif
 template <int MODE, bool UNIT_SIGMA>
-__global__ void __launch_bounds__(LJ_TILE_MAXTHREADS, LJ_TILE_MINBLOCKS)
+__global__ void __launch_bounds__(LJ_TILE_MAXTHREADS, MODE == 5 /* TILE_FORCE_PRUNE */ ? LJ_TILE_PRUNE_MINBLOCKS : LJ_TILE_MINBLOCKS)
 tile_kernel(LJConst c, TileGrid g, TileArgs a, int guarded) {
     LJ_DYNAMIC_SMEM(sm);                                // tile positions, one record per atom (tile_ld)
     __shared__ uint32_t s_off[kTileCellsMax + 1];
