@@ -54,3 +54,16 @@ def test_slab_path_on_the_emulated_library(world, nccl_loop):
     cmd = [sys.executable, os.path.join(HERE, "slab_emul_worker.py"), str(world), "32768", "5", "80", "200", "2"]
     out = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=1200)
     assert out.returncode == 0 and "SLAB EMUL OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
+
+
+def test_edge_cases_on_the_emulated_library():
+    """Two atoms, three cells per axis, mostly empty cells, non-unit sigma / epsilon / mass, tiny and wide shells,
+    negative tau, a large time step: all three force kernels against the oracle (tests/emul_edge_worker.py)."""
+    import build_emul_lib
+    lib = build_emul_lib.build()
+    env = dict(os.environ, LJGPU_LIBRARY=lib, LJGPU_NO_GRAPH="1")
+    for k in ("LJGPU_PRUNE_SKIN", "LJGPU_PAIRLIST", "LJGPU_BRICK"):
+        env.pop(k, None)
+    out = subprocess.run([sys.executable, os.path.join(HERE, "emul_edge_worker.py")], cwd=ROOT, env=env,
+                         capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0 and "EDGE CASES OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
