@@ -269,7 +269,8 @@ def main():
     # step (12 bytes of arguments in), energies read back, and this step's positions delivered into one of two pinned
     # host buffer sets (the reference's double buffer); the delivery of step k overlaps the computation of step k+1 and
     # the last one is waited for inside the timed region.
-    pinned = [[torch.empty(n, dtype=torch.float64, pin_memory=True) for _ in range(3)] for _ in range(2)]
+    blocks = [torch.empty(3 * n, dtype=torch.float64, pin_memory=True) for _ in range(2)]     # x | y | z, one block each
+    pinned = [[blk[k * n:(k + 1) * n] for k in range(3)] for blk in blocks]
     ptrs = [[p.data_ptr() for p in set_] for set_ in pinned]
     for _ in range(4):
         sim.integrate_publish(step, DT, *ptrs[step & 1]); step += 1

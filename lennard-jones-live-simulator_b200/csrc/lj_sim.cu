@@ -1162,9 +1162,13 @@ void ljgpu_sim::step_publish(unsigned step, double dt, double* x, double* y, dou
     check_launch("export");
     CK(cudaEventRecord(ev_pub_ready[b], st));
     CK(cudaStreamWaitEvent(st_copy, ev_pub_ready[b], 0));
-    CK(cudaMemcpyAsync(x, o, N * 8, cudaMemcpyDeviceToHost, st_copy));
-    CK(cudaMemcpyAsync(y, o + N, N * 8, cudaMemcpyDeviceToHost, st_copy));
-    CK(cudaMemcpyAsync(z, o + 2 * N, N * 8, cudaMemcpyDeviceToHost, st_copy));
+    if (y == x + N && z == y + N) {                          // one block on the host too (the adapter's mirror): one transfer
+        CK(cudaMemcpyAsync(x, o, 3 * N * 8, cudaMemcpyDeviceToHost, st_copy));
+    } else {
+        CK(cudaMemcpyAsync(x, o, N * 8, cudaMemcpyDeviceToHost, st_copy));
+        CK(cudaMemcpyAsync(y, o + N, N * 8, cudaMemcpyDeviceToHost, st_copy));
+        CK(cudaMemcpyAsync(z, o + 2 * N, N * 8, cudaMemcpyDeviceToHost, st_copy));
+    }
     CK(cudaEventRecord(ev_pub_done[b], st_copy));
     if (pub_pending) CK(cudaEventSynchronize(ev_pub_done[pub_cur]));
     pub_cur = b; pub_pending = true; pub_step = step;

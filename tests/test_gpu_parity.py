@@ -211,6 +211,19 @@ def test_step_publish_delivers_every_step(lj, n_atoms, kernel):
     a = lj.LennardJonesSimulation(params, st, force_kernel=kernel)
     b = lj.LennardJonesSimulation(params, st, force_kernel=kernel)
     bufs = [[lj.HostBuffer(n_atoms) for _ in range(3)] for _ in range(2)]       # two pinned x/y/z sets
+    if kernel == 3:                                                             # ... one of them a single x|y|z block
+        class Part:
+            def __init__(self, block, k):
+                self.block, self.ptr, self.array = block, block.ptr + 8 * n_atoms * k, block.array[n_atoms * k:n_atoms * (k + 1)]
+
+            def close(self):
+                if self.block is not None and self.ptr == self.block.ptr:
+                    self.block.close()
+                self.block = None
+        for h in bufs[1]:
+            h.close()
+        whole = lj.HostBuffer(3 * n_atoms)
+        bufs[1] = [Part(whole, k) for k in range(3)]
     expected = []
     steps = 45 if kernel == 3 else 8                                            # across a re-binning on the list path
     for s in range(1, steps + 1):
