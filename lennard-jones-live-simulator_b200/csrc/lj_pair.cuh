@@ -85,6 +85,63 @@ pair_table_kernel(TileGrid g, const uint32_t* __restrict__ cstart, const uint32_
     }
 }
 
+// Re-binning, before the state is permuted: one warp per cell re-orders the cell's atoms (the entries of `vals` in
+// the cell's segment of the sorted order) into a nearest-neighbour chain - first atom, then the unplaced atom nearest
+// to it, then the one nearest to that, ... - so that the two consecutive atoms a thread owns are about one sigma
+// apart and their lists overlap as much as possible (oracle liquid state: union 1.36x instead of 1.48x one list).
+// Deterministic (ties broken by lane); cells with more than 64 atoms keep their order.
+__global__ void __launch_bounds__(128)
+pair_order_kernel(unsigned ncell, const uint32_t* __restrict__ cstart, const uint32_t* __restrict__ cend,
+                  const double4* __restrict__ pos_tmp, uint32_t* __restrict__ vals) {
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned cell = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (cell >= ncell) return;
+    const unsigned c0 = cstart[cell], cnt = cend[cell] - c0;
+    if (cnt < 3 || cnt > 64) return;
+    unsigned idx[2] = {0u, 0u};
+    double px[2], py[2], pz[2];
+    bool free_[2];
+    unsigned rank[2] = {0u, 0u};
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const unsigned k = lane + 32u * h;
+        free_[h] = k < cnt;
+        px[h] = py[h] = pz[h] = 0.0;
+        if (free_[h]) {
+            idx[h] = vals[c0 + k];
+            const double4 p = ld_pos(pos_tmp + idx[h]);
+            px[h] = p.x; py[h] = p.y; pz[h] = p.z;
+        }
+    }
+    // the chain starts at the cell's first atom
+    double cx = __shfl_sync(0xffffffffu, px[0], 0), cy = __shfl_sync(0xffffffffu, py[0], 0), cz = __shfl_sync(0xffffffffu, pz[0], 0);
+    if (lane == 0) { free_[0] = false; rank[0] = 0; }
+    for (unsigned placed = 1; placed < cnt; ++placed) {
+        double best = 1.0e300;
+        unsigned who = 0xffffffffu;                                   // lane + 32 * h of my best candidate
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+            if (free_[h]) {
+                const double dx = px[h] - cx, dy = py[h] - cy, dz = pz[h] - cz;
+                const double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
+                if (d2 < best) { best = d2; who = lane + 32u * (unsigned)h; }
+            }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const unsigned ow = __shfl_xor_sync(0xffffffffu, who, o);
+            if (ob < best || (ob == best && ow < who)) { best = ob; who = ow; }
+        }
+        const unsigned wl = who & 31u, wh = who >> 5;
+        const double sx = wh ? px[1] : px[0], sy = wh ? py[1] : py[0], sz = wh ? pz[1] : pz[0];
+        cx = __shfl_sync(0xffffffffu, sx, (int)wl); cy = __shfl_sync(0xffffffffu, sy, (int)wl); cz = __shfl_sync(0xffffffffu, sz, (int)wl);
+        if (lane == wl) { free_[wh] = false; rank[wh] = placed; }
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+        if (lane + 32u * h < cnt) vals[c0 + rank[h]] = idx[h];
+}
+
 struct PairArgs {
     const double4* __restrict__ pos;
     uint32_t* __restrict__ nl32;           // union lists, one row set per (block, thread) slot

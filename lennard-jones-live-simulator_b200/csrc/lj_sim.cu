@@ -150,7 +150,7 @@ struct ljgpu_sim {
     // pruned inner list (single-device Verlet path)
     uint32_t* nl_in = nullptr; uint32_t* nl_in_count = nullptr;
     // EXPERIMENTAL pair path (lj_pair.cuh, LJGPU_PAIRLIST=1): one thread per two home atoms, union lists per slot
-    bool pairlist = false;
+    bool pairlist = false, pair_order = true;          // pair_order: LJGPU_PAIR_ORDER=0 keeps the sorted order inside cells
     unsigned pbx = 0, pby = 0, pbz = 0, pnbx = 0, pnby = 0, pnbz = 0, pnblocks = 0, ptcap = 0, pthreads = 32, pslots = 32, pcapq = 0;
     uint32_t *ptsrc = nullptr, *ptoff = nullptr, *pl = nullptr, *pl_in = nullptr, *pl_count = nullptr, *pl_in_count = nullptr;
     size_t pl_alloc = 0, pslots_alloc = 0;
@@ -433,6 +433,7 @@ void ljgpu_sim::allocate() {
             if (pnblocks < 2u * 148u) pairlist = false;            // fewer bricks than one wave of CTAs: stay on the per-atom path
         }
         if (pairlist) {
+            if (const char* e = std::getenv("LJGPU_PAIR_ORDER")) pair_order = std::atoi(e) != 0;
             CK(cudaMalloc(&ptsrc, (size_t)pnblocks * kPairCellsMax * 4));
             CK(cudaMalloc(&ptoff, (size_t)pnblocks * (kPairCellsMax + 1) * 4));
         }
@@ -523,18 +524,22 @@ void ljgpu_sim::sort_by_cell() {
     check_launch("wrap_key");
     int bits = 1; while ((1ull << bits) < (unsigned long long)ncell) ++bits;
     launches += radix_sort_pairs(keys, vals, n, bits, scr, st);
-    permute_kernel<<<nb_atoms(), kBlock, 0, st>>>(n, vals, pos_tmp, pos,
-                                                  v[0], v[1], v[2], f[0], f[1], f[2], orig,
-                                                  v_alt[0], v_alt[1], v_alt[2], f_alt[0], f_alt[1], f_alt[2], orig_alt);
-    check_launch("permute");
-    for (int k = 0; k < 3; ++k) { std::swap(v[k], v_alt[k]); std::swap(f[k], f_alt[k]); }
-    std::swap(orig, orig_alt);
     CK(cudaMemsetAsync(cstart, 0, (size_t)ncell * 4, st));
     CK(cudaMemsetAsync(cend, 0, (size_t)ncell * 4, st));
     if (n) {
         cell_bounds_kernel<<<nb_atoms(), kBlock, 0, st>>>(n, keys, cstart, cend);
         check_launch("cell_bounds");
     }
+    if (pairlist && pair_order && n) {      // experimental pair path: neighbours in space become neighbours in memory
+        pair_order_kernel<<<cdiv(ncell, 4), 128, 0, st>>>(ncell, cstart, cend, pos_tmp, vals);
+        check_launch("pair_order");
+    }
+    permute_kernel<<<nb_atoms(), kBlock, 0, st>>>(n, vals, pos_tmp, pos,
+                                                  v[0], v[1], v[2], f[0], f[1], f[2], orig,
+                                                  v_alt[0], v_alt[1], v_alt[2], f_alt[0], f_alt[1], f_alt[2], orig_alt);
+    check_launch("permute");
+    for (int k = 0; k < 3; ++k) { std::swap(v[k], v_alt[k]); std::swap(f[k], f_alt[k]); }
+    std::swap(orig, orig_alt);
     cell_count_kernel<<<cdiv(ncell, kBlock), kBlock, 0, st>>>(ncell, cstart, cend, ccount);
     check_launch("cell_count");
 }
@@ -837,6 +842,7 @@ void ljgpu_sim::pair_tables() {
     if (slots > pslots_alloc) {
         dfree(pl_count); dfree(pl_in_count);
         CK(cudaMalloc(&pl_count, slots * 4)); CK(cudaMalloc(&pl_in_count, slots * 4));
+        CK(cudaMemset(pl_count, 0, slots * 4)); CK(cudaMemset(pl_in_count, 0, slots * 4));
         pslots_alloc = slots;
         pl_alloc = 0;                                    // slot numbering changed: lists are re-sized below
         ++graph_gen;
@@ -864,7 +870,21 @@ void ljgpu_sim::pair_build_list() {
         }
         launch_pair<TILE_LIST_FILL>(this, 0);
         fetch_ctrl();
-        if (!h_ctrl->overflow) return;
+        if (!h_ctrl->overflow) {
+            static const bool trace = std::getenv("LJGPU_TRACE_REBUILD") != nullptr;
+            if (trace) {            // union size per thread against the per-atom list lengths
+                std::vector<uint32_t> hc((size_t)pnblocks * pslots), ha(n);
+                CK(cudaMemcpy(hc.data(), pl_count, hc.size() * 4, cudaMemcpyDeviceToHost));
+                CK(cudaMemcpy(ha.data(), nl_count, (size_t)n * 4, cudaMemcpyDeviceToHost));
+                unsigned long long tu = 0, ta = 0, used = 0;
+                for (unsigned b = 0; b < pnblocks; ++b)
+                    for (unsigned t = 0; t < pslots; ++t) { const uint32_t v = hc[(size_t)b * pslots + t]; if (v && v != 0xffffffffu && v <= 8 * pcapq) { tu += v; ++used; } }
+                for (uint32_t v : ha) ta += v;
+                std::fprintf(stderr, "[ljgpu pair list] threads with a list %llu, union entries %.2f per thread, per-atom entries %.2f, gathers vs per-atom walk %.3f, capq %u\n",
+                             used, (double)tu / (double)std::max(1ull, used), (double)ta / (double)n, (double)tu / (double)std::max(1ull, ta), pcapq);
+            }
+            return;
+        }
         pcapq = (h_ctrl->max_count + 16 + 7) / 8;
     }
     throw LjError(LJGPU_ESTATE, "pair list capacity did not converge");
