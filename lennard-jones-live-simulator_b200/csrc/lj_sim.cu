@@ -530,7 +530,8 @@ void ljgpu_sim::sort_by_cell() {
         cell_bounds_kernel<<<nb_atoms(), kBlock, 0, st>>>(n, keys, cstart, cend);
         check_launch("cell_bounds");
     }
-    if (pairlist && pair_order && n) {      // experimental pair path: neighbours in space become neighbours in memory
+    static const bool cell_order = std::getenv("LJGPU_CELL_ORDER") != nullptr;   // tuning knob: the same ordering on the per-atom path
+    if (((pairlist && pair_order) || (cell_order && !slab.on)) && n) {      // neighbours in space become neighbours in memory
         pair_order_kernel<<<cdiv(ncell, 4), 128, 0, st>>>(ncell, cstart, cend, pos_tmp, vals);
         check_launch("pair_order");
     }
