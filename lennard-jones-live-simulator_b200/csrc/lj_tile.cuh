@@ -52,6 +52,9 @@ __device__ __forceinline__ void tile_ld(const double* sm, unsigned j, double& x,
     x = xy.x; y = xy.y;
 #else
     const double* p = sm + 3 * (size_t)j;
+#ifdef LJ_EMUL
+    ljemul::lds_note(p);                   // conflict profile of the x loads (y and z behave alike: same stride)
+#endif
     x = p[0]; y = p[1]; z = p[2];
 #endif
 }

@@ -74,7 +74,7 @@ def build(force=False):
     srcs = [os.path.join(PKG, "csrc", f) for f in ("lj_sim.cu", "lj_sort.cu")]
     deps = srcs + [os.path.join(PKG, "csrc", f) for f in ("lj_common.cuh", "lj_kernels.cuh", "lj_tile.cuh", "lj_pair.cuh", "lj_nccl.h")]
     deps += [os.path.join(PKG, "host", "lj_host.cpp"), os.path.join(ROOT, "include", "ljgpu.h"),
-             os.path.join(HERE, "cuda_emul.h"), os.path.join(HERE, "cuda_runtime_emul.h"), os.path.join(HERE, "nccl_emul.cpp"),
+             os.path.join(HERE, "cuda_emul.h"), os.path.join(HERE, "cuda_runtime_emul.h"), os.path.join(HERE, "nccl_emul.cpp"), os.path.join(HERE, "emul_api.cpp"),
              os.path.abspath(__file__)]
     if not force and os.path.exists(OUT) and all(os.path.getmtime(d) <= os.path.getmtime(OUT) for d in deps):
         return OUT
@@ -92,6 +92,10 @@ def build(force=False):
                         "-include", os.path.join(HERE, "include", "cuda_runtime.h"), "-c", dst, "-o", obj],
                        check=True, timeout=600)
         objs.append(obj)
+    aobj = os.path.join(SCRATCH, "emul_api.o")
+    subprocess.run(["g++", "-std=c++20", "-O1", "-fPIC", "-pthread", "-DLJ_EMUL", "-c", os.path.join(HERE, "emul_api.cpp"), "-o", aobj],
+                   check=True, timeout=300)
+    objs.append(aobj)
     hobj = os.path.join(SCRATCH, "lj_host.o")
     subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-ffp-contract=off", "-c", os.path.join(PKG, "host", "lj_host.cpp"),
                     "-o", hobj], check=True, timeout=300)

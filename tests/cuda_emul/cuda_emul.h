@@ -85,14 +85,30 @@ struct BlockRun {
     Fiber* cur = nullptr;
     const std::function<void()>* kernel = nullptr;
     unsigned long long progress = 0;
+    // optional shared-memory gather profile (LJEMUL_LDS_PROFILE=1): byte offsets of the k-th profiled load of every lane
+    std::vector<std::vector<uint32_t>> lds_addr;          // per warp: [call][lane], 0xffffffff = lane made no such call
+    std::vector<unsigned> lds_calls;                      // per thread: profiled loads so far
     ~BlockRun() { if (stacks) munmap(stacks, stacks_bytes); }
 };
+struct LdsProfile {
+    std::atomic<unsigned long long> instr{0}, wavefronts{0}, lanes{0};
+    bool on = std::getenv("LJEMUL_LDS_PROFILE") != nullptr;
+    ~LdsProfile() {
+        if (on && instr.load())
+            std::fprintf(stderr, "[ljemul lds] 64-bit gathers: %llu warp instructions, %.2f active lanes, %.3f wavefronts per instruction "
+                                 "(conflict-free: 2 for a full warp)\n", instr.load(), (double)lanes.load() / (double)instr.load(),
+                         (double)wavefronts.load() / (double)instr.load());
+    }
+};
+inline LdsProfile g_lds;
 inline thread_local BlockRun* t_run = nullptr;
 inline thread_local unsigned t_tid = 0;
 
 inline void* dynamic_smem() { return t_run->dyn; }
 inline unsigned smem_offset(const void* p) { return (unsigned)(static_cast<const char*>(p) - t_run->dyn); }
 inline void smem_copy(unsigned off, const void* g, unsigned bytes) { std::memcpy(t_run->dyn + off, g, bytes); }
+// Called by tile_ld for every 64-bit shared-memory load of a gathered record (three per record).
+inline void lds_note(const void* p);
 inline double rcp_seed(double a) { return (double)(1.0f / (float)a); }        // ~2^-23 relative error, like MUFU.RCP64H
 inline unsigned long long atomic_load_u64(const unsigned long long* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
 inline void atomic_store_u64(unsigned long long* p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
@@ -101,6 +117,40 @@ inline double atomic_load_f64(const double* p) {
     double d; std::memcpy(&d, &b, 8); return d;
 }
 
+inline void lds_note(const void* p) {
+    if (!g_lds.on) return;
+    BlockRun& r = *t_run;
+    if (r.lds_calls.size() < r.nthreads) { r.lds_calls.assign(r.nthreads, 0); r.lds_addr.assign((r.nthreads + 31) / 32, {}); }
+    const unsigned k = r.lds_calls[t_tid]++;
+    auto& tab = r.lds_addr[t_tid >> 5];
+    if (tab.size() < (size_t)(k + 1) * 32) tab.resize((size_t)(k + 1) * 32, 0xffffffffu);
+    tab[(size_t)k * 32 + (t_tid & 31u)] = (uint32_t)(static_cast<const char*>(p) - r.dyn);
+}
+inline void lds_flush(BlockRun& r) {               // end of a block: conflict degree of every profiled warp instruction
+    if (!g_lds.on) return;
+    unsigned long long ni = 0, nw = 0, nl = 0;
+    for (auto& tab : r.lds_addr)
+        for (size_t k = 0; k + 32 <= tab.size(); k += 32) {
+            unsigned wf = 0, lanes = 0;
+            for (int half = 0; half < 2; ++half) {
+                uint32_t seen[16][16]; unsigned cnt[16] = {};
+                unsigned mx = 0;
+                for (int l = 0; l < 16; ++l) {
+                    const uint32_t a = tab[k + 16 * half + l];
+                    if (a == 0xffffffffu) continue;
+                    ++lanes;
+                    const unsigned bank = (a >> 3) & 15u;
+                    bool dup = false;
+                    for (unsigned q = 0; q < cnt[bank]; ++q) dup = dup || seen[bank][q] == a;
+                    if (!dup) { seen[bank][cnt[bank]++] = a; mx = std::max(mx, cnt[bank]); }
+                }
+                wf += mx;
+            }
+            if (lanes) { ++ni; nw += wf; nl += lanes; }
+        }
+    g_lds.instr += ni; g_lds.wavefronts += nw; g_lds.lanes += nl;
+    r.lds_addr.clear(); r.lds_calls.clear();
+}
 inline void yield_fiber() {
     BlockRun& r = *t_run;
     Fiber* me = r.cur;
@@ -189,6 +239,7 @@ inline void run_block(BlockRun& r, unsigned nthreads, size_t smem, uint3 bidx, d
             ljemul_switch(&r.sched_sp, f.sp);
         }
     }
+    lds_flush(r);
     t_run = nullptr;
 }
 
