@@ -142,6 +142,70 @@ pair_order_kernel(unsigned ncell, const uint32_t* __restrict__ cstart, const uin
         if (lane + 32u * h < cnt) vals[c0 + rank[h]] = idx[h];
 }
 
+// Re-binning, after the tile tables: per brick, rank the pairs by the squared distance between their two atoms
+// (a lone atom counts as distance zero: the shortest list) with a bitonic sort in shared memory; ties by pair
+// number.  rank2pair / pair2rank are per-brick tables of pslots entries.
+constexpr int kPairMapMax = 512;
+__global__ void __launch_bounds__(256)
+pair_map_kernel(TileGrid g, const double4* __restrict__ pos, unsigned pslots,
+                unsigned short* __restrict__ rank2pair, unsigned short* __restrict__ pair2rank) {
+    __shared__ unsigned long long key[kPairMapMax];          // (float bits of d2) << 32 | pair number
+    __shared__ uint32_t s_row_src[kPairHomeRows], s_row_cnt[kPairHomeRows], s_pstart[kPairHomeRows + 1];
+    const unsigned b = blockIdx.x;
+    const TileGeom tg = tile_geometry(b, g);
+    const uint32_t* off = g.toff + (size_t)b * (kPairCellsMax + 1);
+    const uint32_t* src = g.tsrc + (size_t)b * kPairCellsMax;
+    if (threadIdx.x == 0) {
+        unsigned run = 0, q = 0;
+        for (unsigned hz = 1; hz <= tg.bd; ++hz)
+            for (unsigned hy = 1; hy <= tg.bh; ++hy) {
+                const unsigned r = (hz * tg.H + hy) * tg.W;
+                s_row_src[q] = src[r + 1];
+                s_row_cnt[q] = off[r + 1 + tg.bw] - off[r + 1];
+                s_pstart[q++] = run;
+                run += (s_row_cnt[q - 1] + 1u) >> 1;
+            }
+        for (; q <= kPairHomeRows; ++q) s_pstart[q] = run;
+    }
+    __syncthreads();
+    const unsigned np = s_pstart[kPairHomeRows];
+    for (unsigned t = threadIdx.x; t < kPairMapMax; t += blockDim.x) {
+        unsigned long long k = ~0ull;                        // padding sorts to the end
+        if (t < np) {
+            unsigned q = 0;
+#pragma unroll
+            for (int j = 1; j < kPairHomeRows; ++j) q += (s_pstart[j] <= t) ? 1u : 0u;
+            const unsigned pl = t - s_pstart[q];
+            float d2 = 0.0f;
+            if (2u * pl + 1u < s_row_cnt[q]) {
+                const double4 p1 = ld_pos(pos + s_row_src[q] + 2u * pl), p2 = ld_pos(pos + s_row_src[q] + 2u * pl + 1u);
+                const double dx = p1.x - p2.x, dy = p1.y - p2.y, dz = p1.z - p2.z;
+                d2 = (float)(dx * dx + dy * dy + dz * dz);
+            }
+            k = ((unsigned long long)(unsigned)__float_as_int(d2) << 32) | t;     // d2 >= 0: float bits order like the value
+        }
+        key[t] = k;
+    }
+    __syncthreads();
+    for (unsigned size = 2; size <= (unsigned)kPairMapMax; size <<= 1)
+        for (unsigned stride = size >> 1; stride > 0; stride >>= 1) {
+            for (unsigned t = threadIdx.x; t < (unsigned)kPairMapMax; t += blockDim.x) {
+                const unsigned partner = t ^ stride;
+                if (partner > t) {
+                    const bool up = (t & size) == 0;
+                    const unsigned long long x = key[t], y = key[partner];
+                    if ((x > y) == up) { key[t] = y; key[partner] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    for (unsigned t = threadIdx.x; t < np; t += blockDim.x) {
+        const unsigned pair = (unsigned)(key[t] & 0xffffffffull);
+        rank2pair[(size_t)b * pslots + t] = (unsigned short)pair;
+        pair2rank[(size_t)b * pslots + pair] = (unsigned short)t;
+    }
+}
+
 struct PairArgs {
     const double4* __restrict__ pos;
     uint32_t* __restrict__ nl32;           // union lists, one row set per (block, thread) slot
@@ -154,6 +218,12 @@ struct PairArgs {
     StepCtrl* ctrl;
     unsigned capq;                         // list capacity in quads per slot
     unsigned pslots;                       // slots per block (>= pairs of the fullest brick, multiple of 32)
+    // lane balance (pair_map_kernel): the force passes give thread t the pair rank2pair[t] - pairs sorted by the
+    // distance between their two atoms, i.e. by union length, so that the lanes of a warp finish together - and
+    // keep list slot t (coalesced rows); the list build runs in natural order (lanes of a warp share their
+    // candidates: broadcast loads) and writes pair p's list to slot pair2rank[p].  Null: identity.
+    const unsigned short* __restrict__ rank2pair;
+    const unsigned short* __restrict__ pair2rank;
 };
 
 template <int MODE, bool UNIT_SIGMA>
@@ -233,19 +303,22 @@ pair_kernel(LJConst c, TileGrid g, PairArgs a, int guarded) {
     double etot = 0.0;
     unsigned maxcnt = 0;
 
+    constexpr bool kForcePass = MODE == TILE_FORCE_LIST || MODE == TILE_FORCE_PRUNE;
     for (unsigned t = threadIdx.x; t < np; t += blockDim.x) {
+        // pt: the pair (natural numbering: home rows, two consecutive atoms each); slot: where its list lives
+        const unsigned pt = (kForcePass && a.rank2pair) ? a.rank2pair[(size_t)b * a.pslots + t] : t;
+        const unsigned slot = b * a.pslots + ((!kForcePass && a.pair2rank) ? a.pair2rank[(size_t)b * a.pslots + t] : t);
         unsigned q = 0;
 #pragma unroll
-        for (int k = 1; k < kPairHomeRows; ++k) q += (s_pstart[k] <= t) ? 1u : 0u;
+        for (int k = 1; k < kPairHomeRows; ++k) q += (s_pstart[k] <= pt) ? 1u : 0u;
         const unsigned hy = 1 + q % tg.bh, hz = 1 + q / tg.bh;
         const unsigned rbase = (hz * H + hy) * W;
-        const unsigned pl = t - s_pstart[q];
+        const unsigned pl = pt - s_pstart[q];
         const unsigned rs = s_off[rbase + 1], rcnt = s_off[rbase + 1 + tg.bw] - rs;
         const unsigned li1 = rs + 2u * pl;
         const bool has2 = 2u * pl + 1u < rcnt;
         const unsigned li2 = has2 ? li1 + 1u : li1;
         const unsigned i1 = s_src[rbase + 1] + 2u * pl, i2 = i1 + 1u;
-        const unsigned slot = b * a.pslots + t;
         const size_t rowq = ((size_t)(slot >> 5) * a.capq) * 32 + (slot & 31u);      // first quad of the slot
         double p1x, p1y, p1z, p2x, p2y, p2z;
         tile_ld(sm, li1, p1x, p1y, p1z);

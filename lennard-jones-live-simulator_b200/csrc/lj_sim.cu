@@ -153,6 +153,8 @@ struct ljgpu_sim {
     bool pairlist = false, pair_order = true;          // pair_order: LJGPU_PAIR_ORDER=0 keeps the sorted order inside cells
     unsigned pbx = 0, pby = 0, pbz = 0, pnbx = 0, pnby = 0, pnbz = 0, pnblocks = 0, ptcap = 0, pthreads = 32, pslots = 32, pcapq = 0;
     uint32_t *ptsrc = nullptr, *ptoff = nullptr, *pl = nullptr, *pl_in = nullptr, *pl_count = nullptr, *pl_in_count = nullptr;
+    unsigned short *prank2pair = nullptr, *ppair2rank = nullptr;     // lane balance of the force passes (pair_map_kernel)
+    bool pair_balance = true;                                          // LJGPU_PAIR_BALANCE=0: threads take pairs in natural order
     size_t pl_alloc = 0, pslots_alloc = 0;
     TileGrid pair_grid() const {
         return TileGrid{nc, ncz, 1u, 0u, nc, pbx, pby, pbz, pnbx, pnby, pnbz, pnblocks, ptsrc, ptoff};
@@ -307,7 +309,7 @@ ljgpu_sim::~ljgpu_sim() {
     dfree(orig); dfree(orig_alt); dfree(keys); dfree(vals);
     dfree(cstart); dfree(cend); dfree(ccount);
     dfree(nl); dfree(nl_count); dfree(nl_in); dfree(nl_in_count); dfree(tsrc); dfree(toff);
-    dfree(ptsrc); dfree(ptoff); dfree(pl); dfree(pl_in); dfree(pl_count); dfree(pl_in_count);
+    dfree(ptsrc); dfree(ptoff); dfree(pl); dfree(pl_in); dfree(pl_count); dfree(pl_in_count); dfree(prank2pair); dfree(ppair2rank);
     dfree(partial_epot); dfree(partial_ekin); dfree(partial_pred);
     dfree(ctrl); dfree(hist); dfree(out3); dfree(out_u32); dfree(hist_counts);
     if (st_copy) { cudaStreamSynchronize(st_copy); cudaStreamDestroy(st_copy); }
@@ -434,6 +436,7 @@ void ljgpu_sim::allocate() {
         }
         if (pairlist) {
             if (const char* e = std::getenv("LJGPU_PAIR_ORDER")) pair_order = std::atoi(e) != 0;
+            if (const char* e = std::getenv("LJGPU_PAIR_BALANCE")) pair_balance = std::atoi(e) != 0;
             CK(cudaMalloc(&ptsrc, (size_t)pnblocks * kPairCellsMax * 4));
             CK(cudaMalloc(&ptoff, (size_t)pnblocks * (kPairCellsMax + 1) * 4));
         }
@@ -806,7 +809,8 @@ template <int MODE, bool UNIT_SIGMA>
 static void launch_pair2(ljgpu_sim* s, int guarded) {
     const size_t smem = (size_t)s->ptcap * kTileRecBytes;
     PairArgs a{s->pos, s->pl, s->pl_count, s->prune_skin > 0.0 ? s->pl_in : nullptr, s->pl_in_count, s->nl_count,
-               s->f[0], s->f[1], s->f[2], s->partial_epot, s->ctrl, s->pcapq, s->pslots};
+               s->f[0], s->f[1], s->f[2], s->partial_epot, s->ctrl, s->pcapq, s->pslots,
+               s->pair_balance ? s->prank2pair : nullptr, s->pair_balance ? s->ppair2rank : nullptr};
     pair_kernel<MODE, UNIT_SIGMA><<<s->pnblocks, s->pthreads, smem, s->st>>>(s->c, s->pair_grid(), a, guarded);
     s->check_launch("pair_kernel");
 }
@@ -844,9 +848,16 @@ void ljgpu_sim::pair_tables() {
         dfree(pl_count); dfree(pl_in_count);
         CK(cudaMalloc(&pl_count, slots * 4)); CK(cudaMalloc(&pl_in_count, slots * 4));
         CK(cudaMemset(pl_count, 0, slots * 4)); CK(cudaMemset(pl_in_count, 0, slots * 4));
+        dfree(prank2pair); dfree(ppair2rank);
+        CK(cudaMalloc(&prank2pair, slots * 2)); CK(cudaMalloc(&ppair2rank, slots * 2));
         pslots_alloc = slots;
         pl_alloc = 0;                                    // slot numbering changed: lists are re-sized below
         ++graph_gen;
+    }
+    if (pair_balance) {
+        if (pslots > (unsigned)kPairMapMax) throw LjError(LJGPU_ESTATE, "more pairs in a brick than the lane-balance sort holds");
+        pair_map_kernel<<<pnblocks, 256, 0, st>>>(pair_grid(), pos, pslots, prank2pair, ppair2rank);
+        check_launch("pair_map");
     }
 }
 
@@ -1037,7 +1048,7 @@ ljgpu_sim::GraphKey ljgpu_sim::graph_key(bool prune_now, double dt) const {
     GraphKey k;
     std::memset(&k, 0, sizeof k);                      // padding included: keys are compared bytewise
     const void* ptrs[20] = {pos, v[0], v[1], v[2], f[0], f[1], f[2], dij[0], dij[1], dij[2],
-                            nl, nl_in, nl_count, nl_in_count, tsrc, toff, pl, pl_in, pl_count, pl_in_count};
+                            nl, nl_in, nl_count, nl_in_count, tsrc, toff, pl, pl_in, pl_count, prank2pair};
     std::memcpy(k.ptr, ptrs, sizeof ptrs);
     k.shape[0] = n; k.shape[1] = tile_threads; k.shape[2] = tcap; k.shape[3] = capq; k.shape[4] = nblocks_tile; k.shape[5] = nb_force;
     k.shape[6] = pthreads; k.shape[7] = ptcap; k.shape[8] = pcapq; k.shape[9] = pslots;

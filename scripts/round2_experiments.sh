@@ -25,6 +25,7 @@ run)
     probe "per-atom path, atoms inside a cell ordered as a nearest-neighbour chain" LJGPU_CELL_ORDER=1
     probe "pair path (2 entries x 2 atoms, 2 CTAs/SM, 120 regs)" LJGPU_PAIRLIST=1
     probe "pair path without the chain ordering" LJGPU_PAIRLIST=1 LJGPU_PAIR_ORDER=0
+    probe "pair path without the lane balance" LJGPU_PAIRLIST=1 LJGPU_PAIR_BALANCE=0
     probe "pair path, 1 entry x 2 atoms, 3 CTAs/SM" LJGPU_PAIRLIST=1 LJGPU_LIBRARY=$PWD/$V/libljgpu_pair_g1b3.so
     probe "pair path, 2 entries x 2 atoms, 3 CTAs/SM (spills)" LJGPU_PAIRLIST=1 LJGPU_LIBRARY=$PWD/$V/libljgpu_pair_g2b3.so
     probe "pair path, bricks 5x2x2" LJGPU_PAIRLIST=1 LJGPU_LIBRARY=$PWD/$V/libljgpu_pair_bx5.so

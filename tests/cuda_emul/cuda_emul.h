@@ -292,6 +292,7 @@ inline double __hiloint2double(int hi, int lo) {
     const unsigned long long b = ((unsigned long long)(unsigned)hi << 32) | (unsigned)lo;
     double d; std::memcpy(&d, &b, 8); return d;
 }
+inline int __float_as_int(float f) { int v; std::memcpy(&v, &f, 4); return v; }
 inline double __longlong_as_double(long long v) { double d; std::memcpy(&d, &v, 8); return d; }
 inline long long __double_as_longlong(double d) { long long v; std::memcpy(&v, &d, 8); return v; }
 inline unsigned __double2uint_rz(double d) { return d <= 0.0 ? 0u : (d >= 4294967295.0 ? 4294967295u : (unsigned)d); }

@@ -97,6 +97,13 @@ extern "C" int ljemul_forces(int which, unsigned n, double L, double rcut, doubl
     std::vector<uint32_t> slot_count(ntiles * 32, 0), slot_in_count(ntiles * 32, 0);
     out_info[0] = nblocks; out_info[1] = ctrl.max_tile; out_info[2] = ctrl.max_home; out_info[3] = threads;
 
+    // pair kernels: lane balance tables (LJEMUL_PAIR_BALANCE=0 switches them off)
+    const bool balance = which == 1 && !(std::getenv("LJEMUL_PAIR_BALANCE") && std::atoi(std::getenv("LJEMUL_PAIR_BALANCE")) == 0);
+    std::vector<unsigned short> rank2pair(ntiles * 32, 0), pair2rank(ntiles * 32, 0);
+    if (balance) {
+        if (slots_per_block > (unsigned)kPairMapMax) return -6;
+        ljemul::launch(nblocks, 256, 0, [&] { pair_map_kernel(g, p.pos.data(), slots_per_block, rank2pair.data(), pair2rank.data()); });
+    }
     auto run = [&](int mode, uint32_t* nl, uint32_t* nl_in, unsigned capq) {
         if (which == 0) {
             TileArgs a{p.pos.data(), nl, slot_count.data(), nl_in, slot_in_count.data(), f[0].data(), f[1].data(), f[2].data(),
@@ -111,7 +118,8 @@ extern "C" int ljemul_forces(int which, unsigned n, double L, double rcut, doubl
             });
         } else {
             PairArgs a{p.pos.data(), nl, slot_count.data(), nl_in, slot_in_count.data(), atom_count.data(),
-                       f[0].data(), f[1].data(), f[2].data(), partial.data(), &ctrl, capq, slots_per_block};
+                       f[0].data(), f[1].data(), f[2].data(), partial.data(), &ctrl, capq, slots_per_block,
+                       balance ? rank2pair.data() : nullptr, balance ? pair2rank.data() : nullptr};
             ljemul::launch(nblocks, threads, smem, [&] {
                 switch (mode) {
                     case TILE_LIST_COUNT:  pair_kernel<TILE_LIST_COUNT, false>(p.c, g, a, 0); break;
