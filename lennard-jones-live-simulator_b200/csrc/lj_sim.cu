@@ -205,6 +205,7 @@ struct ljgpu_sim {
     unsigned prof_every = 1;        // profile every k-th step (the others replay the CUDA graph); stage times are scaled by k
     unsigned prof_tick = 0;
     bool prof_this_step = true;
+    bool in_rebuild = false;
     struct Pending { int stage; cudaEvent_t a, b; double weight; };
     std::vector<Pending> pending;
     std::vector<cudaEvent_t> pool;
@@ -232,9 +233,9 @@ struct ljgpu_sim {
         if (prof && a) {
             cudaEvent_t b = get_event();
             CK(cudaEventRecord(b, st));
-            // step stages are sampled every prof_every-th step; re-binning / halo stages are always timed
-            const bool sampled = stage != ST_REBUILD && !(stage == ST_HALO && !slab.on);
-            pending.push_back({stage, a, b, sampled && !slab.on ? (double)prof_every : 1.0});
+            // step stages are sampled every prof_every-th step; everything inside a re-binning is always timed
+            const bool sampled = stage != ST_REBUILD && !in_rebuild;
+            pending.push_back({stage, a, b, sampled ? (double)prof_every : 1.0});
         }
     }
     void resolve_pending() {      // stream must be idle
@@ -728,6 +729,7 @@ void ljgpu_sim::setup_p2p() {
 // Re-binning: the reference's list rebuild (.cpp:441-551) on the device layout: sort by cell, dij = 0
 // (.cpp:484-486), tile tables, and on the Verlet path the list itself.
 void ljgpu_sim::rebuild() {
+    struct InRebuild { bool& f; explicit InRebuild(bool& x) : f(x) { f = true; } ~InRebuild() { f = false; } } guard(in_rebuild);
     cudaEvent_t ev = stage_begin();
     static const bool trace = std::getenv("LJGPU_TRACE_REBUILD") != nullptr;     // developer aid: host wall time per section
     auto t0 = std::chrono::steady_clock::now();
@@ -1073,11 +1075,12 @@ void ljgpu_sim::launch_step(double dt) {
     }
     static const bool no_graph = std::getenv("LJGPU_NO_GRAPH") != nullptr;
     bool timed_step = false;
-    if (prof) { timed_step = slab.on || (prof_tick++ % prof_every) == 0; }
+    if (prof) { timed_step = (prof_tick++ % prof_every) == 0; }
     if (timed_step || slab.on || no_graph) {
         HostTrace::Scope hs(htrace, HostTrace::ENQUEUE);
-        prof_this_step = true;
+        prof_this_step = timed_step || !prof;          // slab / no-graph steps that are not sampled carry no event records
         enqueue_step(prune_now, dt);
+        prof_this_step = true;
         return;
     }
     prof_this_step = false;          // graph replay (and its capture) carries no event records
