@@ -68,23 +68,21 @@ predict_finalize_kernel(StepCtrl* __restrict__ ctrl, const double* __restrict__ 
 //     .cpp:431-433 (wrap of the previous step), :336-362 (kick), :368-383 (lambda from the kick1 kinetic
 //     energy), :388-413 (drift, dij += inc), :557-568 (any |dij|^2 > shell^2/4).
 // ---------------------------------------------------------------------------------------------
+// Body shared by the two kick_drift kernels: returns the atom's new position in `p` (valid when i < c.n).
 template <bool TRACK_DISP>
-__global__ void __launch_bounds__(kBlock)
-kick_drift_kernel(LJConst c, double dt, double a, StepCtrl* __restrict__ ctrl,
+__device__ __forceinline__ void kick_drift_body(const LJConst& c, double dt, double a, StepCtrl* __restrict__ ctrl,
                   double4* __restrict__ pos,
                   double* __restrict__ dijx, double* __restrict__ dijy, double* __restrict__ dijz,
                   double* __restrict__ vx, double* __restrict__ vy, double* __restrict__ vz,
-                  const double* __restrict__ fx, const double* __restrict__ fy, const double* __restrict__ fz) {
-    __shared__ double red[32];
-    if (ctrl->stop) return;
+                  const double* __restrict__ fx, const double* __restrict__ fy, const double* __restrict__ fz,
+                  unsigned i, double4& p, double* red, double* red2) {
     // lambda = sqrt(1 + dt/tau * (ekin0/ekin - 1)),  ekin = 0.5*m*sum   (.cpp:354, :373-375)
     const double ek = xmul(xmul(0.5, c.mass), ctrl->pred_sum);
     const double lambda = xsqrt(xadd(1.0, xmul(c.dt_over_tau, xsub(xdiv(c.ekin0, ek), 1.0))));
 
-    const unsigned i = blockIdx.x * kBlock + threadIdx.x;
     double d2 = 0.0, v2 = 0.0;
     if (i < c.n) {
-        double4 p = ld_pos(pos + i);
+        p = ld_pos(pos + i);
         p.x = wrap_coord(p.x, c.L, c.invL);
         p.y = wrap_coord(p.y, c.L, c.invL);
         p.z = wrap_coord(p.z, c.L, c.invL);
@@ -106,7 +104,6 @@ kick_drift_kernel(LJConst c, double dt, double a, StepCtrl* __restrict__ ctrl,
     if (TRACK_DISP) {
         // two maxima in one pass over the block
         d2 = warp_max(d2); v2 = warp_max(v2);
-        __shared__ double red2[32];
         const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
         if (lane == 0) { red[w] = d2; red2[w] = v2; }
         __syncthreads();
@@ -123,6 +120,21 @@ kick_drift_kernel(LJConst c, double dt, double a, StepCtrl* __restrict__ ctrl,
             }
         }
     }
+}
+
+template <bool TRACK_DISP>
+__global__ void __launch_bounds__(kBlock)
+kick_drift_kernel(LJConst c, double dt, double a, StepCtrl* __restrict__ ctrl,
+                  double4* __restrict__ pos,
+                  double* __restrict__ dijx, double* __restrict__ dijy, double* __restrict__ dijz,
+                  double* __restrict__ vx, double* __restrict__ vy, double* __restrict__ vz,
+                  const double* __restrict__ fx, const double* __restrict__ fy, const double* __restrict__ fz) {
+    __shared__ double red[32];
+    __shared__ double red2[32];
+    if (ctrl->stop) return;
+    double4 p;
+    kick_drift_body<TRACK_DISP>(c, dt, a, ctrl, pos, dijx, dijy, dijz, vx, vy, vz, fx, fy, fz,
+                                blockIdx.x * kBlock + threadIdx.x, p, red, red2);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -538,6 +550,43 @@ halo_push_kernel(const StepCtrl* __restrict__ ctrl, const double4* __restrict__ 
             up_mail->nb_vmax2[0] = v2;
             __threadfence_system();
             st_sys_u64(&down_mail->halo_flag[1], seq);          // I am my lower neighbour's upper neighbour
+            st_sys_u64(&up_mail->halo_flag[0], seq);
+        }
+    }
+}
+
+// kick_drift_kernel with the halo push folded in (slab path over peer memory, LJGPU_SLAB_FUSED_PUSH=1): the threads
+// that move an atom of the first / last cell layer also store its new position into the neighbour's halo slot, and
+// the last block to finish publishes this device's fastest-atom value and raises the sequence flags - one launch
+// and one pass over the boundary atoms less than kick_drift + halo_push, and the flags go up earlier.
+__global__ void __launch_bounds__(kBlock)
+kick_drift_push_kernel(LJConst c, double dt, double a, StepCtrl* __restrict__ ctrl,
+                       double4* __restrict__ pos,
+                       double* __restrict__ dijx, double* __restrict__ dijy, double* __restrict__ dijz,
+                       double* __restrict__ vx, double* __restrict__ vy, double* __restrict__ vz,
+                       const double* __restrict__ fx, const double* __restrict__ fy, const double* __restrict__ fz,
+                       unsigned c_lo, unsigned c_hi, double4* __restrict__ down_dst, double4* __restrict__ up_dst,
+                       Mailbox* down_mail, Mailbox* up_mail, unsigned long long seq, unsigned int* ticket) {
+    __shared__ double red[32];
+    __shared__ double red2[32];
+    if (ctrl->stop) return;
+    const unsigned i = blockIdx.x * kBlock + threadIdx.x;
+    double4 p;
+    kick_drift_body<true>(c, dt, a, ctrl, pos, dijx, dijy, dijz, vx, vy, vz, fx, fy, fz, i, p, red, red2);
+    if (i < c.n) {                                   // a one-layer slab pushes every atom both ways
+        if (i < c_lo) st_pos(down_dst + i, p);
+        if (i >= c.n - c_hi) st_pos(up_dst + (i - (c.n - c_hi)), p);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (atomicAdd(ticket, 1u) == gridDim.x - 1) {          // last block: every store and every vmax2 update is fenced
+            *ticket = 0;
+            const double v2 = __longlong_as_double((long long)*(volatile unsigned long long*)&ctrl->vmax2);
+            down_mail->nb_vmax2[1] = v2;
+            up_mail->nb_vmax2[0] = v2;
+            __threadfence_system();
+            st_sys_u64(&down_mail->halo_flag[1], seq);
             st_sys_u64(&up_mail->halo_flag[0], seq);
         }
     }

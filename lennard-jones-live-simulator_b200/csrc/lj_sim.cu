@@ -1014,7 +1014,17 @@ void ljgpu_sim::enqueue_step(bool prune_now, double dt) {
     c.dt_over_tau = dt / p.tau;                                          // .cpp:375
     c.dt = dt;
     cudaEvent_t ev = stage_begin();
-    if (list_mode())
+    static const bool fused_push_env = std::getenv("LJGPU_SLAB_FUSED_PUSH") != nullptr;
+    const bool fused_push = fused_push_env && slab.on && slab.p2p && list_mode();
+    if (fused_push) {
+        ++slab.halo_seq;
+        double4* down_dst = slab.peer_pos[0] + slab.nb_n[0] + slab.nb_hlo[0];
+        double4* up_dst = slab.peer_pos[1] + slab.nb_n[1];
+        kick_drift_push_kernel<<<nb_atoms(), kBlock, 0, st>>>(c, dt, a, ctrl, pos, dij[0], dij[1], dij[2],
+                                                              v[0], v[1], v[2], f[0], f[1], f[2],
+                                                              slab.c_lo, slab.c_hi, down_dst, up_dst,
+                                                              slab.peer_mail[slab.down], slab.peer_mail[slab.up], slab.halo_seq, slab.push_ticket);
+    } else if (list_mode())
         kick_drift_kernel<true><<<nb_atoms(), kBlock, 0, st>>>(c, dt, a, ctrl, pos, dij[0], dij[1], dij[2],
                                                                v[0], v[1], v[2], f[0], f[1], f[2]);
     else
@@ -1022,7 +1032,7 @@ void ljgpu_sim::enqueue_step(bool prune_now, double dt) {
                                                                 v[0], v[1], v[2], f[0], f[1], f[2]);
     check_launch("kick_drift");
     stage_end(ST_KICK_DRIFT, ev);
-    if (slab.on) halo_exchange();
+    if (slab.on && !fused_push) halo_exchange();
     if (prune_now) {       // this step's force pass walks the outer list and emits the inner one
         cudaEvent_t pv = stage_begin();
         if (pairlist) launch_pair<TILE_FORCE_PRUNE>(this, 1);

@@ -31,5 +31,12 @@ run)
     probe "pair path, bricks 5x2x2" LJGPU_PAIRLIST=1 LJGPU_LIBRARY=$PWD/$V/libljgpu_pair_bx5.so
     probe "pair path, bricks 4x2x2, 1 entry x 2 atoms, 3 CTAs/SM" LJGPU_PAIRLIST=1 LJGPU_LIBRARY=$PWD/$V/libljgpu_pair_bx4g1b3.so
     ;;
-*) echo "usage: $0 build|run"; exit 2;;
+run2)   # two GPUs: gpurun --gpus 2 --timeout 600 -- 'bash scripts/round2_experiments.sh run2'
+    for fused in "" 1; do
+        echo "== 2 GPUs, LJGPU_SLAB_FUSED_PUSH=$fused"
+        env ${fused:+LJGPU_SLAB_FUSED_PUSH=1} timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+            --master-port 29577 bench.py --gpus 2 --steps 2000 --warmup 200 --no-cpu 2>/dev/null | python -c "import sys,json; [print({k:d[k] for k in ('value','ms_per_step')}, d['whole_step']['stage_us_per_call']) for d in (json.loads(l) for l in sys.stdin if l.startswith('{'))]"
+    done
+    ;;
+*) echo "usage: $0 build|run|run2"; exit 2;;
 esac
