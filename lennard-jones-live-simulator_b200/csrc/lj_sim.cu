@@ -885,6 +885,13 @@ void ljgpu_sim::pair_build_list() {
         launch_pair<TILE_LIST_FILL>(this, 0);
         fetch_ctrl();
         if (!h_ctrl->overflow) {
+            static const bool list_order = std::getenv("LJGPU_LIST_ORDER") != nullptr;
+            if (list_order) {
+                const unsigned nslots = pnblocks * pslots;
+                list_class_sort_kernel<<<cdiv(nslots, 256), 256, 0, st>>>(pl, pl_in, pl_count, nslots, pcapq);
+                check_launch("list_class_sort");
+                std::swap(pl, pl_in);
+            }
             static const bool trace = std::getenv("LJGPU_TRACE_REBUILD") != nullptr;
             if (trace) {            // union size per thread against the per-atom list lengths
                 std::vector<uint32_t> hc((size_t)pnblocks * pslots), ha(n);
@@ -952,7 +959,15 @@ void ljgpu_sim::build_list() {
             CK(cudaStreamSynchronize(st));
             mx = slab.h_xchg[8]; over = slab.h_xchg[9];
         }
-        if (!over) return;
+        if (!over) {
+            static const bool list_order = std::getenv("LJGPU_LIST_ORDER") != nullptr;
+            if (list_order && n && nl_in) {      // bank-class order: sort into the (currently invalid) inner-list buffer, then swap
+                list_class_sort_kernel<<<cdiv(n, 256), 256, 0, st>>>(nl, nl_in, nl_count, n, capq);
+                check_launch("list_class_sort");
+                std::swap(nl, nl_in);
+            }
+            return;
+        }
         capq = (mx + 12 + 7) / 8;                                 // grow and refill
     }
     throw LjError(LJGPU_ESTATE, "neighbour list capacity did not converge");

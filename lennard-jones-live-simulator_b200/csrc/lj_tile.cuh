@@ -136,6 +136,50 @@ tile_table_kernel(TileGrid g, const uint32_t* __restrict__ cstart, const uint32_
 // (((i>>5)*capq + q)*32 + (i&31))*4.  Entry k of slot i is half-word k&7 of quad k>>3.
 // Replaces the reference's flat [offsets][entries..., sentinel] vector (.cpp:543-550).
 
+// Re-binning, optional (LJGPU_LIST_ORDER=1): copies every slot's list from src to dst with the entries sorted by
+// bank class (j mod 16: the 24-byte records put atom j's x in bank pair 3j mod 16) rotated by the slot number, so
+// that the 16 lanes of a half-warp tend to read 16 different bank pairs at the same step of their walks.  Stable,
+// so the pruned list - a filtered subsequence - inherits the order.  CPU-shim gather profile (liquid, inner-list
+// pass): 4.62 -> 4.04 wavefronts per gather on the per-atom path, 5.18 -> 4.23 on the pair path.  One thread per slot.
+__global__ void __launch_bounds__(256)
+list_class_sort_kernel(const uint32_t* __restrict__ src32, uint32_t* __restrict__ dst32,
+                       const uint32_t* __restrict__ count, unsigned nslots, unsigned capq) {
+    const unsigned slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= nslots) return;
+    const unsigned n = min(count[slot], 8 * capq);
+    const size_t rowq = ((size_t)(slot >> 5) * capq) * 32 + (slot & 31u);
+    const uint4* __restrict__ src = reinterpret_cast<const uint4*>(src32) + rowq;
+    unsigned short* __restrict__ dst = reinterpret_cast<unsigned short*>(dst32) + rowq * 8;
+    const unsigned nq = (n + 7) >> 3, rot = slot & 15u;
+    unsigned char start[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) start[k] = 0;
+    for (unsigned q = 0; q < nq; ++q) {                       // histogram of the rotated classes
+        const uint4 v = __ldg(src + (size_t)q * 32);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+            if (8 * q + e < n) {
+                const unsigned j = (e & 1) ? (w[e >> 1] >> 16) : (w[e >> 1] & 0xffffu);
+                ++start[(j - rot) & 15u];
+            }
+    }
+    unsigned run = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) { const unsigned c = start[k]; start[k] = (unsigned char)run; run += c; }
+    for (unsigned q = 0; q < nq; ++q) {                       // stable scatter; the padding of the last quad is copied
+        const uint4 v = __ldg(src + (size_t)q * 32);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const unsigned j = (e & 1) ? (w[e >> 1] >> 16) : (w[e >> 1] & 0xffffu);
+            const unsigned k = 8 * q + e;
+            const unsigned pos = k < n ? start[(j - rot) & 15u]++ : k;
+            dst[(size_t)(pos >> 3) * 256 + (pos & 7u)] = (unsigned short)j;
+        }
+    }
+}
+
 enum { TILE_FORCE_LIST = 0, TILE_FORCE_CELL = 1, TILE_LIST_COUNT = 2, TILE_LIST_FILL = 3,
        TILE_FORCE_PRUNE = 5 /* force pass over the outer list that also emits the pruned inner list */ };
 

@@ -22,7 +22,9 @@ run)
     LJGPU_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -k experimental_pair -x -q 2>&1 | tail -3
     probe "default" X=1
     probe "prune pass with its own register budget" LJGPU_LIBRARY=$PWD/$V/libljgpu_prune2.so
-    probe "per-atom path, atoms inside a cell ordered as a nearest-neighbour chain" LJGPU_CELL_ORDER=1
+    probe "per-atom path, lists in bank-class order" LJGPU_LIST_ORDER=1
+    probe "pair path, lists in bank-class order" LJGPU_PAIRLIST=1 LJGPU_LIST_ORDER=1
+    probe "pair path 1 entry x 2 atoms 3 CTAs/SM, lists in bank-class order" LJGPU_PAIRLIST=1 LJGPU_LIST_ORDER=1 LJGPU_LIBRARY=$PWD/$V/libljgpu_pair_g1b3.so
     probe "pair path (2 entries x 2 atoms, 2 CTAs/SM, 120 regs)" LJGPU_PAIRLIST=1
     probe "pair path without the chain ordering" LJGPU_PAIRLIST=1 LJGPU_PAIR_ORDER=0
     probe "pair path without the lane balance" LJGPU_PAIRLIST=1 LJGPU_PAIR_BALANCE=0
