@@ -5,6 +5,7 @@
 //          test_adapter nogpu      must throw std::runtime_error("... no CUDA device ...")
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <stdexcept>
@@ -128,11 +129,16 @@ int main(int argc, char** argv) {
     th.signal_integration_step = [&] { frames++; };
     th.signal_ekin = [&](double, double e) { if (e > 0) kilo++; };
     th.start();
-    while (th.iterations() < 2500) std::this_thread::sleep_for(std::chrono::milliseconds(1));
+    // 2500 iterations cross the per-1000-step callback twice; LJGPU_ADAPTER_TEST_ITERS shortens the run where a step
+    // is expensive (the CPU emulation of the library, tests/test_emulated_library.py)
+    const char* it_env = std::getenv("LJGPU_ADAPTER_TEST_ITERS");
+    const unsigned long want_iters = it_env ? std::strtoul(it_env, nullptr, 10) : 2500ul;
+    while (th.iterations() < want_iters) std::this_thread::sleep_for(std::chrono::milliseconds(1));
     th.toggle_pause();
     CHECK(!th.is_running());
     th.stop(); th.wait();
-    CHECK(th.iterations() >= 2500 && kilo.load() >= 2 && frames.load() >= 1);
+    CHECK(th.iterations() >= want_iters && frames.load() >= 1);
+    if (want_iters >= 2500) CHECK(kilo.load() >= 2);
 
     auto st = ljgpu_host::series_stats({1.0, 2.0, 3.0, 4.0});
     CHECK(std::fabs(st.mean - 2.5) < 1e-15 && std::fabs(st.stddev - std::sqrt(5.0 / 3.0)) < 1e-15);

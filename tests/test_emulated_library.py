@@ -67,3 +67,23 @@ def test_edge_cases_on_the_emulated_library():
     out = subprocess.run([sys.executable, os.path.join(HERE, "emul_edge_worker.py")], cwd=ROOT, env=env,
                          capture_output=True, text=True, timeout=900)
     assert out.returncode == 0 and "EDGE CASES OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
+
+
+def test_cpp_adapter_on_the_emulated_library(tmp_path):
+    """The C++ drop-in class (host/lennardjonessimulation.cpp, three rotating mirror buffers over ljgpu_step_publish,
+    mirror modes, parameter reload, movie file, driver thread) linked against the emulated library: the same
+    executable as tests/test_adapter_cpp.py runs on the GPU, with a shorter driver-thread run."""
+    import build_emul_lib
+    lib = build_emul_lib.build()
+    pkg = os.path.join(ROOT, "lennard-jones-live-simulator_b200")
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "liblj_oracle.so"], stdout=subprocess.DEVNULL)
+    exe = str(tmp_path / "test_adapter_emul")
+    subprocess.check_call([
+        "g++", "-std=c++17", "-O1", os.path.join(HERE, "cpp", "test_adapter.cpp"),
+        os.path.join(pkg, "host", "lennardjonessimulation.cpp"), os.path.join(pkg, "host", "threadintegrate.cpp"),
+        "-I", os.path.join(pkg, "host"), "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "oracle"),
+        lib, "-L", os.path.join(ROOT, "oracle"), "-llj_oracle",
+        f"-Wl,-rpath,{os.path.dirname(lib)}", f"-Wl,-rpath,{os.path.join(ROOT, 'oracle')}", "-lpthread", "-o", exe])
+    env = dict(os.environ, LJGPU_NO_GRAPH="1", LJGPU_ADAPTER_TEST_ITERS="40")
+    out = subprocess.run([exe, "gpu"], capture_output=True, text=True, timeout=900, env=env)
+    assert out.returncode == 0 and "OK gpu" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
