@@ -70,7 +70,12 @@ def rewrite_launches(text):
     return "".join(out)
 
 
-def build(force=False):
+def build(force=False, asan=False):
+    """asan=True: the same library with -fsanitize=address (memory checking of kernel and host logic where
+    compute-sanitizer is not available); load it with LD_PRELOAD="libasan.so libstdc++.so.6" - see run_asan.sh."""
+    OUT = os.path.join(HERE, "_build", "libljgpu_emul_asan.so") if asan else globals()["OUT"]
+    SCRATCH = os.path.join(HERE, "_build", "asan") if asan else globals()["SCRATCH"]
+    extra = ["-g", "-fsanitize=address", "-fno-omit-frame-pointer"] if asan else []
     srcs = [os.path.join(PKG, "csrc", f) for f in ("lj_sim.cu", "lj_sort.cu")]
     deps = srcs + [os.path.join(PKG, "csrc", f) for f in ("lj_common.cuh", "lj_kernels.cuh", "lj_tile.cuh", "lj_pair.cuh", "lj_nccl.h")]
     deps += [os.path.join(PKG, "host", "lj_host.cpp"), os.path.join(ROOT, "include", "ljgpu.h"),
@@ -87,24 +92,25 @@ def build(force=False):
         text = text.replace('#include "../../include/ljgpu.h"', f'#include "{os.path.join(ROOT, "include", "ljgpu.h")}"')
         open(dst, "w").write(text)
         obj = dst.replace(".cpp", ".o")
-        subprocess.run(["g++", "-std=c++20", "-O1", "-fPIC", "-pthread", "-mfma", "-ffp-contract=off", "-DLJ_EMUL",
-                        "-I", os.path.join(HERE, "include"), "-I", os.path.join(PKG, "csrc"),
+        subprocess.run(["g++", "-std=c++20", "-O1", "-fPIC", "-pthread", "-mfma", "-ffp-contract=off", "-DLJ_EMUL"] + extra +
+                       ["-I", os.path.join(HERE, "include"), "-I", os.path.join(PKG, "csrc"),
                         "-include", os.path.join(HERE, "include", "cuda_runtime.h"), "-c", dst, "-o", obj],
                        check=True, timeout=600)
         objs.append(obj)
     aobj = os.path.join(SCRATCH, "emul_api.o")
-    subprocess.run(["g++", "-std=c++20", "-O1", "-fPIC", "-pthread", "-DLJ_EMUL", "-c", os.path.join(HERE, "emul_api.cpp"), "-o", aobj],
+    subprocess.run(["g++", "-std=c++20", "-O1", "-fPIC", "-pthread", "-DLJ_EMUL"] + extra + ["-c", os.path.join(HERE, "emul_api.cpp"), "-o", aobj],
                    check=True, timeout=300)
     objs.append(aobj)
     hobj = os.path.join(SCRATCH, "lj_host.o")
-    subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-ffp-contract=off", "-c", os.path.join(PKG, "host", "lj_host.cpp"),
+    subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-ffp-contract=off"] + extra + ["-c", os.path.join(PKG, "host", "lj_host.cpp"),
                     "-o", hobj], check=True, timeout=300)
-    subprocess.run(["g++", "-shared", "-pthread", "-o", OUT] + objs + [hobj, "-ldl"], check=True, timeout=300)
+    subprocess.run(["g++", "-shared", "-pthread"] + (["-fsanitize=address"] if asan else []) + ["-o", OUT] + objs + [hobj, "-ldl"],
+                   check=True, timeout=300)
     # stand-in NCCL for the slab path: ranks are threads of one process (found through LD_LIBRARY_PATH by lj_nccl.h)
     subprocess.run(["g++", "-std=c++20", "-O1", "-fPIC", "-shared", "-pthread", "-o", os.path.join(SCRATCH, "libnccl.so.2"),
-                    os.path.join(HERE, "nccl_emul.cpp")], check=True, timeout=300)
+                    os.path.join(HERE, "nccl_emul.cpp")], check=True, timeout=300) if not asan else None
     return OUT
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv))
+    print(build(force="--force" in sys.argv, asan="--asan" in sys.argv))
