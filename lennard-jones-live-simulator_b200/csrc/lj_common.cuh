@@ -243,6 +243,43 @@ __device__ __forceinline__ void cp_async16(unsigned saddr, const void* g) {
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 #endif
 
+// Monotonic counters in shared memory with release / acquire semantics at CTA scope: how the staging warp and the
+// computing warps of the brick kernel hand tiles over (a counter, unlike an mbarrier phase bit, cannot alias when a
+// waiter is several hand-overs ahead).
+__device__ __forceinline__ unsigned ld_acquire_smem(const unsigned* p) {
+#ifdef LJ_EMUL
+    return *reinterpret_cast<const volatile unsigned*>(p);
+#else
+    unsigned v;
+    asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_addr(p)) : "memory");
+    return v;
+#endif
+}
+__device__ __forceinline__ void st_release_smem(unsigned* p, unsigned v) {
+#ifdef LJ_EMUL
+    *reinterpret_cast<volatile unsigned*>(p) = v;
+    ljemul::note_progress();
+#else
+    asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" :: "r"(smem_addr(p)), "r"(v) : "memory");
+#endif
+}
+__device__ __forceinline__ void spin_pause() {
+#ifdef LJ_EMUL
+    ljemul::yield_fiber();
+#else
+    __nanosleep(64);
+#endif
+}
+
+// Barrier among a subset of a CTA's warps (bar.sync id, count): the staging warps of the brick kernel use id 1.
+__device__ __forceinline__ void named_barrier_sync(unsigned id, unsigned nthreads) {
+#ifdef LJ_EMUL
+    ljemul::named_sync(id, nthreads);
+#else
+    asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory");
+#endif
+}
+
 // ---------------------------------------------------------------------------------------------
 // Device-wide primitives implemented in lj_sort.cu
 // ---------------------------------------------------------------------------------------------

@@ -3,7 +3,6 @@
 // Path replaced: class LennardJonesSimulation, /root/reference/src/simulator/lennardjonessimulation.{h,cpp}
 // (".cpp"/".h" below).  No CPU fallback: every entry point fails with LJGPU_ECUDA when there is no device.
 #include "lj_tile.cuh"
-#include "lj_pair.cuh"
 #include "lj_nccl.h"
 #include "../../include/ljgpu.h"
 
@@ -82,7 +81,7 @@ struct Slab {
 
 } // namespace
 
-static void set_tile_attributes(size_t smem);
+static void set_tile_attributes(ljgpu_sim* s);
 
 // LJGPU_TRACE_HOST=1: wall-clock spent by the stepping thread per host section (totals, maxima and every
 // event above 2 ms), printed when the simulation is destroyed.  Adds no synchronisation.
@@ -145,22 +144,12 @@ struct ljgpu_sim {
     // shared-memory tiles (lj_tile.cuh) and the Verlet list of 16-bit tile indices
     uint32_t *tsrc = nullptr, *toff = nullptr;
     unsigned bxd = kTileBX, byd = kTileBY, bzd = kTileBZ;      // brick size in cells
-    unsigned nbx = 0, nby = 0, nbz = 0, nblocks_tile = 0, tcap = 0, tile_threads = 128, tile_threads_min = 32;
+    unsigned nbx = 0, nby = 0, nbz = 0, nblocks_tile = 0, tcap = 0, tile_slots = 2, tile_ipb = 1;
+    int num_sms = 148;
+    unsigned tile_grid_ctas[8][2] = {{0}};     // CTAs of the persistent brick kernel per (mode, unit sigma): resident CTAs per SM x SMs
     uint32_t* nl = nullptr; uint32_t* nl_count = nullptr; unsigned capq = 0; size_t nl_alloc = 0;
     // pruned inner list (single-device Verlet path)
     uint32_t* nl_in = nullptr; uint32_t* nl_in_count = nullptr;
-    // EXPERIMENTAL pair path (lj_pair.cuh, LJGPU_PAIRLIST=1): one thread per two home atoms, union lists per slot
-    bool pairlist = false, pair_order = true;          // pair_order: LJGPU_PAIR_ORDER=0 keeps the sorted order inside cells
-    unsigned pbx = 0, pby = 0, pbz = 0, pnbx = 0, pnby = 0, pnbz = 0, pnblocks = 0, ptcap = 0, pthreads = 32, pslots = 32, pcapq = 0;
-    uint32_t *ptsrc = nullptr, *ptoff = nullptr, *pl = nullptr, *pl_in = nullptr, *pl_count = nullptr, *pl_in_count = nullptr;
-    unsigned short *prank2pair = nullptr, *ppair2rank = nullptr;     // lane balance of the force passes (pair_map_kernel)
-    bool pair_balance = true;                                          // LJGPU_PAIR_BALANCE=0: threads take pairs in natural order
-    size_t pl_alloc = 0, pslots_alloc = 0;
-    TileGrid pair_grid() const {
-        return TileGrid{nc, ncz, 1u, 0u, nc, pbx, pby, pbz, pnbx, pnby, pnbz, pnblocks, ptsrc, ptoff};
-    }
-    void pair_tables();
-    void pair_build_list();
     double prune_skin = 0.0; unsigned prune_interval = 8, since_prune = 0;
 
     // reductions
@@ -310,7 +299,6 @@ ljgpu_sim::~ljgpu_sim() {
     dfree(orig); dfree(orig_alt); dfree(keys); dfree(vals);
     dfree(cstart); dfree(cend); dfree(ccount);
     dfree(nl); dfree(nl_count); dfree(nl_in); dfree(nl_in_count); dfree(tsrc); dfree(toff);
-    dfree(ptsrc); dfree(ptoff); dfree(pl); dfree(pl_in); dfree(pl_count); dfree(pl_in_count); dfree(prank2pair); dfree(ppair2rank);
     dfree(partial_epot); dfree(partial_ekin); dfree(partial_pred);
     dfree(ctrl); dfree(hist); dfree(out3); dfree(out_u32); dfree(hist_counts);
     if (st_copy) { cudaStreamSynchronize(st_copy); cudaStreamDestroy(st_copy); }
@@ -427,20 +415,7 @@ void ljgpu_sim::allocate() {
         }
         CK(cudaMalloc(&tsrc, (size_t)nblocks_tile * kTileCellsMax * 4));
         CK(cudaMalloc(&toff, (size_t)nblocks_tile * (kTileCellsMax + 1) * 4));
-        nb_force = nblocks_tile;                                   // one partial per CTA
-        // experimental pair path: bricks of 6x2x2 cells when that still gives the SMs a few waves of CTAs
-        pairlist = std::getenv("LJGPU_PAIRLIST") != nullptr && !slab.on && mode == LJGPU_KERNEL_VERLET;
-        if (pairlist) {
-            pbx = kPairBX; pby = kPairBY; pbz = kPairBZ;
-            pnbx = cdiv(nc, pbx); pnby = cdiv(nc, pby); pnbz = cdiv(nc, pbz); pnblocks = pnbx * pnby * pnbz;
-            if (pnblocks < 2u * 148u) pairlist = false;            // fewer bricks than one wave of CTAs: stay on the per-atom path
-        }
-        if (pairlist) {
-            if (const char* e = std::getenv("LJGPU_PAIR_ORDER")) pair_order = std::atoi(e) != 0;
-            if (const char* e = std::getenv("LJGPU_PAIR_BALANCE")) pair_balance = std::atoi(e) != 0;
-            CK(cudaMalloc(&ptsrc, (size_t)pnblocks * kPairCellsMax * 4));
-            CK(cudaMalloc(&ptoff, (size_t)pnblocks * (kPairCellsMax + 1) * 4));
-        }
+        nb_force = nblocks_tile * kBrickItemsMax;                  // one partial per (brick, work item): room for the most items a brick may have
     } else {
         // j splits: enough blocks to fill 148 SMs a few times over, each split at least 64 atoms wide
         const unsigned nba = cdiv(N, kBlock);
@@ -452,6 +427,7 @@ void ljgpu_sim::allocate() {
         nb_force = nba * nsplit;
     }
     CK(cudaMalloc(&partial_epot, (size_t)std::max(nb_force, 1u) * 8));
+    CK(cudaMemset(partial_epot, 0, (size_t)std::max(nb_force, 1u) * 8));
 
     if (slab.on) {
         const size_t layer = N / nc + 1;
@@ -533,11 +509,6 @@ void ljgpu_sim::sort_by_cell() {
     if (n) {
         cell_bounds_kernel<<<nb_atoms(), kBlock, 0, st>>>(n, keys, cstart, cend);
         check_launch("cell_bounds");
-    }
-    static const bool cell_order = std::getenv("LJGPU_CELL_ORDER") != nullptr;   // tuning knob: the same ordering on the per-atom path
-    if (((pairlist && pair_order) || (cell_order && !slab.on)) && n) {      // neighbours in space become neighbours in memory
-        pair_order_kernel<<<cdiv(ncell, 4), 128, 0, st>>>(ncell, cstart, cend, pos_tmp, vals);
-        check_launch("pair_order");
     }
     permute_kernel<<<nb_atoms(), kBlock, 0, st>>>(n, vals, pos_tmp, pos,
                                                   v[0], v[1], v[2], f[0], f[1], f[2], orig,
@@ -758,20 +729,20 @@ void ljgpu_sim::rebuild() {
     fetch_ctrl();
     // launch shapes only grow (a few spare shared-memory records cost nothing; a changed shape costs a graph capture)
     tcap = std::max(tcap, ((h_ctrl->max_tile + 63) / 64) * 64);
-    tile_threads = std::max(tile_threads_min,
-                            std::min((unsigned)LJ_TILE_MAXTHREADS, std::max(32u, ((h_ctrl->max_home + 31) / 32) * 32)));
-    tile_threads_min = tile_threads;
-    nb_force = nblocks_tile;
-    if ((size_t)tcap * kTileRecBytes > 200 * 1024)
+    tile_ipb = std::max(tile_ipb, (h_ctrl->max_home + 31) / 32);
+    if (tile_ipb > (unsigned)kBrickItemsMax) throw LjError(LJGPU_ESTATE, "a brick holds more home atoms than the brick kernel's work items cover");
+    nb_force = nblocks_tile * tile_ipb;
+    // as many tiles in flight per CTA as fit beside the kernel's static shared memory (the ring never needs more than four)
+    tile_slots = (unsigned)std::min<size_t>(kBrickSlotsMax, (size_t)(220 * 1024) / ((size_t)tcap * kTileRecBytes));
+    if (const char* e = std::getenv("LJGPU_BRICK_SLOTS")) tile_slots = std::max(2u, std::min(tile_slots, (unsigned)std::atoi(e)));   // tuning knob
+    if (tile_slots < 2)
         throw LjError(LJGPU_ESTATE, "a cell neighbourhood does not fit in shared memory (density too inhomogeneous)");
     if (h_ctrl->max_tile > 65535) throw LjError(LJGPU_ESTATE, "tile too large for 16-bit list indices");
-    set_tile_attributes((size_t)tcap * kTileRecBytes);
+    set_tile_attributes(this);
 
     lap("tile_table");
-    if (pairlist) { pair_tables(); pair_build_list(); }
-    else if (mode == LJGPU_KERNEL_VERLET) build_list();
+    if (mode == LJGPU_KERNEL_VERLET) build_list();
     lap("build_list");
-    if (pairlist) nb_force = pnblocks;                   // one epot partial per pair CTA
     stage_end(ST_REBUILD, ev);
     ++rebuilds;
     if (since_rebuild > 0) last_interval = since_rebuild;
@@ -779,26 +750,36 @@ void ljgpu_sim::rebuild() {
     dirty_since_rebuild = false;
 }
 
+// The persistent brick kernel (lj_tile.cuh): as many CTAs as stay resident (occupancy x SMs), each streaming bricks
+// through its two-slot ring of shared-memory tiles.
+static size_t tile_smem(const ljgpu_sim* s) { return (size_t)s->tcap * kTileRecBytes * s->tile_slots; }
+
 template <int MODE, bool UNIT_SIGMA>
 static void launch_tile2(ljgpu_sim* s, int guarded) {
-    const size_t smem = (size_t)s->tcap * kTileRecBytes;
     TileArgs a{s->pos, s->nl, s->nl_count, s->prune_skin > 0.0 ? s->nl_in : nullptr, s->nl_in_count,
-               s->f[0], s->f[1], s->f[2], s->partial_epot, s->ctrl, s->capq,
+               s->f[0], s->f[1], s->f[2], s->partial_epot, s->ctrl, s->capq, s->tcap, s->tile_slots, s->tile_ipb,
                s->slab.p2p ? s->slab.mail : nullptr, s->slab.halo_seq};
-    tile_kernel<MODE, UNIT_SIGMA><<<s->nblocks_tile, s->tile_threads, smem, s->st>>>(s->c, s->tile_grid(), a, guarded);
+    const unsigned grid = std::max(1u, std::min(s->nblocks_tile, s->tile_grid_ctas[MODE][UNIT_SIGMA ? 1 : 0]));
+    tile_kernel<MODE, UNIT_SIGMA><<<grid, kBrickThreads, tile_smem(s), s->st>>>(s->c, s->tile_grid(), a, guarded);
     s->check_launch("tile_kernel");
 }
-// Static shared memory counts against the 48 KB default too: opt in well before the limit.  Done at
-// re-binning time (never inside a stream capture).
+// Dynamic shared memory beyond 48 KB is an opt-in, and the grid is sized from the occupancy the driver reports for
+// this instantiation.  Done at re-binning time (never inside a stream capture).
 template <int MODE, bool US>
-static void tile_attr(size_t smem) {
+static void tile_prepare(ljgpu_sim* s) {
+    const size_t smem = tile_smem(s);
     CK(cudaFuncSetAttribute(tile_kernel<MODE, US>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tile_kernel<MODE, US>, kBrickThreads, smem));
+    if (per_sm < 1) throw LjError(LJGPU_ESTATE, "the brick kernel does not fit on an SM with this tile size");
+    static const int cap = std::getenv("LJGPU_BRICK_CTAS_PER_SM") ? std::atoi(std::getenv("LJGPU_BRICK_CTAS_PER_SM")) : 0;   // tuning knob
+    if (cap > 0) per_sm = std::min(per_sm, cap);
+    s->tile_grid_ctas[MODE][US ? 1 : 0] = (unsigned)per_sm * (unsigned)s->num_sms;
 }
-static void set_tile_attributes(size_t smem) {
-    if (smem <= 40 * 1024) return;
-    tile_attr<TILE_FORCE_LIST, true>(smem); tile_attr<TILE_FORCE_LIST, false>(smem);
-    tile_attr<TILE_FORCE_PRUNE, true>(smem); tile_attr<TILE_FORCE_PRUNE, false>(smem);
-    tile_attr<TILE_FORCE_CELL, false>(smem); tile_attr<TILE_LIST_COUNT, false>(smem); tile_attr<TILE_LIST_FILL, false>(smem);
+static void set_tile_attributes(ljgpu_sim* s) {
+    tile_prepare<TILE_FORCE_LIST, true>(s); tile_prepare<TILE_FORCE_LIST, false>(s);
+    tile_prepare<TILE_FORCE_PRUNE, true>(s); tile_prepare<TILE_FORCE_PRUNE, false>(s);
+    tile_prepare<TILE_FORCE_CELL, false>(s); tile_prepare<TILE_LIST_COUNT, false>(s); tile_prepare<TILE_LIST_FILL, false>(s);
 }
 
 template <int MODE>
@@ -807,116 +788,12 @@ static void launch_tile(ljgpu_sim* s, int guarded) {
     else launch_tile2<MODE, false>(s, guarded);
 }
 
-template <int MODE, bool UNIT_SIGMA>
-static void launch_pair2(ljgpu_sim* s, int guarded) {
-    const size_t smem = (size_t)s->ptcap * kTileRecBytes;
-    PairArgs a{s->pos, s->pl, s->pl_count, s->prune_skin > 0.0 ? s->pl_in : nullptr, s->pl_in_count, s->nl_count,
-               s->f[0], s->f[1], s->f[2], s->partial_epot, s->ctrl, s->pcapq, s->pslots,
-               s->pair_balance ? s->prank2pair : nullptr, s->pair_balance ? s->ppair2rank : nullptr};
-    pair_kernel<MODE, UNIT_SIGMA><<<s->pnblocks, s->pthreads, smem, s->st>>>(s->c, s->pair_grid(), a, guarded);
-    s->check_launch("pair_kernel");
-}
-template <int MODE>
-static void launch_pair(ljgpu_sim* s, int guarded) {
-    if ((MODE == TILE_FORCE_LIST || MODE == TILE_FORCE_PRUNE) && s->c.sigma2 == 1.0) launch_pair2<MODE, true>(s, guarded);
-    else launch_pair2<MODE, false>(s, guarded);
-}
-template <int MODE, bool US>
-static void pair_attr(size_t smem) {
-    CK(cudaFuncSetAttribute(pair_kernel<MODE, US>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-}
-
-// Pair path, re-binning part 1: tile tables of the 6x2x2 bricks, launch shapes (only ever growing).
-void ljgpu_sim::pair_tables() {
-    CK(cudaMemsetAsync(&ctrl->max_tile, 0, sizeof(unsigned), st));
-    CK(cudaMemsetAsync(&ctrl->max_home, 0, sizeof(unsigned), st));
-    pair_table_kernel<<<cdiv(pnblocks, 4), 128, 0, st>>>(pair_grid(), cstart, ccount, ptsrc, ptoff, ctrl);
-    check_launch("pair_table");
-    fetch_ctrl();
-    if (h_ctrl->max_tile > 65535) throw LjError(LJGPU_ESTATE, "pair tile too large for 16-bit list indices");
-    ptcap = std::max(ptcap, ((h_ctrl->max_tile + 63) / 64) * 64);
-    if ((size_t)ptcap * kTileRecBytes > 100 * 1024)
-        throw LjError(LJGPU_ESTATE, "a pair-brick neighbourhood does not fit in shared memory twice per SM");
-    pslots = std::max(pslots, ((h_ctrl->max_home + 31) / 32) * 32);
-    pthreads = std::min((unsigned)LJ_PAIR_MAXTHREADS, pslots);
-    const size_t smem = (size_t)ptcap * kTileRecBytes;
-    if (smem > 40 * 1024) {
-        pair_attr<TILE_FORCE_LIST, true>(smem); pair_attr<TILE_FORCE_LIST, false>(smem);
-        pair_attr<TILE_FORCE_PRUNE, true>(smem); pair_attr<TILE_FORCE_PRUNE, false>(smem);
-        pair_attr<TILE_LIST_COUNT, false>(smem); pair_attr<TILE_LIST_FILL, false>(smem);
-    }
-    const size_t slots = (size_t)pnblocks * pslots;
-    if (slots > pslots_alloc) {
-        dfree(pl_count); dfree(pl_in_count);
-        CK(cudaMalloc(&pl_count, slots * 4)); CK(cudaMalloc(&pl_in_count, slots * 4));
-        CK(cudaMemset(pl_count, 0, slots * 4)); CK(cudaMemset(pl_in_count, 0, slots * 4));
-        dfree(prank2pair); dfree(ppair2rank);
-        CK(cudaMalloc(&prank2pair, slots * 2)); CK(cudaMalloc(&ppair2rank, slots * 2));
-        pslots_alloc = slots;
-        pl_alloc = 0;                                    // slot numbering changed: lists are re-sized below
-        ++graph_gen;
-    }
-    if (pair_balance) {
-        if (pslots > (unsigned)kPairMapMax) throw LjError(LJGPU_ESTATE, "more pairs in a brick than the lane-balance sort holds");
-        pair_map_kernel<<<pnblocks, 256, 0, st>>>(pair_grid(), pos, pslots, prank2pair, ppair2rank);
-        check_launch("pair_map");
-    }
-}
-
-// Pair path, re-binning part 2: union lists (count once for the capacity, then fill; grow and refill on overflow).
-void ljgpu_sim::pair_build_list() {
-    const size_t ntiles = cdiv((unsigned)((size_t)pnblocks * pslots), 32);
-    for (int attempt = 0; attempt < 4; ++attempt) {
-        CK(cudaMemsetAsync(&ctrl->max_count, 0, sizeof(unsigned), st));
-        CK(cudaMemsetAsync(&ctrl->overflow, 0, sizeof(unsigned), st));
-        if (pcapq == 0) {
-            launch_pair<TILE_LIST_COUNT>(this, 0);
-            fetch_ctrl();
-            pcapq = (h_ctrl->max_count + 16 + 7) / 8;
-        }
-        const size_t need = ntiles * pcapq * 32 * 4;
-        if (need > pl_alloc) {
-            const size_t want = ntiles * (pcapq + 2) * 32 * 4;
-            dfree(pl); dfree(pl_in);
-            CK(cudaMalloc(&pl, want * 4)); CK(cudaMalloc(&pl_in, want * 4));
-            pl_alloc = want;
-            ++graph_gen;
-        }
-        launch_pair<TILE_LIST_FILL>(this, 0);
-        fetch_ctrl();
-        if (!h_ctrl->overflow) {
-            static const bool list_order = std::getenv("LJGPU_LIST_ORDER") != nullptr;
-            if (list_order) {
-                const unsigned nslots = pnblocks * pslots;
-                list_class_sort_kernel<<<cdiv(nslots, 256), 256, 0, st>>>(pl, pl_in, pl_count, nslots, pcapq);
-                check_launch("list_class_sort");
-                std::swap(pl, pl_in);
-            }
-            static const bool trace = std::getenv("LJGPU_TRACE_REBUILD") != nullptr;
-            if (trace) {            // union size per thread against the per-atom list lengths
-                std::vector<uint32_t> hc((size_t)pnblocks * pslots), ha(n);
-                CK(cudaMemcpy(hc.data(), pl_count, hc.size() * 4, cudaMemcpyDeviceToHost));
-                CK(cudaMemcpy(ha.data(), nl_count, (size_t)n * 4, cudaMemcpyDeviceToHost));
-                unsigned long long tu = 0, ta = 0, used = 0;
-                for (unsigned b = 0; b < pnblocks; ++b)
-                    for (unsigned t = 0; t < pslots; ++t) { const uint32_t v = hc[(size_t)b * pslots + t]; if (v && v != 0xffffffffu && v <= 8 * pcapq) { tu += v; ++used; } }
-                for (uint32_t v : ha) ta += v;
-                std::fprintf(stderr, "[ljgpu pair list] threads with a list %llu, union entries %.2f per thread, per-atom entries %.2f, gathers vs per-atom walk %.3f, capq %u\n",
-                             used, (double)tu / (double)std::max(1ull, used), (double)ta / (double)n, (double)tu / (double)std::max(1ull, ta), pcapq);
-            }
-            return;
-        }
-        pcapq = (h_ctrl->max_count + 16 + 7) / 8;
-    }
-    throw LjError(LJGPU_ESTATE, "pair list capacity did not converge");
-}
-
 void ljgpu_sim::build_list() {
     const unsigned ntiles = cdiv(cap_atoms, 32);
     static const bool trace = std::getenv("LJGPU_TRACE_REBUILD") != nullptr;
     auto note = [&](const char* what) {
-        if (trace) std::fprintf(stderr, "[ljgpu build_list r%d] %s n=%u halo=%u+%u tcap=%u threads=%u capq=%u blocks=%u\n",
-                                slab.rank, what, n, slab.h_lo, slab.h_hi, tcap, tile_threads, capq, nblocks_tile);
+        if (trace) std::fprintf(stderr, "[ljgpu build_list r%d] %s n=%u halo=%u+%u tcap=%u capq=%u blocks=%u\n",
+                                slab.rank, what, n, slab.h_lo, slab.h_hi, tcap, capq, nblocks_tile);
     };
     note("enter");
     for (int attempt = 0; attempt < 4; ++attempt) {
@@ -960,12 +837,6 @@ void ljgpu_sim::build_list() {
             mx = slab.h_xchg[8]; over = slab.h_xchg[9];
         }
         if (!over) {
-            static const bool list_order = std::getenv("LJGPU_LIST_ORDER") != nullptr;
-            if (list_order && n && nl_in) {      // bank-class order: sort into the (currently invalid) inner-list buffer, then swap
-                list_class_sort_kernel<<<cdiv(n, 256), 256, 0, st>>>(nl, nl_in, nl_count, n, capq);
-                check_launch("list_class_sort");
-                std::swap(nl, nl_in);
-            }
             return;
         }
         capq = (mx + 12 + 7) / 8;                                 // grow and refill
@@ -983,8 +854,6 @@ void ljgpu_sim::launch_force(bool timed) {
         check_launch("allpairs_reduce");
     } else if (mode == LJGPU_KERNEL_CELL) {
         launch_tile<TILE_FORCE_CELL>(this, 1);
-    } else if (pairlist) {
-        launch_pair<TILE_FORCE_LIST>(this, 1);
     } else {
         launch_tile<TILE_FORCE_LIST>(this, 1);
     }
@@ -1050,8 +919,7 @@ void ljgpu_sim::enqueue_step(bool prune_now, double dt) {
     if (slab.on && !fused_push) halo_exchange();
     if (prune_now) {       // this step's force pass walks the outer list and emits the inner one
         cudaEvent_t pv = stage_begin();
-        if (pairlist) launch_pair<TILE_FORCE_PRUNE>(this, 1);
-        else launch_tile<TILE_FORCE_PRUNE>(this, 1);
+        launch_tile<TILE_FORCE_PRUNE>(this, 1);
         prune_commit_kernel<<<1, 1, 0, st>>>(ctrl);
         check_launch("prune_commit");
         stage_end(ST_GHOST, pv);                        // reported as ms_ghost / n_ghost: force passes that also pruned
@@ -1075,10 +943,9 @@ ljgpu_sim::GraphKey ljgpu_sim::graph_key(bool prune_now, double dt) const {
     GraphKey k;
     std::memset(&k, 0, sizeof k);                      // padding included: keys are compared bytewise
     const void* ptrs[20] = {pos, v[0], v[1], v[2], f[0], f[1], f[2], dij[0], dij[1], dij[2],
-                            nl, nl_in, nl_count, nl_in_count, tsrc, toff, pl, pl_in, pl_count, prank2pair};
+                            nl, nl_in, nl_count, nl_in_count, tsrc, toff, nullptr, nullptr, nullptr, nullptr};
     std::memcpy(k.ptr, ptrs, sizeof ptrs);
-    k.shape[0] = n; k.shape[1] = tile_threads; k.shape[2] = tcap; k.shape[3] = capq; k.shape[4] = nblocks_tile; k.shape[5] = nb_force;
-    k.shape[6] = pthreads; k.shape[7] = ptcap; k.shape[8] = pcapq; k.shape[9] = pslots;
+    k.shape[0] = n; k.shape[1] = tile_grid_ctas[TILE_FORCE_LIST][1]; k.shape[2] = tcap; k.shape[3] = capq; k.shape[4] = nblocks_tile; k.shape[5] = nb_force; k.shape[6] = tile_slots; k.shape[7] = tile_ipb;
     k.dt = dt; k.gen = graph_gen; k.prune = prune_now ? 1 : 0;
     return k;
 }
@@ -1330,6 +1197,7 @@ static int create_common(const ljgpu_params* p, int rank, int world, const void*
             NCK(A.CommInitRank(&s->slab.comm, world, id, rank));
         }
         CK(cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking));
+        CK(cudaDeviceGetAttribute(&s->num_sms, cudaDevAttrMultiProcessorCount, dev));
         s->n = 0;
         s->setup_constants();
         s->allocate();

@@ -45,9 +45,10 @@ int main() {
     cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
     printf("%s: %d SMs, clock %d kHz\n", p.name, p.multiProcessorCount, p.clockRate);
     const int sms = p.multiProcessorCount;
-    run<1>(1, 128, sms);  run<1>(2, 256, sms);  run<1>(4, 256, sms);  run<1>(8, 256, sms);
-    run<2>(1, 128, sms);  run<2>(4, 256, sms);
-    run<4>(1, 128, sms);  run<4>(2, 256, sms);  run<4>(8, 256, sms);
-    run<8>(1, 128, sms);  run<8>(4, 256, sms);  run<8>(8, 256, sms);
+    // sweep: resident warps per SM x independent chains per thread (how much parallelism the FP64 pipe needs)
+    for (int w : {4, 8, 16, 32, 64}) {
+        const int threads = w >= 8 ? 256 : 128, blocks = w * 32 / threads;
+        run<1>(blocks, threads, sms); run<2>(blocks, threads, sms); run<4>(blocks, threads, sms); run<8>(blocks, threads, sms);
+    }
     return 0;
 }

@@ -26,4 +26,5 @@ def run(n, kernel, steps, rho=0.8, kT=1.0, warm=200):
 
 if __name__ == "__main__":
     n = int(sys.argv[1]); kernel = int(sys.argv[2]); steps = int(sys.argv[3]) if len(sys.argv) > 3 else 200
-    run(n, kernel, steps)
+    warm = int(sys.argv[4]) if len(sys.argv) > 4 else 200
+    run(n, kernel, steps, warm=warm)

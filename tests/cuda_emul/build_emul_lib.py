@@ -77,7 +77,7 @@ def build(force=False, asan=False):
     SCRATCH = os.path.join(HERE, "_build", "asan") if asan else globals()["SCRATCH"]
     extra = ["-g", "-fsanitize=address", "-fno-omit-frame-pointer"] if asan else []
     srcs = [os.path.join(PKG, "csrc", f) for f in ("lj_sim.cu", "lj_sort.cu")]
-    deps = srcs + [os.path.join(PKG, "csrc", f) for f in ("lj_common.cuh", "lj_kernels.cuh", "lj_tile.cuh", "lj_pair.cuh", "lj_nccl.h")]
+    deps = srcs + [os.path.join(PKG, "csrc", f) for f in ("lj_common.cuh", "lj_kernels.cuh", "lj_tile.cuh", "lj_nccl.h")]
     deps += [os.path.join(PKG, "host", "lj_host.cpp"), os.path.join(ROOT, "include", "ljgpu.h"),
              os.path.join(HERE, "cuda_emul.h"), os.path.join(HERE, "cuda_runtime_emul.h"), os.path.join(HERE, "nccl_emul.cpp"), os.path.join(HERE, "emul_api.cpp"),
              os.path.abspath(__file__)]

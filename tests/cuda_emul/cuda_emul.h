@@ -75,6 +75,7 @@ struct Fiber { void* sp = nullptr; bool done = false; unsigned tid = 0; };
 // One running block: its fibers, barrier state and dynamic shared memory.  Lives on the host thread that runs it.
 struct BlockRun {
     unsigned nthreads = 0, live = 0, bar_count = 0, bar_gen = 0;
+    unsigned nbar_count[16] = {}, nbar_gen[16] = {};   // named barriers (bar.sync id, count)
     std::vector<WarpState> warps;
     std::vector<Fiber> fibers;
     std::vector<char> dyn_storage;
@@ -162,6 +163,13 @@ inline void sync_block() {
     if (++r.bar_count == r.live) { r.bar_count = 0; ++r.bar_gen; ++r.progress; }
     else while (r.bar_gen == gen) yield_fiber();
 }
+inline void note_progress() { ++t_run->progress; }
+inline void named_sync(unsigned id, unsigned count) {
+    BlockRun& r = *t_run;
+    const unsigned gen = r.nbar_gen[id];
+    if (++r.nbar_count[id] == count) { r.nbar_count[id] = 0; ++r.nbar_gen[id]; ++r.progress; }
+    else while (r.nbar_gen[id] == gen) yield_fiber();
+}
 inline void sync_warp() {
     BlockRun& r = *t_run;
     WarpState& w = r.warps[t_tid >> 5];
@@ -203,6 +211,7 @@ inline void fiber_main() {
 // Runs one block to completion on the calling host thread.
 inline void run_block(BlockRun& r, unsigned nthreads, size_t smem, uint3 bidx, dim3 grid, const std::function<void()>& kernel) {
     r.nthreads = r.live = nthreads; r.bar_count = 0; r.kernel = &kernel; r.progress = 0;
+    for (int k = 0; k < 16; ++k) { r.nbar_count[k] = 0; r.nbar_gen[k] = 0; }
     r.warps.assign((nthreads + 31) / 32, WarpState());
     for (unsigned w = 0; w < r.warps.size(); ++w) r.warps[w].live = std::min(32u, nthreads - 32 * w);
     if (r.dyn_storage.size() < smem + 64) r.dyn_storage.resize(smem + 64);

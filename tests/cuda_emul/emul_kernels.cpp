@@ -1,11 +1,11 @@
-// emul_kernels.cpp - TEST INFRASTRUCTURE ONLY (see cuda_emul.h).  Runs the tile kernels (lj_tile.cuh) and the
-// experimental pair kernels (lj_pair.cuh) of the product sources on the CPU shim for one configuration:
+// emul_kernels.cpp - TEST INFRASTRUCTURE ONLY (see cuda_emul.h).  Runs the persistent brick kernel (lj_tile.cuh)
+// of the product sources on the CPU shim for one configuration:
 // binning by the reference's cell id, tile tables, list count + fill, a force pass over the outer list, a force
 // pass that also prunes, a force pass over the pruned list.  The Python test compares the three force sets
 // with each other (bit-identical) and with the oracle.
 #include "cuda_emul.h"
 
-#include "../../lennard-jones-live-simulator_b200/csrc/lj_pair.cuh"
+#include "../../lennard-jones-live-simulator_b200/csrc/lj_tile.cuh"
 
 #include <cstdio>
 #include <numeric>
@@ -63,72 +63,49 @@ unsigned cdivu(unsigned a, unsigned b) { return (a + b - 1) / b; }
 
 }  // namespace
 
-// which: 0 = tile kernels (one thread per atom), 1 = pair kernels (one thread per two atoms).
+// ctas: CTAs of the persistent kernel (fewer CTAs than bricks => every CTA streams several bricks through its ring).
 // out_f: 3 passes x 3 components x n (original atom order): outer list, pruning pass, pruned list.
 // out_epot: the three sums of (s12 - s6 - ecut) over ordered pairs.  out_counts: per-atom list length (n).
 // Returns 0, or a negative code when a capacity / shape check fails.
-extern "C" int ljemul_forces(int which, unsigned n, double L, double rcut, double shell, double sigma, double epsilon,
+extern "C" int ljemul_forces(unsigned ctas, unsigned n, double L, double rcut, double shell, double sigma, double epsilon,
                              double prune_skin, unsigned bx, unsigned by, unsigned bz,
                              const double* x, const double* y, const double* z,
                              double* out_f, double* out_epot, uint32_t* out_counts, uint32_t* out_info) {
     Problem p = bin(n, L, rcut, shell, sigma, epsilon, prune_skin, x, y, z);
     const unsigned nc = p.nc;
-    const unsigned cells_max = which ? kPairCellsMax : kTileCellsMax;
-    if (bx < 1 || by < 1 || bz < 1 || bx > (unsigned)(which ? kPairBX : kTileBX) || by > 2 || bz > 2) return -1;
+    if (bx < 1 || by < 1 || bz < 1 || bx > (unsigned)kTileBX || by > 2 || bz > 2) return -1;
     if (bx + 2 > nc || by + 2 > nc || bz + 2 > nc) return -2;              // a tile must not contain a cell twice
     const unsigned nbx = cdivu(nc, bx), nby = cdivu(nc, by), nbz = cdivu(nc, bz), nblocks = nbx * nby * nbz;
-    std::vector<uint32_t> tsrc((size_t)nblocks * cells_max), toff((size_t)nblocks * (cells_max + 1));
+    std::vector<uint32_t> tsrc((size_t)nblocks * kTileCellsMax), toff((size_t)nblocks * (kTileCellsMax + 1));
     TileGrid g{nc, nc, 1u, 0u, nc, bx, by, bz, nbx, nby, nbz, nblocks, tsrc.data(), toff.data()};
     StepCtrl ctrl;
     std::memset(&ctrl, 0, sizeof ctrl);
     std::vector<double> f[3] = {std::vector<double>(n), std::vector<double>(n), std::vector<double>(n)};
-    std::vector<double> partial(nblocks);
-    std::vector<uint32_t> atom_count(n, 0);
+    std::vector<double> partial;
 
-    if (which == 0) ljemul::launch(cdivu(nblocks, 4), 128, 0, [&] { tile_table_kernel(g, p.cstart.data(), p.ccount.data(), tsrc.data(), toff.data(), &ctrl); });
-    else            ljemul::launch(cdivu(nblocks, 4), 128, 0, [&] { pair_table_kernel(g, p.cstart.data(), p.ccount.data(), tsrc.data(), toff.data(), &ctrl); });
+    ljemul::launch(cdivu(nblocks, 4), 128, 0, [&] { tile_table_kernel(g, p.cstart.data(), p.ccount.data(), tsrc.data(), toff.data(), &ctrl); });
     if (ctrl.max_tile > 65535) return -3;
     const unsigned tcap = ((ctrl.max_tile + 63) / 64) * 64;
-    const size_t smem = (size_t)tcap * kTileRecBytes;
-    const unsigned slots_per_block = std::max(32u, ((ctrl.max_home + 31) / 32) * 32);
-    const unsigned threads = std::min((unsigned)(which ? LJ_PAIR_MAXTHREADS : LJ_TILE_MAXTHREADS), slots_per_block);
-    const size_t slots = which ? (size_t)nblocks * slots_per_block : (size_t)n;
-    const size_t ntiles = (slots + 31) / 32;
+    const unsigned slots = 3, ipb = (ctrl.max_home + 31) / 32;
+    const size_t smem = (size_t)tcap * kTileRecBytes * slots;
+    partial.assign((size_t)nblocks * ipb, 0.0);
+    const size_t ntiles = ((size_t)n + 31) / 32;
     std::vector<uint32_t> slot_count(ntiles * 32, 0), slot_in_count(ntiles * 32, 0);
-    out_info[0] = nblocks; out_info[1] = ctrl.max_tile; out_info[2] = ctrl.max_home; out_info[3] = threads;
+    const unsigned grid = std::max(1u, std::min(ctas, nblocks));
+    out_info[0] = nblocks; out_info[1] = ctrl.max_tile; out_info[2] = ctrl.max_home; out_info[3] = grid;
 
-    // pair kernels: lane balance tables (LJEMUL_PAIR_BALANCE=0 switches them off)
-    const bool balance = which == 1 && !(std::getenv("LJEMUL_PAIR_BALANCE") && std::atoi(std::getenv("LJEMUL_PAIR_BALANCE")) == 0);
-    std::vector<unsigned short> rank2pair(ntiles * 32, 0), pair2rank(ntiles * 32, 0);
-    if (balance) {
-        if (slots_per_block > (unsigned)kPairMapMax) return -6;
-        ljemul::launch(nblocks, 256, 0, [&] { pair_map_kernel(g, p.pos.data(), slots_per_block, rank2pair.data(), pair2rank.data()); });
-    }
     auto run = [&](int mode, uint32_t* nl, uint32_t* nl_in, unsigned capq) {
-        if (which == 0) {
-            TileArgs a{p.pos.data(), nl, slot_count.data(), nl_in, slot_in_count.data(), f[0].data(), f[1].data(), f[2].data(),
-                       partial.data(), &ctrl, capq, nullptr, 0ull};
-            ljemul::launch(nblocks, threads, smem, [&] {
-                switch (mode) {
-                    case TILE_LIST_COUNT:  tile_kernel<TILE_LIST_COUNT, false>(p.c, g, a, 0); break;
-                    case TILE_LIST_FILL:   tile_kernel<TILE_LIST_FILL, false>(p.c, g, a, 0); break;
-                    case TILE_FORCE_LIST:  tile_kernel<TILE_FORCE_LIST, true>(p.c, g, a, 1); break;
-                    case TILE_FORCE_PRUNE: tile_kernel<TILE_FORCE_PRUNE, true>(p.c, g, a, 1); break;
-                }
-            });
-        } else {
-            PairArgs a{p.pos.data(), nl, slot_count.data(), nl_in, slot_in_count.data(), atom_count.data(),
-                       f[0].data(), f[1].data(), f[2].data(), partial.data(), &ctrl, capq, slots_per_block,
-                       balance ? rank2pair.data() : nullptr, balance ? pair2rank.data() : nullptr};
-            ljemul::launch(nblocks, threads, smem, [&] {
-                switch (mode) {
-                    case TILE_LIST_COUNT:  pair_kernel<TILE_LIST_COUNT, false>(p.c, g, a, 0); break;
-                    case TILE_LIST_FILL:   pair_kernel<TILE_LIST_FILL, false>(p.c, g, a, 0); break;
-                    case TILE_FORCE_LIST:  pair_kernel<TILE_FORCE_LIST, true>(p.c, g, a, 1); break;
-                    case TILE_FORCE_PRUNE: pair_kernel<TILE_FORCE_PRUNE, true>(p.c, g, a, 1); break;
-                }
-            });
-        }
+        TileArgs a{p.pos.data(), nl, slot_count.data(), nl_in, slot_in_count.data(), f[0].data(), f[1].data(), f[2].data(),
+                   partial.data(), &ctrl, capq, tcap, slots, ipb, nullptr, 0ull};
+        ljemul::launch(grid, kBrickThreads, smem, [&] {
+            switch (mode) {
+                case TILE_LIST_COUNT:  tile_kernel<TILE_LIST_COUNT, false>(p.c, g, a, 0); break;
+                case TILE_LIST_FILL:   tile_kernel<TILE_LIST_FILL, false>(p.c, g, a, 0); break;
+                case TILE_FORCE_LIST:  tile_kernel<TILE_FORCE_LIST, true>(p.c, g, a, 1); break;
+                case TILE_FORCE_PRUNE: tile_kernel<TILE_FORCE_PRUNE, true>(p.c, g, a, 1); break;
+                case TILE_FORCE_CELL:  tile_kernel<TILE_FORCE_CELL, false>(p.c, g, a, 1); break;
+            }
+        });
     };
     auto collect = [&](int pass) {
         for (int k = 0; k < 3; ++k)
@@ -137,6 +114,7 @@ extern "C" int ljemul_forces(int which, unsigned n, double L, double rcut, doubl
         for (double v : partial) e += v;
         out_epot[pass] = e;
         for (auto& v : f) std::fill(v.begin(), v.end(), 0.0);
+        std::fill(partial.begin(), partial.end(), 0.0);
     };
 
     run(TILE_LIST_COUNT, nullptr, nullptr, 0);
@@ -146,7 +124,7 @@ extern "C" int ljemul_forces(int which, unsigned n, double L, double rcut, doubl
     ctrl.max_count = 0; ctrl.overflow = 0;
     run(TILE_LIST_FILL, nl.data(), nullptr, capq);
     if (ctrl.overflow) return -4;
-    for (unsigned s = 0; s < n; ++s) out_counts[p.orig[s]] = which ? atom_count[s] : slot_count[s];
+    for (unsigned s = 0; s < n; ++s) out_counts[p.orig[s]] = slot_count[s];
 
     if (sigma != 1.0) return -5;                              // the force instantiations above are the unit-sigma ones
     run(TILE_FORCE_LIST, nl.data(), nullptr, capq);           // pass 0: outer list (no inner list offered)
@@ -160,5 +138,11 @@ extern "C" int ljemul_forces(int which, unsigned n, double L, double rcut, doubl
     unsigned long long inner_total = 0;
     for (uint32_t v : slot_in_count) inner_total += v;
     out_info[7] = (uint32_t)std::min<unsigned long long>(inner_total, 0xffffffffull);
+    run(TILE_FORCE_CELL, nullptr, nullptr, 0);                // pass 3: cell-list force kernel (no list)
+    for (int k = 0; k < 3; ++k)
+        for (unsigned s = 0; s < n; ++s) out_f[((size_t)3 * 3 + k) * n + p.orig[s]] = f[k][s];
+    double e = 0.0;
+    for (double v : partial) e += v;
+    out_epot[3] = e;
     return 0;
 }

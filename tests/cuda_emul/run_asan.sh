@@ -1,9 +1,8 @@
 #!/bin/bash
 # TEST INFRASTRUCTURE ONLY.  Memory checking without compute-sanitizer: the emulated product library built with
 # AddressSanitizer (global memory = heap blocks with red zones, dynamic shared memory likewise), then the parity
-# subset, the edge cases, the slab worker and (optionally) the experimental paths run against it.  Takes ~10 minutes.
-#   tests/cuda_emul/run_asan.sh            # default paths
-#   tests/cuda_emul/run_asan.sh all        # + pair path, list order, fused halo push
+# subset, the edge cases and the slab worker run against it.  Takes ~10 minutes.
+#   tests/cuda_emul/run_asan.sh
 set -e
 cd "$(dirname "$0")/../.."
 python tests/cuda_emul/build_emul_lib.py >/dev/null                     # plain build: provides the stand-in NCCL
@@ -20,8 +19,4 @@ python -m pytest $T -m gpu -x -q -p no:cacheprovider \
 python tests/emul_edge_worker.py | tail -1
 for w in 2 4; do python tests/slab_emul_worker.py $w 32768 3 70 200 2 | tail -1; done
 LJGPU_SLAB_NCCL=1 python tests/slab_emul_worker.py 2 32768 3 70 200 2 | tail -1
-if [ "$1" = all ]; then
-    LJGPU_SLAB_FUSED_PUSH=1 python tests/slab_emul_worker.py 3 32768 3 70 200 2 | tail -1
-    LJGPU_LIST_ORDER=1 LJGPU_TEST_EXPERIMENTAL=1 python -m pytest $T -m gpu -k experimental_pair -x -q -p no:cacheprovider
-fi
 echo "ASAN RUN CLEAN"

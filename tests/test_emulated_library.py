@@ -25,7 +25,6 @@ def test_gpu_parity_suite_against_the_emulated_library():
     import build_emul_lib
     lib = build_emul_lib.build()
     env = dict(os.environ, LJGPU_LIBRARY=lib, LJGPU_NO_GRAPH="1")
-    env.pop("LJGPU_TEST_EXPERIMENTAL", None)
     cmd = [sys.executable, "-m", "pytest", "tests/test_gpu_parity.py", "-m", "gpu", "-x", "-q", "-p", "no:cacheprovider"]
     for name in SKIP:
         cmd += ["--deselect", f"tests/test_gpu_parity.py::{name}"]

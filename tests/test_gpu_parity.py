@@ -320,36 +320,6 @@ def _crc(a):
     return zlib.crc32(np.ascontiguousarray(a).tobytes()) & 0xFFFFFFFF
 
 
-@pytest.mark.skipif(not os.environ.get("LJGPU_TEST_EXPERIMENTAL"), reason="experimental pair path: set LJGPU_TEST_EXPERIMENTAL=1")
-def test_experimental_pair_path_matches_oracle(lj, monkeypatch):
-    """lj_pair.cuh (one thread per two atoms, union lists; LJGPU_PAIRLIST=1): same parity bar as the default
-    path, across re-binnings, and bit-identical with and without the pruned inner list."""
-    monkeypatch.setenv("LJGPU_PAIRLIST", "1")
-    cfg = ol.config(262144)                       # 23 cells per axis: 4 x 12 x 12 = 576 pair bricks
-    melt = ol.Oracle(cfg)
-    melt.run(1, 100, DT)                          # off the lattice: near-cancelling lattice forces measure noise, not parity
-    o, g = make_pair(lj, cfg, 3, state=melt.state())
-    assert g.get_layout()["list_capacity"] == 0   # the per-atom list is not built on the pair path
-    check_step(o, g, what="pair path step 0")
-    for s in range(1, 6):
-        o.integrate(s, DT); g.integrate(s, DT)
-        check_step(o, g, what=f"pair path step {s}")
-    nb = o.neighbor_counts()                      # per-atom list lengths of the last build (step 0 on both sides)
-    mean, mx = g.get_list_stats()
-    assert mx == int(nb.max()) and abs(mean - float(nb.mean())) < 1e-9
-    g.integrate_n(6, 120, DT)
-    e_pruned = g.get_energies()
-    assert g.get_timers()["rebuilds"] >= 2 and g.get_layout()["n_ghosts"] > 0
-    g.close()
-    monkeypatch.setenv("LJGPU_PRUNE_SKIN", "0")
-    o2, g2 = make_pair(lj, cfg, 3, state=melt.state())
-    for s in range(1, 6):
-        g2.integrate(s, DT)
-    g2.integrate_n(6, 120, DT)
-    assert g2.get_energies() == e_pruned
-    g2.close()
-
-
 def test_full_size_n1048576_against_reference_golden_vectors(lj):
     """BASELINE configs[3] at full size, without running the oracle here: the golden vectors were
     written by the reference's own code (tests/golden/make_golden.py).  Integer outputs bit-exact; energies
