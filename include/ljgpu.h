@@ -71,9 +71,9 @@ typedef struct ljgpu_sim ljgpu_sim;   /* opaque */
  * while profiling is enabled (ljgpu_set_profiling), measured with CUDA events on the
  * integrator's own stream. Milliseconds and launch counts. */
 typedef struct ljgpu_timers {
-    /* ms_ghost / n_ghost: force passes that also emitted the pruned inner list (no ghost atoms exist) */
-    double   ms_predict, ms_kick_drift, ms_ghost, ms_force, ms_kick2, ms_rebuild, ms_halo;
-    uint64_t n_predict, n_kick_drift, n_ghost, n_force, n_kick2, n_rebuild, n_halo;
+    /* ms_force_prune / n_force_prune: force passes that also emitted the pruned inner list */
+    double   ms_predict, ms_kick_drift, ms_force_prune, ms_force, ms_kick2, ms_rebuild, ms_halo;
+    uint64_t n_predict, n_kick_drift, n_force_prune, n_force, n_kick2, n_rebuild, n_halo;
     uint64_t steps;            /* integrate steps completed                         */
     uint64_t rebuilds;         /* cell re-binnings (+ list builds) so far           */
     uint64_t kernel_launches;  /* every kernel this handle has launched             */
@@ -141,7 +141,12 @@ int ljgpu_step_n_timed(ljgpu_sim* s, uint32_t first, uint32_t n, double dt, doub
  * the caller's next step computes.  When the call returns, the delivery started by the PREVIOUS
  * ljgpu_step_publish is complete; the one started by this call is complete after the next ljgpu_step_publish
  * or ljgpu_publish_wait.  Alternate between two sets of buffers (pinned: ljgpu_alloc_host), exactly like the
- * reference's double buffer.  On slabs the call is collective and delivers before returning. */
+ * reference's double buffer.
+ * On slabs (peer-memory step loop) the call is collective and every device delivers only ITS slice of the frame:
+ * original indices [rank * S, min(N, (rank + 1) * S)), S = ceil(N / world), of x, y and z - every device first scatters
+ * the atoms it owns into the slices of their owners over NVLink, then each owner copies its slice out over its own
+ * PCIe link.  x, y, z address the whole frame on every rank; pass memory shared by the ranks' processes (POSIX shared
+ * memory pinned with ljgpu_register_host) and one consumer sees the whole system, moved once instead of `world` times. */
 int ljgpu_step_publish(ljgpu_sim* s, uint32_t step, double dt, double* x, double* y, double* z);
 
 /* Blocks until the delivery started by the last ljgpu_step_publish is complete (no-op if none is pending). */
@@ -176,9 +181,20 @@ int ljgpu_maxwell_boltzmann(double kT, double mass, int32_t nr_particles, uint32
  *   cell_of_atom[i] = iz*nx*ny + iy*nx + ix with ix = min((unsigned)(x/dx), nx-1)   (:447-476)
  *   count_of_atom[i] = #{ j != i : min-image dist2 <= cutoff^2 }  when inclusive != 0  (:518-540)
  *                    = #{ j != i : min-image dist2 <  cutoff^2 }  when inclusive == 0  (:291-305)
- * cutoff must not exceed rcut + shell. */
+ * cutoff must not exceed rcut + shell.  Both probes only read the simulation: the neighbour count bins a copy of the
+ * published positions (it neither re-bins the integrator nor resets its displacement accumulators), so probing does
+ * not change when the next list rebuild happens.  On slabs the calls are collective and return the whole system. */
 int ljgpu_get_cell_ids(ljgpu_sim* s, uint32_t* cell_of_atom, uint32_t dims[3]);
 int ljgpu_get_neighbor_counts(ljgpu_sim* s, double cutoff, int inclusive, uint32_t* count_of_atom);
+
+/* Per-atom lengths of the lists the force kernel actually walks (Verlet path), original atom order:
+ *   which = 0: the list built at the last re-binning, the reference's neighbor_list (lennardjonessimulation.cpp:518-550:
+ *              j != i with min-image dist2 <= (rcut+shell)^2 at the positions of that re-binning); its lengths equal the
+ *              reference's per-atom list lengths.  The acceptance test here contracts d2 with FMA, so a pair whose
+ *              dist2 lies within an ulp of (rcut+shell)^2 may be classified differently - such a pair is 0.4 sigma
+ *              outside the force cutoff and cannot change a force; ljgpu_get_neighbor_counts is the bit-exact probe;
+ *   which = 1: the pruned inner list (entries within rcut + 0.12 sigma at the last pruning), LJGPU_ESTATE if none exists. */
+int ljgpu_get_list_counts(ljgpu_sim* s, int which, uint32_t* count_of_atom);
 
 /* write_to_movie_file (lennardjonessimulation.cpp:121-157): u32 N when create != 0, then one
  * frame = 3 f64 box edges + N x 7 f64 {x,y,z,vx,vy,vz,|v|}, native endianness. */
@@ -191,11 +207,10 @@ int ljgpu_write_movie_frame(ljgpu_sim* s, const char* path, int create);
 int ljgpu_set_profiling(ljgpu_sim* s, int enabled);
 int ljgpu_get_timers(ljgpu_sim* s, ljgpu_timers* out);
 int ljgpu_reset_timers(ljgpu_sim* s);
-/* Force path actually in use (LJGPU_KERNEL_*), cells per axis, current list capacity per atom, and - in the
- * last argument, historically named n_ghosts; this layout has no ghost atoms - the number of steps whose force
- * pass was served by the pruned inner list. */
+/* Force path actually in use (LJGPU_KERNEL_*), cells per axis, current list capacity per atom, and the number of
+ * steps whose force pass was served by the pruned inner list. */
 int ljgpu_get_layout(ljgpu_sim* s, int32_t* force_kernel, uint32_t* cells_per_axis,
-                     uint32_t* list_capacity, uint64_t* n_ghosts);
+                     uint32_t* list_capacity, uint64_t* inner_list_steps);
 
 /* ---- several devices: z-slab decomposition ------------------------------------------------------
  * The box is cut into `world` slabs of whole cell layers along z (the slowest index of the reference's
@@ -217,10 +232,19 @@ int ljgpu_slab_info(ljgpu_sim* s, int32_t* rank, int32_t* world, uint32_t* first
 /* Mean and maximum Verlet-list length per atom of the current list (0 on the other paths). */
 int ljgpu_get_list_stats(ljgpu_sim* s, double* mean_length, uint32_t* max_length);
 
+/* Measured FP64 throughput of one device in TFLOP/s (eight independent DFMA chains per thread, 64 warps per SM,
+ * best of five launches, CUDA events): the roofline denominator of the force kernels, measured on the spot instead
+ * of quoted (nominal B200: 148 SMs x 64 DFMA/clk x 2 x 1.965 GHz = 37.2).  device = -1: the current device. */
+int ljgpu_measure_fp64_peak(int device, double* tflops);
+
 /* Page-locked host memory for query buffers (cudaMallocHost / cudaFreeHost): copies into such a
  * buffer are true DMA; any other host pointer works too, only slower. */
 int ljgpu_alloc_host(size_t bytes, void** out);
 int ljgpu_free_host(void* p);
+/* Page-lock memory the caller already owns (cudaHostRegister / cudaHostUnregister), e.g. a POSIX shared-memory
+ * segment that several ranks' processes publish into. */
+int ljgpu_register_host(void* p, size_t bytes);
+int ljgpu_unregister_host(void* p);
 
 #ifdef __cplusplus
 }

@@ -8,5 +8,5 @@ directory name contains hyphens, so import it with
 from .binding import (  # noqa: F401
     LJParams, LennardJonesParameters, LennardJonesSimulation, LJGpuError, load_library, library_path,
     KERNEL_AUTO, KERNEL_ALLPAIRS, KERNEL_CELL, KERNEL_VERLET, host_initialize, host_rng_reset,
-    maxwell_boltzmann, device_count, EXPORTED_SYMBOLS, slab_layers, slab_unique_id, HostBuffer,
+    maxwell_boltzmann, device_count, EXPORTED_SYMBOLS, slab_layers, slab_unique_id, HostBuffer, measure_fp64_peak, SharedFrames,
 )

@@ -17,9 +17,9 @@ EXPORTED_SYMBOLS = [
     "ljgpu_create", "ljgpu_destroy", "ljgpu_set_state", "ljgpu_update_params", "ljgpu_step",
     "ljgpu_step_n", "ljgpu_get_positions", "ljgpu_get_velocities", "ljgpu_get_forces",
     "ljgpu_get_energies", "ljgpu_get_energy_history", "ljgpu_get_speed_histogram",
-    "ljgpu_maxwell_boltzmann", "ljgpu_get_cell_ids", "ljgpu_get_neighbor_counts",
+    "ljgpu_maxwell_boltzmann", "ljgpu_get_cell_ids", "ljgpu_get_neighbor_counts", "ljgpu_get_list_counts",
     "ljgpu_write_movie_frame", "ljgpu_set_profiling", "ljgpu_get_timers", "ljgpu_reset_timers",
-    "ljgpu_get_layout", "ljgpu_step_n_timed", "ljgpu_get_list_stats", "ljgpu_alloc_host", "ljgpu_free_host",
+    "ljgpu_get_layout", "ljgpu_step_n_timed", "ljgpu_get_list_stats", "ljgpu_alloc_host", "ljgpu_free_host", "ljgpu_measure_fp64_peak", "ljgpu_register_host", "ljgpu_unregister_host",
     "ljgpu_slab_layers", "ljgpu_slab_unique_id", "ljgpu_create_slab", "ljgpu_slab_info",
     "ljgpu_step_publish", "ljgpu_publish_wait",
 ]
@@ -54,6 +54,71 @@ class HostBuffer:
             pass
 
 
+class SharedFrames:
+    """Two position frames (x | y | z, original atom order, 3 N doubles each) in host memory that every rank's process
+    can write: page-locked memory on one device, POSIX shared memory registered with CUDA (ljgpu_register_host) by
+    every rank on slabs - there ljgpu_step_publish lets each device deliver only its slice of the frame, so the
+    consumer's view of the whole system is assembled by `world` PCIe links in parallel.  `dist` = torch.distributed
+    (or None): used to agree on the segment names."""
+
+    def __init__(self, n, world=1, rank=0, dist=None):
+        self._lib = load_library()
+        self.n, self.world, self.rank = int(n), int(world), int(rank)
+        self._shm, self._host, self.frames = [], [], []
+        if self.world == 1:
+            for _ in range(2):
+                hb = HostBuffer(3 * self.n)
+                self._host.append(hb)
+                self.frames.append(hb.array)
+            return
+        from multiprocessing import shared_memory
+        names = [None, None]
+        if self.rank == 0:
+            for b in range(2):
+                seg = shared_memory.SharedMemory(create=True, size=3 * self.n * 8)
+                self._shm.append(seg)
+                names[b] = seg.name
+        dist.broadcast_object_list(names, src=0)
+        if self.rank != 0:
+            for b in range(2):
+                self._shm.append(shared_memory.SharedMemory(name=names[b]))
+        for seg in self._shm:
+            arr = np.ndarray((3 * self.n,), dtype=np.float64, buffer=seg.buf)
+            if self.rank == 0:
+                arr[:] = 0.0                       # touch the pages before they are pinned
+            self.frames.append(arr)
+        dist.barrier()
+        for arr in self.frames:
+            _check(self._lib, self._lib.ljgpu_register_host(C.c_void_p(arr.ctypes.data), C.c_size_t(arr.nbytes)))
+
+    def pointers(self):
+        """[[x, y, z] of frame 0, [x, y, z] of frame 1] as raw addresses for integrate_publish."""
+        return [[f.ctypes.data + k * self.n * 8 for k in range(3)] for f in self.frames]
+
+    def xyz(self, b):
+        f = self.frames[b]
+        return f[:self.n], f[self.n:2 * self.n], f[2 * self.n:]
+
+    def frame_is_finite(self, b):
+        return bool(np.isfinite(self.frames[b]).all())
+
+    def close(self):
+        for arr in self.frames if self.world > 1 else []:
+            self._lib.ljgpu_unregister_host(C.c_void_p(arr.ctypes.data))
+        self.frames = []
+        for hb in self._host:
+            hb.close()
+        self._host = []
+        for seg in self._shm:
+            try:
+                seg.close()
+                if self.rank == 0:
+                    seg.unlink()
+            except Exception:
+                pass
+        self._shm = []
+
+
 class LJParams(C.Structure):
     """struct ljgpu_params (include/ljgpu.h)."""
     _fields_ = [
@@ -66,9 +131,9 @@ class LJParams(C.Structure):
 
 class LJTimers(C.Structure):
     _fields_ = [(k, C.c_double) for k in
-                ("ms_predict", "ms_kick_drift", "ms_ghost", "ms_force", "ms_kick2", "ms_rebuild", "ms_halo")] + \
+                ("ms_predict", "ms_kick_drift", "ms_force_prune", "ms_force", "ms_kick2", "ms_rebuild", "ms_halo")] + \
                [(k, C.c_uint64) for k in
-                ("n_predict", "n_kick_drift", "n_ghost", "n_force", "n_kick2", "n_rebuild", "n_halo",
+                ("n_predict", "n_kick_drift", "n_force_prune", "n_force", "n_kick2", "n_rebuild", "n_halo",
                  "steps", "rebuilds", "kernel_launches")]
 
 
@@ -110,6 +175,7 @@ def load_library():
     lib.ljgpu_maxwell_boltzmann.argtypes = [C.c_double, C.c_double, C.c_int32, C.c_uint32, C.c_double, vp]
     lib.ljgpu_get_cell_ids.argtypes = [vp, vp, vp]
     lib.ljgpu_get_neighbor_counts.argtypes = [vp, C.c_double, C.c_int, vp]
+    lib.ljgpu_get_list_counts.argtypes = [vp, C.c_int, vp]
     lib.ljgpu_write_movie_frame.argtypes = [vp, C.c_char_p, C.c_int]
     lib.ljgpu_set_profiling.argtypes = [vp, C.c_int]
     lib.ljgpu_get_timers.argtypes = [vp, C.POINTER(LJTimers)]
@@ -118,6 +184,9 @@ def load_library():
                                      C.POINTER(C.c_uint64)]
     lib.ljgpu_step_n_timed.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_double, dp]
     lib.ljgpu_get_list_stats.argtypes = [vp, dp, C.POINTER(C.c_uint32)]
+    lib.ljgpu_measure_fp64_peak.argtypes = [C.c_int, dp]
+    lib.ljgpu_register_host.argtypes = [vp, C.c_size_t]
+    lib.ljgpu_unregister_host.argtypes = [vp]
     lib.ljgpu_step_publish.argtypes = [vp, C.c_uint32, C.c_double, vp, vp, vp]
     lib.ljgpu_publish_wait.argtypes = [vp]
     lib.ljgpu_alloc_host.argtypes = [C.c_size_t, C.POINTER(vp)]
@@ -193,6 +262,14 @@ def slab_unique_id():
     lib = load_library()
     _check(lib, lib.ljgpu_slab_unique_id(buf))
     return buf.raw
+
+
+def measure_fp64_peak(device=-1):
+    """Measured DFMA throughput of a device in TFLOP/s (the force kernels' roofline denominator)."""
+    lib = load_library()
+    out = C.c_double()
+    _check(lib, lib.ljgpu_measure_fp64_peak(int(device), C.byref(out)))
+    return out.value
 
 
 def host_rng_reset():
@@ -363,6 +440,13 @@ class LennardJonesSimulation:
         _check(self._lib, self._lib.ljgpu_get_neighbor_counts(self._h, cutoff, 1 if inclusive else 0, _ptr(out)))
         return out
 
+    def get_list_counts(self, inner=False):
+        """Per-atom lengths of the list the force kernel walks: the list of the last re-binning (the reference's
+        neighbor_list) or, inner=True, the pruned inner list."""
+        out = np.empty(self.n, dtype=np.uint32)
+        _check(self._lib, self._lib.ljgpu_get_list_counts(self._h, 1 if inner else 0, _ptr(out)))
+        return out
+
     def write_to_movie_file(self, path, create=False):
         _check(self._lib, self._lib.ljgpu_write_movie_frame(self._h, os.fsencode(path), 1 if create else 0))
 
@@ -389,4 +473,4 @@ class LennardJonesSimulation:
     def get_layout(self):
         k, nc, cap, g = C.c_int32(), C.c_uint32(), C.c_uint32(), C.c_uint64()
         _check(self._lib, self._lib.ljgpu_get_layout(self._h, C.byref(k), C.byref(nc), C.byref(cap), C.byref(g)))
-        return {"force_kernel": k.value, "cells_per_axis": nc.value, "list_capacity": cap.value, "n_ghosts": g.value}
+        return {"force_kernel": k.value, "cells_per_axis": nc.value, "list_capacity": cap.value, "inner_list_steps": g.value}

@@ -88,7 +88,7 @@ struct StepCtrl {
     unsigned int stop;            // a re-binning is due: remaining steps of the batch do nothing
     unsigned int steps_done;      // steps completed in the current batch
     unsigned int next_step;       // the `step` argument of the integrate() call being executed (history, log cadence)
-    unsigned int pad0;
+    unsigned int ticket;          // blocks of the current kick2 launch that have finished (the last one finalizes the step)
     unsigned int overflow;        // list capacity exceeded during a build
     unsigned int max_count;       // max list length seen by the last build
     unsigned int max_tile;        // largest shared-memory tile (atoms) over all home blocks
@@ -101,6 +101,9 @@ struct StepCtrl {
     unsigned int inner_used;      // steps that used it (statistics)
     double vmax_last;             // max_i |v_i| of the last completed step (host sizes the pruning cadence from it)
     double red[4];                // slab path: {epot_sum, ekin_sum, pred_sum, rebuild votes}, local then all-reduced
+    // slab path over peer memory: sequence numbers of the halo pushes and of the mailbox all-reduces done so far.  They live on
+    // the device (not in kernel arguments) so that a captured CUDA graph of a step stays valid from step to step.
+    unsigned long long halo_seq, red_seq;
 };
 
 // Slab path, peer-memory exchange: every device owns one mailbox that its peers write over NVLink.
@@ -110,6 +113,7 @@ struct Mailbox {
     unsigned long long red_flag[2][kMaxPeers];       // [parity][source rank] = sequence number of the deposited sums
     double red[2][kMaxPeers][4];                     // [parity][source rank]{epot_sum, ekin_sum, pred_sum, rebuild vote}
     double nb_vmax2[2];                              // max |v|^2 of this step's drift on my lower [0] / upper [1] neighbour (pushed with the halo)
+    unsigned long long pub_flag[kMaxPeers];          // [source rank] = sequence number of the publication whose atoms that rank has scattered into my frame slice
     unsigned int error;                              // a wait timed out (peer gone): results are invalid
     unsigned int pad;
 };

@@ -321,19 +321,143 @@ count_cells_kernel(LJConst c, CellGrid g, const double4* __restrict__ pos, doubl
     cell_traverse<true>(c, g, pos, tile, op);
 }
 
+// ---- slab path over peer memory (NVLink loads/stores, no NCCL in the step loop) ----------------------
+__device__ __forceinline__ unsigned long long ld_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+#ifdef LJ_EMUL
+    v = ljemul::atomic_load_u64(p);
+#else
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+#endif
+    return v;
+}
+__device__ __forceinline__ void st_sys_u64(unsigned long long* p, unsigned long long v) {
+#ifdef LJ_EMUL
+    ljemul::atomic_store_u64(p, v);
+#else
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+#endif
+}
+__device__ __forceinline__ double ld_sys_f64(const double* p) {
+    double v;
+#ifdef LJ_EMUL
+    v = ljemul::atomic_load_f64(p);
+#else
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+#endif
+    return v;
+}
+// Spin until *flag >= seq; gives up after ~2 s (a peer died) so that no kernel can hang the device.
+__device__ __forceinline__ bool wait_flag(const unsigned long long* flag, unsigned long long seq, unsigned int* error) {
+    const long long t0 = clock64();
+    while (ld_sys_u64(flag) < seq) {
+        if (clock64() - t0 > 4000000000ll) { atomicExch(error, 1u); return false; }
+        __nanosleep(100);
+    }
+    __threadfence_system();
+    return true;
+}
+
 // ---------------------------------------------------------------------------------------------
-// K3  kick2 + kinetic sums, .cpp:336-362.  Also forms sum |v' + a f|^2, which is exactly the kinetic sum
-//     the next step's kick1 will produce (same forces, same operations), so the thermostat factor of
-//     the next step is known without another pass.
+// K3  kick2 + kinetic sums + the step's final reductions and publication, ONE launch.  .cpp:336-362, :95-96, :327-329.
+//     Also forms sum |v' + a f|^2, which is exactly the kinetic sum the next step's kick1 will produce (same forces,
+//     same operations), so the thermostat factor of the next step is known without another pass.
+//     Every block reduces its atoms' two kinetic sums and a fixed slice of the force pass's energy partials; the
+//     block that finishes last (ticket) adds the per-block sums in fixed order - so the result does not depend on
+//     which block that is - and publishes energies, history and the re-binning flag.  On the slab path over peer
+//     memory (SLAB) the last block also runs the all-reduce through the mailboxes.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock)
-kick2_kernel(LJConst c, double a, const StepCtrl* __restrict__ ctrl,
+constexpr int kKick2Block = 256;
+
+// three sums at once: one barrier pair instead of three.  All threads call; results valid in thread 0.
+__device__ __forceinline__ void block_sum3(double& a, double& b, double& cc, double (*red)[3]) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    a = warp_sum(a); b = warp_sum(b); cc = warp_sum(cc);
+    if (lane == 0) { red[w][0] = a; red[w][1] = b; red[w][2] = cc; }
+    __syncthreads();
+    const int nw = (blockDim.x + 31) >> 5;
+    if (w == 0) {
+        a = lane < nw ? red[lane][0] : 0.0; b = lane < nw ? red[lane][1] : 0.0; cc = lane < nw ? red[lane][2] : 0.0;
+        a = warp_sum(a); b = warp_sum(b); cc = warp_sum(cc);
+    }
+    __syncthreads();
+}
+
+// fixed-order sum of p[0..n) by the threads of one block (four accumulators per thread so the loads overlap)
+__device__ __forceinline__ double strided_sum_block(const double* __restrict__ p, unsigned n) {
+    const unsigned T = blockDim.x;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    unsigned k = threadIdx.x;
+    for (; k + 3 * T < n; k += 4 * T) { a0 += p[k]; a1 += p[k + T]; a2 += p[k + 2 * T]; a3 += p[k + 3 * T]; }
+    for (; k < n; k += T) a0 += p[k];
+    return (a0 + a1) + (a2 + a3);
+}
+
+// The tail of integrate() (.cpp:95-98 and the per-step bookkeeping of this layout), one thread.
+__device__ __forceinline__ void publish_step(const LJConst& c, StepCtrl* __restrict__ ctrl, HistEntry* __restrict__ hist,
+                                             double se, double sk, double sp, bool rebuild_due, double vmax2) {
+    const double ekin = xmul(xmul(0.5, c.mass), sk);
+    const double epot = xmul(xmul(xmul(se, 4.0), c.epsilon), 0.5);
+    ctrl->epot_sum = se;
+    ctrl->pred_sum = sp;
+    ctrl->ekin = ekin; ctrl->epot = epot; ctrl->etot = xadd(ekin, epot);
+    HistEntry& h = hist[ctrl->hist_head % kHistCap];
+    h.ekin = ekin; h.epot = epot; h.step = ctrl->next_step; h.pad = 0;
+    ctrl->next_step += 1;
+    ctrl->hist_head += 1;
+    ctrl->steps_done += 1;
+    if (rebuild_due) ctrl->stop = 1;
+    // pruned inner list: the displacement bound advances by this step's fastest atom
+    const double vmax = sqrt(vmax2);
+    ctrl->vmax_last = vmax;
+    ctrl->drift_bound += vmax * c.dt;
+    ctrl->vmax2 = 0ull;
+}
+
+// All-reduce of four doubles over the devices through their mailboxes (peer memory over NVLink), by one block of at
+// least 4 * world threads: thread r deposits this device's sums in peer r's mailbox (its own included), fences,
+// raises the flag and waits for peer r's deposit in mine; the deposits are then added in rank order, so every device
+// gets identical sums.  tot / g are shared-memory arrays of four doubles; g is valid for every thread on return.
+__device__ __forceinline__ void mailbox_allreduce(const double* tot, double* g, double* dep,
+                                                  Mailbox* mine, Mailbox* const* __restrict__ peers,
+                                                  int rank, int world, unsigned long long seq) {
+    const unsigned par = (unsigned)(seq & 1ull);
+    if ((int)threadIdx.x < world) {
+        Mailbox* dst = peers[threadIdx.x];
+        double* slot = dst->red[par][rank];
+        slot[0] = tot[0]; slot[1] = tot[1]; slot[2] = tot[2]; slot[3] = tot[3];
+        __threadfence_system();
+        st_sys_u64(&dst->red_flag[par][rank], seq);
+        wait_flag(&mine->red_flag[par][threadIdx.x], seq, &mine->error);
+    }
+    __syncthreads();                                       // every deposit has arrived before anyone reads
+    if ((int)threadIdx.x < world * 4) dep[threadIdx.x] = ld_sys_f64(&mine->red[par][threadIdx.x >> 2][threadIdx.x & 3]);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int r = 0; r < world; ++r)
+            for (int k = 0; k < 4; ++k) s[k] += dep[r * 4 + k];
+        g[0] = s[0]; g[1] = s[1]; g[2] = s[2]; g[3] = s[3];
+    }
+    __syncthreads();
+}
+
+struct SlabRed { Mailbox* mine; Mailbox* const* peers; int rank, world; };
+
+// KIND: 0 = one device, 1 = slab over peer memory (mailbox all-reduce here), 2 = slab with the NCCL step loop (local sums only:
+// ncclAllReduce and slab_publish_kernel follow)
+template <int KIND>
+__global__ void __launch_bounds__(kKick2Block)
+kick2_kernel(LJConst c, double a, StepCtrl* __restrict__ ctrl, HistEntry* __restrict__ hist,
              double* __restrict__ vx, double* __restrict__ vy, double* __restrict__ vz,
              const double* __restrict__ fx, const double* __restrict__ fy, const double* __restrict__ fz,
-             double* __restrict__ partial_ekin, double* __restrict__ partial_pred) {
-    __shared__ double red[32];
+             const double* __restrict__ partial_epot, unsigned nb_epot,
+             double* __restrict__ block_sums /* [3][gridDim.x]: epot slice, ekin, pred */, SlabRed sr) {
+    __shared__ double red[kKick2Block / 32][3];
+    __shared__ unsigned s_last;
+    __shared__ double s_tot[4], s_g[4], s_dep[kMaxPeers * 4], s_nbv2;
     if (ctrl->stop) return;
-    const unsigned i = blockIdx.x * kBlock + threadIdx.x;
+    const unsigned i = blockIdx.x * kKick2Block + threadIdx.x;
     double s1 = 0.0, s2 = 0.0;
     if (i < c.n) {
         const double gx = xmul(a, fx[i]), gy = xmul(a, fy[i]), gz = xmul(a, fz[i]);
@@ -342,40 +466,62 @@ kick2_kernel(LJConst c, double a, const StepCtrl* __restrict__ ctrl,
         s1 = xnorm2(ux, uy, uz);
         s2 = xnorm2(xadd(ux, gx), xadd(uy, gy), xadd(uz, gz));
     }
-    s1 = block_sum(s1, red);
-    s2 = block_sum(s2, red);
-    if (threadIdx.x == 0) { partial_ekin[blockIdx.x] = s1; partial_pred[blockIdx.x] = s2; }
-}
-
-// Final reductions in fixed order, energies (.cpp:95-96, :327-329, :361), history, rebuild flag.
-__global__ void __launch_bounds__(kFinalizeThreads)
-step_finalize_kernel(LJConst c, StepCtrl* __restrict__ ctrl, HistEntry* __restrict__ hist,
-                     const double* __restrict__ partial_epot, unsigned nb_epot,
-                     const double* __restrict__ partial_ekin, const double* __restrict__ partial_pred,
-                     unsigned nb_kick) {
-    __shared__ double red[32];
-    if (ctrl->stop) return;
-    double se = strided_sum(partial_epot, nb_epot), sk = strided_sum(partial_ekin, nb_kick), sp = strided_sum(partial_pred, nb_kick);
-    se = block_sum(se, red);
-    sk = block_sum(sk, red);
-    sp = block_sum(sp, red);
+    // this block's slice of the force pass's energy partials (fixed slices => fixed summation order)
+    const unsigned per = (nb_epot + gridDim.x - 1) / gridDim.x;
+    double s0 = 0.0;
+    for (unsigned k = threadIdx.x; k < per; k += kKick2Block) {
+        const unsigned j = blockIdx.x * per + k;
+        if (j < nb_epot) s0 += partial_epot[j];
+    }
+    block_sum3(s0, s1, s2, red);
+    const unsigned G = gridDim.x;
     if (threadIdx.x == 0) {
-        const double ekin = xmul(xmul(0.5, c.mass), sk);
-        const double epot = xmul(xmul(xmul(se, 4.0), c.epsilon), 0.5);
-        ctrl->epot_sum = se;
-        ctrl->pred_sum = sp;
-        ctrl->ekin = ekin; ctrl->epot = epot; ctrl->etot = xadd(ekin, epot);
-        HistEntry& h = hist[ctrl->hist_head % kHistCap];
-        h.ekin = ekin; h.epot = epot; h.step = ctrl->next_step; h.pad = 0;
-        ctrl->next_step += 1;
-        ctrl->hist_head += 1;
-        ctrl->steps_done += 1;
-        if (__longlong_as_double((long long)ctrl->maxdisp2) > c.disp_thresh) ctrl->stop = 1;
+        block_sums[blockIdx.x] = s0; block_sums[G + blockIdx.x] = s1; block_sums[2 * G + blockIdx.x] = s2;
+        __threadfence();
+        s_last = atomicAdd(&ctrl->ticket, 1u) == G - 1 ? 1u : 0u;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    double se = strided_sum_block(block_sums, G), sk = strided_sum_block(block_sums + G, G), sp = strided_sum_block(block_sums + 2 * G, G);
+    block_sum3(se, sk, sp, red);
+    if (KIND == 0) {
+        if (threadIdx.x == 0) {
+            ctrl->ticket = 0;
+            const bool due = __longlong_as_double((long long)ctrl->maxdisp2) > c.disp_thresh;
+            ctrl->maxdisp2 = 0ull;
+            publish_step(c, ctrl, hist, se, sk, sp, due, __longlong_as_double((long long)ctrl->vmax2));
+        }
+        return;
+    }
+    if (KIND == 2) {
+        if (threadIdx.x == 0) {
+            ctrl->ticket = 0;
+            ctrl->red[0] = se; ctrl->red[1] = sk; ctrl->red[2] = sp;
+            ctrl->red[3] = (__longlong_as_double((long long)ctrl->maxdisp2) > c.disp_thresh) ? 1.0 : 0.0;
+            ctrl->maxdisp2 = 0ull;
+        }
+        return;
+    }
+    if (threadIdx.x == 0) {
+        ctrl->ticket = 0;
+        s_tot[0] = se; s_tot[1] = sk; s_tot[2] = sp;
+        s_tot[3] = (__longlong_as_double((long long)ctrl->maxdisp2) > c.disp_thresh) ? 1.0 : 0.0;
         ctrl->maxdisp2 = 0ull;
-        const double vmax = sqrt(__longlong_as_double((long long)ctrl->vmax2));
-        ctrl->vmax_last = vmax;
-        ctrl->drift_bound += vmax * c.dt;
-        ctrl->vmax2 = 0ull;
+        // the neighbours' fastest-atom values of this step arrived with the halo the force kernel waited for;
+        // read them before my deposit releases the neighbours into the next step's push
+        s_nbv2 = fmax(ld_sys_f64(&sr.mine->nb_vmax2[0]), ld_sys_f64(&sr.mine->nb_vmax2[1]));
+    }
+    __syncthreads();
+    const unsigned long long seq = ctrl->red_seq + 1ull;      // (read by every thread before thread 0 stores it back below)
+    mailbox_allreduce(s_tot, s_g, s_dep, sr.mine, sr.peers, sr.rank, sr.world, seq);
+    if (threadIdx.x == 0) {
+        ctrl->red_seq = seq;
+        ctrl->red[0] = s_g[0]; ctrl->red[1] = s_g[1]; ctrl->red[2] = s_g[2]; ctrl->red[3] = s_g[3];
+        // pruned inner list: pairs of this device involve its own atoms and the two neighbours' boundary atoms, so the
+        // displacement bound advances by the fastest atom among the three devices
+        publish_step(c, ctrl, hist, s_g[0], s_g[1], s_g[2], s_g[3] > 0.0,
+                     fmax(__longlong_as_double((long long)ctrl->vmax2), s_nbv2));
     }
 }
 
@@ -490,49 +636,12 @@ slab_reduce_kernel(LJConst c, StepCtrl* __restrict__ ctrl,
     }
 }
 
-// ---- slab path over peer memory (NVLink loads/stores, no NCCL in the step loop) ----------------------
-__device__ __forceinline__ unsigned long long ld_sys_u64(const unsigned long long* p) {
-    unsigned long long v;
-#ifdef LJ_EMUL
-    v = ljemul::atomic_load_u64(p);
-#else
-    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-#endif
-    return v;
-}
-__device__ __forceinline__ void st_sys_u64(unsigned long long* p, unsigned long long v) {
-#ifdef LJ_EMUL
-    ljemul::atomic_store_u64(p, v);
-#else
-    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
-#endif
-}
-__device__ __forceinline__ double ld_sys_f64(const double* p) {
-    double v;
-#ifdef LJ_EMUL
-    v = ljemul::atomic_load_f64(p);
-#else
-    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
-#endif
-    return v;
-}
-// Spin until *flag >= seq; gives up after ~2 s (a peer died) so that no kernel can hang the device.
-__device__ __forceinline__ bool wait_flag(const unsigned long long* flag, unsigned long long seq, unsigned int* error) {
-    const long long t0 = clock64();
-    while (ld_sys_u64(flag) < seq) {
-        if (clock64() - t0 > 4000000000ll) { atomicExch(error, 1u); return false; }
-        __nanosleep(100);
-    }
-    __threadfence_system();
-    return true;
-}
-
 // Halo push: my two boundary layers are contiguous slot ranges; write them straight into the halo slots of
 // the ring neighbours' position arrays (peer pointers), then publish the step sequence in their mailboxes.
 __global__ void __launch_bounds__(256)
-halo_push_kernel(const StepCtrl* __restrict__ ctrl, const double4* __restrict__ pos, unsigned n, unsigned c_lo, unsigned c_hi,
+halo_push_kernel(StepCtrl* __restrict__ ctrl, const double4* __restrict__ pos, unsigned n, unsigned c_lo, unsigned c_hi,
                  double4* __restrict__ down_dst, double4* __restrict__ up_dst,
-                 Mailbox* down_mail, Mailbox* up_mail, unsigned long long seq, unsigned int* ticket) {
+                 Mailbox* down_mail, Mailbox* up_mail, unsigned int* ticket) {
     if (ctrl->stop) return;
     const unsigned total = c_lo + c_hi;
     for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < total; k += gridDim.x * blockDim.x) {
@@ -549,10 +658,45 @@ halo_push_kernel(const StepCtrl* __restrict__ ctrl, const double4* __restrict__ 
             down_mail->nb_vmax2[1] = v2;
             up_mail->nb_vmax2[0] = v2;
             __threadfence_system();
+            const unsigned long long seq = ctrl->halo_seq + 1ull;       // (only this block touches the counter)
+            ctrl->halo_seq = seq;
             st_sys_u64(&down_mail->halo_flag[1], seq);          // I am my lower neighbour's upper neighbour
             st_sys_u64(&up_mail->halo_flag[0], seq);
         }
     }
+}
+
+// Publication on the slab path (ljgpu_step_publish): the frame of positions in ORIGINAL atom order is cut into `world`
+// contiguous slices of S atoms; device r assembles slice r.  Every device scatters the atoms it owns straight into the
+// slice buffers of their owners over NVLink (8-byte peer stores), then tells every owner that its part is in; each owner
+// then copies its slice to the host over its own PCIe link (3 x 8 x N / world bytes per device instead of 24 N on each).
+struct PubTargets { double* slice[kMaxPeers]; Mailbox* mail[kMaxPeers]; };
+__global__ void __launch_bounds__(256)
+slab_publish_scatter_kernel(LJConst c, const double4* __restrict__ pos, const uint32_t* __restrict__ orig, unsigned S, unsigned nglobal,
+                            PubTargets tgt, int rank, int world, unsigned long long seq, unsigned int* ticket) {
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < c.n; i += gridDim.x * blockDim.x) {
+        const double4 p = pos[i];
+        const unsigned o = orig[i];
+        const unsigned d = o / S, off = o - d * S;
+        const unsigned len = min(S, nglobal - d * S);           // atoms of slice d (the last one may be shorter)
+        double* dst = tgt.slice[d];
+        dst[off] = wrap_coord(p.x, c.L, c.invL);
+        dst[len + off] = wrap_coord(p.y, c.L, c.invL);
+        dst[2 * (size_t)len + off] = wrap_coord(p.z, c.L, c.invL);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (atomicAdd(ticket, 1u) == gridDim.x - 1) {          // last block: every store of every block is fenced
+            *ticket = 0;
+            __threadfence_system();
+            for (int r = 0; r < world; ++r) st_sys_u64(&tgt.mail[r]->pub_flag[rank], seq);
+        }
+    }
+}
+// copy stream of a slice owner: wait until every device has scattered its atoms of publication `seq` into my slice
+__global__ void slab_publish_wait_kernel(Mailbox* mine, int world, unsigned long long seq) {
+    if ((int)threadIdx.x < world) wait_flag(&mine->pub_flag[threadIdx.x], seq, &mine->error);
 }
 
 // kick_drift_kernel with the halo push folded in (slab path over peer memory, LJGPU_SLAB_FUSED_PUSH=1): the threads
@@ -566,7 +710,7 @@ kick_drift_push_kernel(LJConst c, double dt, double a, StepCtrl* __restrict__ ct
                        double* __restrict__ vx, double* __restrict__ vy, double* __restrict__ vz,
                        const double* __restrict__ fx, const double* __restrict__ fy, const double* __restrict__ fz,
                        unsigned c_lo, unsigned c_hi, double4* __restrict__ down_dst, double4* __restrict__ up_dst,
-                       Mailbox* down_mail, Mailbox* up_mail, unsigned long long seq, unsigned int* ticket) {
+                       Mailbox* down_mail, Mailbox* up_mail, unsigned int* ticket) {
     __shared__ double red[32];
     __shared__ double red2[32];
     if (ctrl->stop) return;
@@ -586,77 +730,36 @@ kick_drift_push_kernel(LJConst c, double dt, double a, StepCtrl* __restrict__ ct
             down_mail->nb_vmax2[1] = v2;
             up_mail->nb_vmax2[0] = v2;
             __threadfence_system();
+            const unsigned long long seq = ctrl->halo_seq + 1ull;
+            ctrl->halo_seq = seq;
             st_sys_u64(&down_mail->halo_flag[1], seq);
             st_sys_u64(&up_mail->halo_flag[0], seq);
         }
     }
 }
 
-// Local reductions + all-reduce through the mailboxes + publication, one launch.
-//   what: 0 = full step, 1 = constructor (epot only), 2 = predict (pred_sum only)
+// Local reductions + all-reduce through the mailboxes + publication, one launch: the constructor's energy
+// (what = 1, epot only) and the predicted kinetic sum (what = 2).  The per-step variant lives in kick2_kernel<true>.
 __global__ void __launch_bounds__(kFinalizeThreads)
-slab_exchange_kernel(LJConst c, StepCtrl* __restrict__ ctrl, HistEntry* __restrict__ hist, int what,
+slab_exchange_kernel(LJConst c, StepCtrl* __restrict__ ctrl, int what,
                      const double* __restrict__ partial_epot, unsigned nb_epot,
-                     const double* __restrict__ partial_ekin, const double* __restrict__ partial_pred, unsigned nb_kick,
-                     Mailbox* mine, Mailbox* const* __restrict__ peers, int rank, int world, unsigned long long seq) {
+                     const double* __restrict__ partial_pred, unsigned nb_kick, SlabRed sr) {
     __shared__ double red[32];
-    __shared__ double tot[4];
-    __shared__ double nbv2;
-    if (what == 0 && ctrl->stop) return;
+    __shared__ double tot[4], g[4], dep[kMaxPeers * 4];
     double se = strided_sum(partial_epot, nb_epot);
-    double sk = partial_ekin ? strided_sum(partial_ekin, nb_kick) : 0.0;
     double sp = strided_sum(partial_pred, nb_kick);
     se = block_sum(se, red);
-    sk = block_sum(sk, red);
     sp = block_sum(sp, red);
-    const unsigned par = (unsigned)(seq & 1ull);
-    if (threadIdx.x == 0) {
-        tot[0] = se; tot[1] = sk; tot[2] = sp;
-        tot[3] = (__longlong_as_double((long long)ctrl->maxdisp2) > c.disp_thresh) ? 1.0 : 0.0;
-        ctrl->maxdisp2 = 0ull;
-        // the neighbours' fastest-atom values of this step arrived with the halo the force kernel waited for;
-        // read them before my deposit releases the neighbours into the next step's push
-        nbv2 = fmax(ld_sys_f64(&mine->nb_vmax2[0]), ld_sys_f64(&mine->nb_vmax2[1]));
-    }
+    if (threadIdx.x == 0) { tot[0] = se; tot[1] = 0.0; tot[2] = sp; tot[3] = 0.0; }
     __syncthreads();
-    // thread r deposits my four sums in peer r's mailbox (its own included), fences, raises the flag
-    if ((int)threadIdx.x < world) {
-        Mailbox* dst = peers[threadIdx.x];
-        double* slot = dst->red[par][rank];
-        slot[0] = tot[0]; slot[1] = tot[1]; slot[2] = tot[2]; slot[3] = tot[3];
-        __threadfence_system();
-        st_sys_u64(&dst->red_flag[par][rank], seq);
-        // ... and waits for peer r's deposit in mine
-        wait_flag(&mine->red_flag[par][threadIdx.x], seq, &mine->error);
-    }
-    __syncthreads();                                       // every deposit has arrived before anyone reads
-    __shared__ double dep[kMaxPeers * 4];
-    if ((int)threadIdx.x < world * 4) dep[threadIdx.x] = ld_sys_f64(&mine->red[par][threadIdx.x >> 2][threadIdx.x & 3]);
-    __syncthreads();
+    const unsigned long long seq = ctrl->red_seq + 1ull;
+    mailbox_allreduce(tot, g, dep, sr.mine, sr.peers, sr.rank, sr.world, seq);
     if (threadIdx.x == 0) {
-        double g[4] = {0.0, 0.0, 0.0, 0.0};
-        for (int r = 0; r < world; ++r)                    // rank order on every device: identical sums everywhere
-            for (int k = 0; k < 4; ++k) g[k] += dep[r * 4 + k];
+        ctrl->red_seq = seq;
         ctrl->red[0] = g[0]; ctrl->red[1] = g[1]; ctrl->red[2] = g[2]; ctrl->red[3] = g[3];
         if (what == 2) { ctrl->pred_sum = g[2]; return; }
-        const double epot = xmul(xmul(xmul(g[0], 4.0), c.epsilon), 0.5);
         ctrl->epot_sum = g[0];
-        if (what == 1) { ctrl->epot = epot; return; }
-        const double ekin = xmul(xmul(0.5, c.mass), g[1]);
-        ctrl->pred_sum = g[2];
-        ctrl->ekin = ekin; ctrl->epot = epot; ctrl->etot = xadd(ekin, epot);
-        HistEntry& h = hist[ctrl->hist_head % kHistCap];
-        h.ekin = ekin; h.epot = epot; h.step = ctrl->next_step; h.pad = 0;
-        ctrl->next_step += 1;
-        ctrl->hist_head += 1;
-        ctrl->steps_done += 1;
-        if (g[3] > 0.0) ctrl->stop = 1;
-        // pruned inner list: pairs of this device involve its own atoms and the two neighbours' boundary
-        // atoms, so the displacement bound advances by the fastest atom among the three devices
-        const double vmax = sqrt(fmax(__longlong_as_double((long long)ctrl->vmax2), nbv2));
-        ctrl->vmax_last = vmax;
-        ctrl->drift_bound += vmax * c.dt;
-        ctrl->vmax2 = 0ull;
+        ctrl->epot = xmul(xmul(xmul(g[0], 4.0), c.epsilon), 0.5);
     }
 }
 
@@ -745,6 +848,48 @@ import_state_kernel(unsigned n, const double* __restrict__ x, const double* __re
     if (i >= n) return;
     pos[i] = make_double4(x[i], y[i], z[i], 0.0);
     orig[i] = i;
+}
+
+// values of the device's atoms to their original indices (query kernels of integer per-atom data)
+__global__ void __launch_bounds__(kBlock)
+scatter_u32_kernel(unsigned n, const uint32_t* __restrict__ src, const uint32_t* __restrict__ orig, uint32_t* __restrict__ out) {
+    const unsigned i = blockIdx.x * kBlock + threadIdx.x;
+    if (i < n) out[orig[i]] = src[i];
+}
+
+// Neighbour-count probe: cell key (.cpp:468-476) of every atom of the whole system from already wrapped positions in
+// original order; vals = original index.
+__global__ void __launch_bounds__(kBlock)
+probe_key_kernel(LJConst c, const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
+                 double4* __restrict__ pos_out, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    const unsigned i = blockIdx.x * kBlock + threadIdx.x;
+    if (i >= c.n) return;
+    const double px = x[i], py = y[i], pz = z[i];
+    pos_out[i] = make_double4(px, py, pz, 0.0);
+    const unsigned ix = cell_coord(px, c.cell_edge, c.nc), iy = cell_coord(py, c.cell_edge, c.nc), iz = cell_coord(pz, c.cell_edge, c.nc);
+    keys[i] = iz * c.nc * c.nc + iy * c.nc + ix;
+    vals[i] = i;
+}
+__global__ void __launch_bounds__(kBlock)
+gather_pos_kernel(unsigned n, const uint32_t* __restrict__ perm, const double4* __restrict__ in, double4* __restrict__ out) {
+    const unsigned i = blockIdx.x * kBlock + threadIdx.x;
+    if (i < n) out[i] = in[perm[i]];
+}
+
+// FP64 roofline denominator, measured in place (ljgpu_measure_fp64_peak): eight independent DFMA chains per thread.
+__global__ void __launch_bounds__(256)
+fp64_peak_kernel(double* __restrict__ out, int iters, double a, double b) {
+    double acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = threadIdx.x * 1e-9 + k;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = fma(acc[k], a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += acc[k];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
 // K8  speed histogram, graphwidget.cpp:225-230: bin = min((int)(|v| / vmax * nbins), nbins-1),

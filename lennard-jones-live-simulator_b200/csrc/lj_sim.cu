@@ -10,6 +10,7 @@
 #include <chrono>
 #include <cstdlib>
 #include <cmath>
+#include <cstddef>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -38,7 +39,7 @@ struct LjError : std::runtime_error {
 
 inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
 
-enum Stage { ST_PREDICT = 0, ST_KICK_DRIFT, ST_GHOST, ST_FORCE, ST_KICK2, ST_REBUILD, ST_HALO, ST_COUNT };
+enum Stage { ST_PREDICT = 0, ST_KICK_DRIFT, ST_FORCE_PRUNE, ST_FORCE, ST_KICK2, ST_REBUILD, ST_HALO, ST_COUNT };
 
 template <class T>
 void dfree(T*& p) { if (p) { cudaFree(p); p = nullptr; } }
@@ -72,11 +73,16 @@ struct Slab {
     Mailbox* peer_mail[kMaxPeers] = {nullptr};
     Mailbox** d_peer_mail = nullptr;      // device copy of the pointer table
     double4* peer_pos[2] = {nullptr, nullptr};    // position arrays of my lower / upper neighbour
-    void* ipc_opened[kMaxPeers + 2] = {nullptr};  // mappings to close
+    void* ipc_opened[3 * kMaxPeers + 2] = {nullptr};  // mappings to close
     int n_ipc_opened = 0;
     unsigned nb_n[2] = {0, 0}, nb_hlo[2] = {0, 0};   // owned atoms and lower-halo size of the two neighbours
-    unsigned long long halo_seq = 0, red_seq = 0;
+    unsigned long long pub_seq = 0;
     unsigned int* push_ticket = nullptr;
+    // publication (ljgpu_step_publish): my slice of the original-order frame, two buffers; the peers' slices
+    unsigned pub_S = 0;                    // atoms per slice: ceil(N / world)
+    double* pub_slice[2] = {nullptr, nullptr};
+    double* peer_pub[2][kMaxPeers] = {{nullptr}};
+    unsigned int* pub_ticket = nullptr;
 };
 
 } // namespace
@@ -153,13 +159,18 @@ struct ljgpu_sim {
     double prune_skin = 0.0; unsigned prune_interval = 8, since_prune = 0;
 
     // reductions
-    double *partial_epot = nullptr, *partial_ekin = nullptr, *partial_pred = nullptr;
+    double *partial_epot = nullptr, *kick_sums = nullptr, *partial_pred = nullptr;     // kick_sums: [3][blocks of kick2]
     unsigned nb_force = 0;
     double* apf[3] = {nullptr, nullptr, nullptr}; unsigned nsplit = 1, jchunk = 0;
 
     StepCtrl* ctrl = nullptr; StepCtrl* h_ctrl = nullptr;
     HistEntry* hist = nullptr;
 
+    // scratch of the neighbour-count probe (allocated on first use): the probe bins a COPY of the published positions,
+    // so it never touches the integrator's own binning, lists or displacement accumulators
+    double4 *probe_pos = nullptr, *probe_sorted = nullptr;
+    uint32_t *probe_keys = nullptr, *probe_vals = nullptr, *probe_cstart = nullptr, *probe_cend = nullptr, *probe_ccount = nullptr;
+    void probe_neighbor_counts(double cut2, int inclusive, uint32_t* host_out);
     // staging for queries
     double* out3 = nullptr; uint32_t* out_u32 = nullptr; unsigned long long* hist_counts = nullptr;
     // asynchronous publication of positions (ljgpu_step_publish): staging buffers, copy stream, events
@@ -267,7 +278,8 @@ struct ljgpu_sim {
     void halo_exchange();
     void allreduce_red();
     void setup_p2p();
-    void slab_finalize(int what, unsigned nb_epot, const double* pekin, unsigned nb_kick);
+    void slab_finalize(int what, unsigned nb_epot, unsigned nb_kick);
+    SlabRed slab_red() const { return SlabRed{slab.mail, slab.d_peer_mail, slab.rank, slab.world}; }
     void rebuild();
     void build_list();
     void launch_force(bool timed);
@@ -299,8 +311,9 @@ ljgpu_sim::~ljgpu_sim() {
     dfree(orig); dfree(orig_alt); dfree(keys); dfree(vals);
     dfree(cstart); dfree(cend); dfree(ccount);
     dfree(nl); dfree(nl_count); dfree(nl_in); dfree(nl_in_count); dfree(tsrc); dfree(toff);
-    dfree(partial_epot); dfree(partial_ekin); dfree(partial_pred);
+    dfree(partial_epot); dfree(kick_sums); dfree(partial_pred);
     dfree(ctrl); dfree(hist); dfree(out3); dfree(out_u32); dfree(hist_counts);
+    dfree(probe_pos); dfree(probe_sorted); dfree(probe_keys); dfree(probe_vals); dfree(probe_cstart); dfree(probe_cend); dfree(probe_ccount);
     if (st_copy) { cudaStreamSynchronize(st_copy); cudaStreamDestroy(st_copy); }
     for (int b = 0; b < 2; ++b) {
         dfree(pub3[b]);
@@ -310,7 +323,7 @@ ljgpu_sim::~ljgpu_sim() {
     for (int k = 0; k < 2; ++k) { dfree(slab.sendbuf[k]); dfree(slab.recvbuf[k]); dfree(slab.hcount[k]); dfree(slab.hoff[k]); }
     dfree(slab.xchg);
     for (int k = 0; k < slab.n_ipc_opened; ++k) cudaIpcCloseMemHandle(slab.ipc_opened[k]);
-    dfree(slab.mail); dfree(slab.d_peer_mail); dfree(slab.push_ticket);
+    dfree(slab.mail); dfree(slab.d_peer_mail); dfree(slab.push_ticket); dfree(slab.pub_ticket); dfree(slab.pub_slice[0]); dfree(slab.pub_slice[1]);
     if (slab.h_xchg) cudaFreeHost(slab.h_xchg);
     if (h_ctrl) cudaFreeHost(h_ctrl);
     if (h_scalar) cudaFreeHost(h_scalar);
@@ -383,7 +396,7 @@ void ljgpu_sim::allocate() {
     CK(cudaMalloc(&out3, 3 * N * 8));
     CK(cudaMalloc(&out_u32, N * 4));
     CK(cudaMalloc(&hist_counts, kMaxBins * sizeof(unsigned long long)));
-    CK(cudaMalloc(&partial_ekin, (size_t)nbmax * 8));
+    CK(cudaMalloc(&kick_sums, (size_t)3 * cdiv(A, kKick2Block) * 8));
     CK(cudaMalloc(&partial_pred, (size_t)nbmax * 8));
 
     if (list_mode()) {
@@ -402,7 +415,7 @@ void ljgpu_sim::allocate() {
         bxd = kTileBX; byd = kTileBY; bzd = kTileBZ;
         auto count_blocks = [&] { nbx = cdiv(nc, bxd); nby = cdiv(nc, byd); nbz = cdiv(nhz, bzd); nblocks_tile = nbx * nby * nbz; };
         count_blocks();
-        while (nblocks_tile < 6u * 148u && bxd * byd * bzd > 1) {
+        while (nblocks_tile < 2u * 148u && bxd * byd * bzd > 1) {     // (one persistent CTA per SM streams its bricks: two or more bricks per CTA keep its ring busy)
             if (bxd > 1 && bxd >= byd && bxd >= bzd) --bxd; else if (byd > 1 && byd >= bzd) --byd; else --bzd;
             count_blocks();
         }
@@ -453,7 +466,8 @@ static unsigned host_layer(double z, double L, double invL, double edge, unsigne
 
 void ljgpu_sim::upload_state(const double* x, const double* y, const double* z,
                              const double* vx, const double* vy, const double* vz) {
-    CK(cudaMemsetAsync(ctrl, 0, sizeof(StepCtrl), st));
+    // everything but the slab sequence counters at the end of the block: the peers' mailboxes remember the sequence numbers
+    CK(cudaMemsetAsync(ctrl, 0, offsetof(StepCtrl, halo_seq), st));
     pred_valid = false;
     since_rebuild = 0;
     if (!slab.on) {
@@ -619,14 +633,13 @@ void ljgpu_sim::halo_exchange() {
     auto& A = ljnccl::api();
     cudaEvent_t ev = stage_begin();
     if (slab.p2p) {
-        ++slab.halo_seq;
         // my first layer -> lower neighbour's UPPER halo slots; my last layer -> upper neighbour's LOWER halo slots
         double4* down_dst = slab.peer_pos[0] + slab.nb_n[0] + slab.nb_hlo[0];
         double4* up_dst = slab.peer_pos[1] + slab.nb_n[1];
         const unsigned total = slab.c_lo + slab.c_hi;
         const unsigned blocks = std::max(1u, std::min(cdiv(total, 256), 296u));
         halo_push_kernel<<<blocks, 256, 0, st>>>(ctrl, pos, n, slab.c_lo, slab.c_hi, down_dst, up_dst,
-                                                 slab.peer_mail[slab.down], slab.peer_mail[slab.up], slab.halo_seq, slab.push_ticket);
+                                                 slab.peer_mail[slab.down], slab.peer_mail[slab.up], slab.push_ticket);
         check_launch("halo_push");
         stage_end(ST_HALO, ev);
         return;
@@ -644,17 +657,16 @@ void ljgpu_sim::allreduce_red() {
     NCK(ljnccl::api().AllReduce(ctrl->red, ctrl->red, 4, ljnccl::kFloat64, ljnccl::kSum, slab.comm, st));
 }
 
-// Slab path: local sums -> global sums -> publication.  Over peer memory this is ONE kernel (mailbox
-// all-reduce inside); on the NCCL fallback it is reduce kernel + ncclAllReduce + publish kernel.
-void ljgpu_sim::slab_finalize(int what, unsigned nb_epot, const double* pekin, unsigned nb_kick) {
+// Slab path, constructor (what = 1: epot) and prediction (what = 2: pred_sum): local sums -> global sums -> publication.
+// Over peer memory this is ONE kernel (mailbox all-reduce inside); on the NCCL fallback it is reduce kernel +
+// ncclAllReduce + publish kernel.  (The per-step variant is part of kick2_kernel.)
+void ljgpu_sim::slab_finalize(int what, unsigned nb_epot, unsigned nb_kick) {
     if (slab.p2p) {
-        ++slab.red_seq;
-        slab_exchange_kernel<<<1, kFinalizeThreads, 0, st>>>(c, ctrl, hist, what, partial_epot, nb_epot, pekin, partial_pred, nb_kick,
-                                                             slab.mail, slab.d_peer_mail, slab.rank, slab.world, slab.red_seq);
+        slab_exchange_kernel<<<1, kFinalizeThreads, 0, st>>>(c, ctrl, what, partial_epot, nb_epot, partial_pred, nb_kick, slab_red());
         check_launch("slab_exchange");
         return;
     }
-    slab_reduce_kernel<<<1, kFinalizeThreads, 0, st>>>(c, ctrl, partial_epot, nb_epot, pekin, partial_pred, nb_kick);
+    slab_reduce_kernel<<<1, kFinalizeThreads, 0, st>>>(c, ctrl, partial_epot, nb_epot, nullptr, partial_pred, nb_kick);
     check_launch("slab_reduce");
     allreduce_red();
     slab_publish_kernel<<<1, 32, 0, st>>>(c, ctrl, hist, what);
@@ -669,11 +681,19 @@ void ljgpu_sim::setup_p2p() {
     CK(cudaMemset(slab.mail, 0, sizeof(Mailbox)));
     CK(cudaMalloc(&slab.push_ticket, sizeof(unsigned)));
     CK(cudaMemset(slab.push_ticket, 0, sizeof(unsigned)));
-    struct Handles { cudaIpcMemHandle_t pos, mail; };
-    static_assert(sizeof(Handles) == 128, "two 64-byte IPC handles");
+    CK(cudaMalloc(&slab.pub_ticket, sizeof(unsigned)));
+    CK(cudaMemset(slab.pub_ticket, 0, sizeof(unsigned)));
+    slab.pub_S = cdiv(nglobal, slab.world);
+    for (int b = 0; b < 2; ++b) {
+        CK(cudaMalloc(&slab.pub_slice[b], (size_t)3 * slab.pub_S * 8));
+        CK(cudaMemset(slab.pub_slice[b], 0, (size_t)3 * slab.pub_S * 8));
+    }
+    struct Handles { cudaIpcMemHandle_t pos, mail, pub[2]; };
+    static_assert(sizeof(Handles) == 256, "four 64-byte IPC handles");
     Handles mine;
     CK(cudaIpcGetMemHandle(&mine.pos, pos));
     CK(cudaIpcGetMemHandle(&mine.mail, slab.mail));
+    for (int b = 0; b < 2; ++b) CK(cudaIpcGetMemHandle(&mine.pub[b], slab.pub_slice[b]));
     Handles* d_all = nullptr;
     CK(cudaMalloc(&d_all, sizeof(Handles) * (slab.world + 1)));
     CK(cudaMemcpy(d_all + slab.world, &mine, sizeof(Handles), cudaMemcpyHostToDevice));
@@ -688,8 +708,11 @@ void ljgpu_sim::setup_p2p() {
         slab.ipc_opened[slab.n_ipc_opened++] = p;
         return p;
     };
-    for (int r = 0; r < slab.world; ++r)
+    for (int r = 0; r < slab.world; ++r) {
         slab.peer_mail[r] = r == slab.rank ? slab.mail : static_cast<Mailbox*>(open(all[r].mail));
+        for (int b = 0; b < 2; ++b)
+            slab.peer_pub[b][r] = r == slab.rank ? slab.pub_slice[b] : static_cast<double*>(open(all[r].pub[b]));
+    }
     slab.peer_pos[0] = static_cast<double4*>(open(all[slab.down].pos));
     slab.peer_pos[1] = slab.up == slab.down ? slab.peer_pos[0] : static_cast<double4*>(open(all[slab.up].pos));
     CK(cudaMalloc(&slab.d_peer_mail, sizeof(Mailbox*) * kMaxPeers));
@@ -758,7 +781,7 @@ template <int MODE, bool UNIT_SIGMA>
 static void launch_tile2(ljgpu_sim* s, int guarded) {
     TileArgs a{s->pos, s->nl, s->nl_count, s->prune_skin > 0.0 ? s->nl_in : nullptr, s->nl_in_count,
                s->f[0], s->f[1], s->f[2], s->partial_epot, s->ctrl, s->capq, s->tcap, s->tile_slots, s->tile_ipb,
-               s->slab.p2p ? s->slab.mail : nullptr, s->slab.halo_seq};
+               s->slab.p2p ? s->slab.mail : nullptr};
     const unsigned grid = std::max(1u, std::min(s->nblocks_tile, s->tile_grid_ctas[MODE][UNIT_SIGMA ? 1 : 0]));
     tile_kernel<MODE, UNIT_SIGMA><<<grid, kBrickThreads, tile_smem(s), s->st>>>(s->c, s->tile_grid(), a, guarded);
     s->check_launch("tile_kernel");
@@ -862,7 +885,7 @@ void ljgpu_sim::launch_force(bool timed) {
 
 void ljgpu_sim::finalize_epot_only() {
     if (slab.on) {
-        slab_finalize(1, nb_force, nullptr, 0);
+        slab_finalize(1, nb_force, 0);
     } else {
         init_finalize_kernel<<<1, kFinalizeThreads, 0, st>>>(c, ctrl, partial_epot, nb_force);
         check_launch("init_finalize");
@@ -883,7 +906,7 @@ void ljgpu_sim::launch_predict(double dt) {
     predict_kernel<<<nb_atoms(), kBlock, 0, st>>>(n, a, v[0], v[1], v[2], f[0], f[1], f[2], partial_pred);
     check_launch("predict");
     if (slab.on) {
-        slab_finalize(2, 0, nullptr, nb_atoms());
+        slab_finalize(2, 0, nb_atoms());
     } else {
         predict_finalize_kernel<<<1, kFinalizeThreads, 0, st>>>(ctrl, partial_pred, nb_atoms());
         check_launch("predict_finalize");
@@ -901,13 +924,12 @@ void ljgpu_sim::enqueue_step(bool prune_now, double dt) {
     static const bool fused_push_env = std::getenv("LJGPU_SLAB_FUSED_PUSH") != nullptr;
     const bool fused_push = fused_push_env && slab.on && slab.p2p && list_mode();
     if (fused_push) {
-        ++slab.halo_seq;
         double4* down_dst = slab.peer_pos[0] + slab.nb_n[0] + slab.nb_hlo[0];
         double4* up_dst = slab.peer_pos[1] + slab.nb_n[1];
         kick_drift_push_kernel<<<nb_atoms(), kBlock, 0, st>>>(c, dt, a, ctrl, pos, dij[0], dij[1], dij[2],
                                                               v[0], v[1], v[2], f[0], f[1], f[2],
                                                               slab.c_lo, slab.c_hi, down_dst, up_dst,
-                                                              slab.peer_mail[slab.down], slab.peer_mail[slab.up], slab.halo_seq, slab.push_ticket);
+                                                              slab.peer_mail[slab.down], slab.peer_mail[slab.up], slab.push_ticket);
     } else if (list_mode())
         kick_drift_kernel<true><<<nb_atoms(), kBlock, 0, st>>>(c, dt, a, ctrl, pos, dij[0], dij[1], dij[2],
                                                                v[0], v[1], v[2], f[0], f[1], f[2]);
@@ -922,19 +944,24 @@ void ljgpu_sim::enqueue_step(bool prune_now, double dt) {
         launch_tile<TILE_FORCE_PRUNE>(this, 1);
         prune_commit_kernel<<<1, 1, 0, st>>>(ctrl);
         check_launch("prune_commit");
-        stage_end(ST_GHOST, pv);                        // reported as ms_ghost / n_ghost: force passes that also pruned
+        stage_end(ST_FORCE_PRUNE, pv);
     } else {
         launch_force(true);
     }
     ev = stage_begin();
-    kick2_kernel<<<nb_atoms(), kBlock, 0, st>>>(c, a, ctrl, v[0], v[1], v[2], f[0], f[1], f[2], partial_ekin, partial_pred);
-    check_launch("kick2");
-    if (slab.on) {
-        slab_finalize(0, nb_force, partial_ekin, nb_atoms());
+    const unsigned nb2 = std::max(1u, cdiv(n, kKick2Block));
+    if (!slab.on) {
+        kick2_kernel<0><<<nb2, kKick2Block, 0, st>>>(c, a, ctrl, hist, v[0], v[1], v[2], f[0], f[1], f[2], partial_epot, nb_force, kick_sums, SlabRed{});
+        check_launch("kick2");
+    } else if (slab.p2p) {
+        kick2_kernel<1><<<nb2, kKick2Block, 0, st>>>(c, a, ctrl, hist, v[0], v[1], v[2], f[0], f[1], f[2], partial_epot, nb_force, kick_sums, slab_red());
+        check_launch("kick2");
     } else {
-        step_finalize_kernel<<<1, kFinalizeThreads, 0, st>>>(c, ctrl, hist, partial_epot, nb_force,
-                                                             partial_ekin, partial_pred, nb_atoms());
-        check_launch("step_finalize");
+        kick2_kernel<2><<<nb2, kKick2Block, 0, st>>>(c, a, ctrl, hist, v[0], v[1], v[2], f[0], f[1], f[2], partial_epot, nb_force, kick_sums, SlabRed{});
+        check_launch("kick2");
+        allreduce_red();
+        slab_publish_kernel<<<1, 32, 0, st>>>(c, ctrl, hist, 0);
+        check_launch("slab_publish");
     }
     stage_end(ST_KICK2, ev);
 }
@@ -943,9 +970,12 @@ ljgpu_sim::GraphKey ljgpu_sim::graph_key(bool prune_now, double dt) const {
     GraphKey k;
     std::memset(&k, 0, sizeof k);                      // padding included: keys are compared bytewise
     const void* ptrs[20] = {pos, v[0], v[1], v[2], f[0], f[1], f[2], dij[0], dij[1], dij[2],
-                            nl, nl_in, nl_count, nl_in_count, tsrc, toff, nullptr, nullptr, nullptr, nullptr};
+                            nl, nl_in, nl_count, nl_in_count, tsrc, toff,
+                            slab.p2p ? (const void*)(slab.peer_pos[0] + slab.nb_n[0] + slab.nb_hlo[0]) : nullptr,     // where my halo pushes land
+                            slab.p2p ? (const void*)(slab.peer_pos[1] + slab.nb_n[1]) : nullptr, nullptr, nullptr};
     std::memcpy(k.ptr, ptrs, sizeof ptrs);
     k.shape[0] = n; k.shape[1] = tile_grid_ctas[TILE_FORCE_LIST][1]; k.shape[2] = tcap; k.shape[3] = capq; k.shape[4] = nblocks_tile; k.shape[5] = nb_force; k.shape[6] = tile_slots; k.shape[7] = tile_ipb;
+    k.shape[8] = slab.c_lo; k.shape[9] = slab.c_hi;
     k.dt = dt; k.gen = graph_gen; k.prune = prune_now ? 1 : 0;
     return k;
 }
@@ -968,7 +998,7 @@ void ljgpu_sim::launch_step(double dt) {
     static const bool no_graph = std::getenv("LJGPU_NO_GRAPH") != nullptr;
     bool timed_step = false;
     if (prof) { timed_step = (prof_tick++ % prof_every) == 0; }
-    if (timed_step || slab.on || no_graph) {
+    if (timed_step || (slab.on && !slab.p2p) || no_graph) {      // (the NCCL step loop is not captured)
         HostTrace::Scope hs(htrace, HostTrace::ENQUEUE);
         prof_this_step = timed_step || !prof;          // slab / no-graph steps that are not sampled carry no event records
         enqueue_step(prune_now, dt);
@@ -979,12 +1009,23 @@ void ljgpu_sim::launch_step(double dt) {
     const GraphKey key = graph_key(prune_now, dt);
     StepGraph* hit = nullptr;
     for (auto& e : graphs) if (e.key == key) { hit = &e; break; }
+    cudaGraphExec_t recycle = nullptr;                   // an executable graph of the same shape whose parameters can be updated in place
     if (!hit) {
         if (graphs.size() >= 12) {                    // evict the least recently used
-            size_t lru = 0;
-            for (size_t k = 1; k < graphs.size(); ++k) if (graphs[k].used < graphs[lru].used) lru = k;
-            cudaGraphExecDestroy(graphs[lru].exec);
+            size_t lru = graphs.size();
+            for (size_t k = 0; k < graphs.size(); ++k)      // prefer one of the same kind (plain / pruning): same topology
+                if (graphs[k].key.prune == key.prune && (lru == graphs.size() || graphs[k].used < graphs[lru].used)) lru = k;
+            if (lru == graphs.size()) {
+                lru = 0;
+                for (size_t k = 1; k < graphs.size(); ++k) if (graphs[k].used < graphs[lru].used) lru = k;
+                cudaGraphExecDestroy(graphs[lru].exec);
+            } else {
+                recycle = graphs[lru].exec;
+            }
             graphs.erase(graphs.begin() + (long)lru);
+        } else if (slab.on) {                          // slabs: every re-binning changes counts baked into the launches - keep two graphs, update them
+            for (size_t k = 0; k < graphs.size(); ++k)
+                if (graphs[k].key.prune == key.prune) { recycle = graphs[k].exec; graphs.erase(graphs.begin() + (long)k); break; }
         }
         graphs.emplace_back();
         hit = &graphs.back();
@@ -999,9 +1040,14 @@ void ljgpu_sim::launch_step(double dt) {
         CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
         cudaGraph_t graph = nullptr;
         try { enqueue_step(prune_now, dt); }
-        catch (...) { cudaStreamEndCapture(st, &graph); if (graph) cudaGraphDestroy(graph); throw; }
+        catch (...) { cudaStreamEndCapture(st, &graph); if (graph) cudaGraphDestroy(graph); if (recycle) cudaGraphExecDestroy(recycle); throw; }
         CK(cudaStreamEndCapture(st, &graph));
-        CK(cudaGraphInstantiate(&g.exec, graph, 0));
+        if (recycle) {                                 // same kernels, new arguments: far cheaper than a fresh instantiation
+            cudaGraphExecUpdateResultInfo info;
+            if (cudaGraphExecUpdate(recycle, graph, &info) == cudaSuccess) g.exec = recycle;
+            else { cudaGetLastError(); cudaGraphExecDestroy(recycle); }
+        }
+        if (!g.exec) CK(cudaGraphInstantiate(&g.exec, graph, 0));
         cudaGraphDestroy(graph);
         g.kernels = launches - l0;
         for (int k = 0; k < ST_COUNT; ++k) { g.cnt[k] = cnt[k] - cnt0[k]; cnt[k] = cnt0[k]; }
@@ -1038,13 +1084,60 @@ void ljgpu_sim::run_steps(unsigned first, unsigned nsteps, double dt) {
             fetch_ctrl();
         }
         const unsigned done = h_ctrl->steps_done;
-        if (prune_skin > 0.0 && h_ctrl->vmax_last > 0.0)     // steps until the fastest atom has covered s_in/2, with margin
-            prune_interval = std::max(1u, (unsigned)(0.85 * c.prune_half / (h_ctrl->vmax_last * dt)));
+        if (prune_skin > 0.0 && h_ctrl->vmax_last * std::fabs(dt) > 0.0)     // steps until the fastest atom has covered s_in/2, with margin
+            prune_interval = (unsigned)std::max(1.0, std::min(1.0e6, 0.85 * c.prune_half / (h_ctrl->vmax_last * std::fabs(dt))));
         step += done; remaining -= done; steps += done; since_rebuild += done;
         if (done) dirty_since_rebuild = true;
         if (h_ctrl->stop) { HostTrace::Scope hs(htrace, HostTrace::REBUILD); rebuild(); }
         else if (done != batch) throw LjError(LJGPU_ESTATE, "step batch ended early without a rebuild request");
     }
+}
+
+// Neighbour-count parity probe (include/ljgpu.h): bins a copy of the published (wrapped) positions of the WHOLE
+// system with the reference's cell assignment and counts with the reference's uncontracted comparisons.  The
+// integrator's own state is only read.  On slabs every device first assembles the whole system (collective).
+void ljgpu_sim::probe_neighbor_counts(double cut2, int inclusive, uint32_t* host_out) {
+    const size_t N = nglobal;
+    const unsigned nbN = std::max(1u, cdiv(N, kBlock));
+    if (!list_mode()) {
+        count_allpairs_kernel<<<nb_atoms(), kBlock, 0, st>>>(c, pos, orig, cut2, inclusive, out_u32);
+        check_launch("neighbor_count");
+        CK(cudaMemcpyAsync(host_out, out_u32, N * 4, cudaMemcpyDeviceToHost, st));
+        sync();
+        return;
+    }
+    const unsigned ncell_g = nc * nc * nc;
+    if (!probe_pos) {
+        CK(cudaMalloc(&probe_pos, N * sizeof(double4))); CK(cudaMalloc(&probe_sorted, N * sizeof(double4)));
+        CK(cudaMalloc(&probe_keys, N * 4)); CK(cudaMalloc(&probe_vals, N * 4));
+        CK(cudaMalloc(&probe_cstart, (size_t)ncell_g * 4)); CK(cudaMalloc(&probe_cend, (size_t)ncell_g * 4)); CK(cudaMalloc(&probe_ccount, (size_t)ncell_g * 4));
+    }
+    // published positions in original order (slab: summed over the devices, every atom is owned by exactly one)
+    if (slab.on) CK(cudaMemsetAsync(out3, 0, 3 * N * 8, st));
+    if (n) {
+        export_positions_kernel<<<nb_atoms(), kBlock, 0, st>>>(c, pos, orig, out3, out3 + N, out3 + 2 * N);
+        check_launch("export");
+    }
+    if (slab.on) NCK(ljnccl::api().AllReduce(out3, out3, 3 * N, ljnccl::kFloat64, ljnccl::kSum, slab.comm, st));
+    LJConst cg = c;                     // the whole box, one device's view
+    cg.n = (unsigned)N; cg.slab = 0; cg.zlo = 0; cg.nzl = nc;
+    probe_key_kernel<<<nbN, kBlock, 0, st>>>(cg, out3, out3 + N, out3 + 2 * N, probe_pos, probe_keys, probe_vals);
+    check_launch("probe_key");
+    int bits = 1; while ((1ull << bits) < (unsigned long long)ncell_g) ++bits;
+    launches += radix_sort_pairs(probe_keys, probe_vals, N, bits, scr, st);
+    CK(cudaMemsetAsync(probe_cstart, 0, (size_t)ncell_g * 4, st));
+    CK(cudaMemsetAsync(probe_cend, 0, (size_t)ncell_g * 4, st));
+    cell_bounds_kernel<<<nbN, kBlock, 0, st>>>((unsigned)N, probe_keys, probe_cstart, probe_cend);
+    check_launch("cell_bounds");
+    cell_count_kernel<<<cdiv(ncell_g, kBlock), kBlock, 0, st>>>(ncell_g, probe_cstart, probe_cend, probe_ccount);
+    check_launch("cell_count");
+    gather_pos_kernel<<<nbN, kBlock, 0, st>>>((unsigned)N, probe_vals, probe_pos, probe_sorted);
+    check_launch("gather_pos");
+    CellGrid g{probe_cstart, probe_ccount, nc};
+    count_cells_kernel<<<cdiv(ncell_g, kCellWarps), kCellWarps * 32, 0, st>>>(cg, g, probe_sorted, cut2, inclusive, out_u32, probe_vals);
+    check_launch("neighbor_count");
+    CK(cudaMemcpyAsync(host_out, out_u32, N * 4, cudaMemcpyDeviceToHost, st));
+    sync();
 }
 
 void ljgpu_sim::export3(int what, double* a, double* b, double* cc) {
@@ -1073,7 +1166,43 @@ void ljgpu_sim::export3(int what, double* a, double* b, double* cc) {
 // computes.  On return the PREVIOUS delivery is complete; the current one is in flight.
 void ljgpu_sim::step_publish(unsigned step, double dt, double* x, double* y, double* z) {
     run_steps(step, 1, dt);
-    if (slab.on) { export3(0, x, y, z); return; }          // slabs: every rank assembles the whole system (collective), synchronous
+    if (slab.on && !slab.p2p) { export3(0, x, y, z); return; }      // NCCL step loop: every rank assembles the whole system, synchronous
+    if (slab.on) {
+        // Peer-memory slabs: every device scatters the atoms it owns into the frame slices of their owners (NVLink), each
+        // owner copies ITS slice - original indices [rank * S, rank * S + len) of x, y and z - to the host over its own
+        // PCIe link, on the copy stream, while the next step computes.  x, y, z address the WHOLE frame (N doubles each);
+        // for one consumer to see all of it they must be memory shared by the ranks' processes.
+        if (!st_copy) {
+            CK(cudaStreamCreateWithFlags(&st_copy, cudaStreamNonBlocking));
+            for (int b = 0; b < 2; ++b) {
+                CK(cudaEventCreateWithFlags(&ev_pub_ready[b], cudaEventDisableTiming));
+                CK(cudaEventCreateWithFlags(&ev_pub_done[b], cudaEventDisableTiming));
+            }
+        }
+        const int b = pub_cur ^ 1;
+        ++slab.pub_seq;
+        PubTargets tgt{};
+        for (int r = 0; r < slab.world; ++r) { tgt.slice[r] = slab.peer_pub[b][r]; tgt.mail[r] = slab.peer_mail[r]; }
+        const unsigned blocks = std::max(1u, std::min(cdiv(n, 256), 4u * (unsigned)num_sms));
+        slab_publish_scatter_kernel<<<blocks, 256, 0, st>>>(c, pos, orig, slab.pub_S, nglobal, tgt, slab.rank, slab.world, slab.pub_seq, slab.pub_ticket);
+        check_launch("slab_publish_scatter");
+        CK(cudaEventRecord(ev_pub_ready[b], st));
+        CK(cudaStreamWaitEvent(st_copy, ev_pub_ready[b], 0));
+        slab_publish_wait_kernel<<<1, 32, 0, st_copy>>>(slab.mail, slab.world, slab.pub_seq);
+        check_launch("slab_publish_wait");
+        const size_t first = (size_t)slab.rank * slab.pub_S;
+        const size_t len = first < nglobal ? std::min<size_t>(slab.pub_S, nglobal - first) : 0;
+        if (len) {
+            const double* o = slab.pub_slice[b];
+            CK(cudaMemcpyAsync(x + first, o, len * 8, cudaMemcpyDeviceToHost, st_copy));
+            CK(cudaMemcpyAsync(y + first, o + len, len * 8, cudaMemcpyDeviceToHost, st_copy));
+            CK(cudaMemcpyAsync(z + first, o + 2 * len, len * 8, cudaMemcpyDeviceToHost, st_copy));
+        }
+        CK(cudaEventRecord(ev_pub_done[b], st_copy));
+        if (pub_pending) CK(cudaEventSynchronize(ev_pub_done[pub_cur]));
+        pub_cur = b; pub_pending = true; pub_step = step;
+        return;
+    }
     const size_t N = nglobal;
     if (!st_copy) {
         CK(cudaStreamCreateWithFlags(&st_copy, cudaStreamNonBlocking));
@@ -1307,15 +1436,17 @@ int ljgpu_step_n(ljgpu_sim* s, uint32_t first, uint32_t n, double dt) {
 int ljgpu_step_n_timed(ljgpu_sim* s, uint32_t first, uint32_t n, double dt, double* device_ms) {
     if (!device_ms) return fail(LJGPU_EINVAL, "null argument");
     return with_sim(s, [&] {
-        cudaEvent_t a, b;
-        CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
-        CK(cudaEventRecord(a, s->st));
+        struct Events {
+            cudaEvent_t a = nullptr, b = nullptr;
+            ~Events() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }      // also when run_steps throws
+        } ev;
+        CK(cudaEventCreate(&ev.a)); CK(cudaEventCreate(&ev.b));
+        CK(cudaEventRecord(ev.a, s->st));
         s->run_steps(first, n, dt);
-        CK(cudaEventRecord(b, s->st));
-        CK(cudaEventSynchronize(b));
+        CK(cudaEventRecord(ev.b, s->st));
+        CK(cudaEventSynchronize(ev.b));
         float ms = 0.f;
-        CK(cudaEventElapsedTime(&ms, a, b));
-        cudaEventDestroy(a); cudaEventDestroy(b);
+        CK(cudaEventElapsedTime(&ms, ev.a, ev.b));
         *device_ms = ms;
     });
 }
@@ -1398,18 +1529,29 @@ int ljgpu_get_neighbor_counts(ljgpu_sim* s, double cutoff, int inclusive, uint32
     return with_sim(s, [&] {
         if (!(cutoff > 0) || cutoff > s->p.rcut + s->p.shell)
             throw LjError(LJGPU_EINVAL, "cutoff must be in (0, rcut + shell]");
-        if (s->slab.on) throw LjError(LJGPU_ESTATE, "the neighbour-count probe is not available on the slab path");
-        const double cut2 = cutoff * cutoff;
-        if (s->list_mode()) {
-            if (s->dirty_since_rebuild) s->rebuild();       // positions wrapped + cell-sorted again
-            CellGrid g{s->cstart, s->ccount, s->nc};
-            count_cells_kernel<<<cdiv(s->ncell, kCellWarps), kCellWarps * 32, 0, s->st>>>(
-                s->c, g, s->pos, cut2, inclusive, s->out_u32, s->orig);
-        } else {
-            count_allpairs_kernel<<<s->nb_atoms(), kBlock, 0, s->st>>>(s->c, s->pos, s->orig, cut2, inclusive, s->out_u32);
+        s->probe_neighbor_counts(cutoff * cutoff, inclusive, count_of_atom);
+    });
+}
+
+int ljgpu_get_list_counts(ljgpu_sim* s, int which, uint32_t* count_of_atom) {
+    if (!count_of_atom) return fail(LJGPU_EINVAL, "null argument");
+    return with_sim(s, [&] {
+        if (s->mode != LJGPU_KERNEL_VERLET) throw LjError(LJGPU_ESTATE, "only the Verlet path keeps a neighbour list");
+        if (which != 0 && which != 1) throw LjError(LJGPU_EINVAL, "which: 0 = the list of the last re-binning, 1 = the pruned inner list");
+        const uint32_t* src = which == 0 ? s->nl_count : s->nl_in_count;
+        if (which == 1) {
+            s->fetch_ctrl();
+            if (!s->nl_in || !s->h_ctrl->inner_valid) throw LjError(LJGPU_ESTATE, "no pruned inner list exists at the moment");
         }
-        s->check_launch("neighbor_count");
-        CK(cudaMemcpyAsync(count_of_atom, s->out_u32, (size_t)s->n * 4, cudaMemcpyDeviceToHost, s->st));
+        const size_t N = s->nglobal;
+        if (s->slab.on) CK(cudaMemsetAsync(s->out_u32, 0, N * 4, s->st));
+        if (s->n) {
+            scatter_u32_kernel<<<s->nb_atoms(), kBlock, 0, s->st>>>(s->n, src, s->orig, s->out_u32);
+            s->check_launch("scatter_u32");
+        }
+        if (s->slab.on)
+            NCK(ljnccl::api().AllReduce(s->out_u32, s->out_u32, N, ljnccl::kUint32, ljnccl::kSum, s->slab.comm, s->st));
+        CK(cudaMemcpyAsync(count_of_atom, s->out_u32, N * 4, cudaMemcpyDeviceToHost, s->st));
         s->sync();
     });
 }
@@ -1449,9 +1591,9 @@ int ljgpu_get_timers(ljgpu_sim* s, ljgpu_timers* out) {
     if (!out) return fail(LJGPU_EINVAL, "null argument");
     return with_sim(s, [&] {
         s->sync();
-        out->ms_predict = s->ms[ST_PREDICT]; out->ms_kick_drift = s->ms[ST_KICK_DRIFT]; out->ms_ghost = s->ms[ST_GHOST];
+        out->ms_predict = s->ms[ST_PREDICT]; out->ms_kick_drift = s->ms[ST_KICK_DRIFT]; out->ms_force_prune = s->ms[ST_FORCE_PRUNE];
         out->ms_force = s->ms[ST_FORCE]; out->ms_kick2 = s->ms[ST_KICK2]; out->ms_rebuild = s->ms[ST_REBUILD]; out->ms_halo = s->ms[ST_HALO];
-        out->n_predict = s->cnt[ST_PREDICT]; out->n_kick_drift = s->cnt[ST_KICK_DRIFT]; out->n_ghost = s->cnt[ST_GHOST];
+        out->n_predict = s->cnt[ST_PREDICT]; out->n_kick_drift = s->cnt[ST_KICK_DRIFT]; out->n_force_prune = s->cnt[ST_FORCE_PRUNE];
         out->n_force = s->cnt[ST_FORCE]; out->n_kick2 = s->cnt[ST_KICK2]; out->n_rebuild = s->cnt[ST_REBUILD]; out->n_halo = s->cnt[ST_HALO];
         out->steps = s->steps; out->rebuilds = s->rebuilds; out->kernel_launches = s->launches;
     });
@@ -1466,12 +1608,12 @@ int ljgpu_reset_timers(ljgpu_sim* s) {
 }
 
 int ljgpu_get_layout(ljgpu_sim* s, int32_t* force_kernel, uint32_t* cells_per_axis,
-                     uint32_t* list_capacity, uint64_t* n_ghosts) {
+                     uint32_t* list_capacity, uint64_t* inner_list_steps) {
     return with_sim(s, [&] {
         if (force_kernel) *force_kernel = s->mode;
         if (cells_per_axis) *cells_per_axis = s->nc;
         if (list_capacity) *list_capacity = 8 * s->capq;
-        if (n_ghosts) { s->fetch_ctrl(); *n_ghosts = s->h_ctrl->inner_used; }   // steps served by the pruned inner list (no ghost atoms exist in this layout)
+        if (inner_list_steps) { s->fetch_ctrl(); *inner_list_steps = s->h_ctrl->inner_used; }
     });
 }
 
@@ -1489,6 +1631,46 @@ int ljgpu_get_list_stats(ljgpu_sim* s, double* mean_length, uint32_t* max_length
         if (mean_length) *mean_length = mean;
         if (max_length) *max_length = mx;
     });
+}
+
+int ljgpu_measure_fp64_peak(int device, double* tflops) {
+    if (!tflops) return fail(LJGPU_EINVAL, "null argument");
+    return guarded([&] {
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); throw LjError(LJGPU_ECUDA, "no CUDA device available"); }
+        if (device < 0) CK(cudaGetDevice(&device));
+        if (device >= ndev) throw LjError(LJGPU_EINVAL, "device ordinal out of range");
+        CK(cudaSetDevice(device));
+        int sms = 0;
+        CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+        const int blocks = sms * 8, threads = 256, iters = 8192;       // 64 warps per SM, 8 chains each
+        double* out = nullptr;
+        CK(cudaMalloc(&out, sizeof(double) * blocks * threads));
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        struct Guard { double*& o; cudaEvent_t &a, &b; ~Guard() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); cudaFree(o); } } guard{out, e0, e1};
+        CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+        float best = 1e30f;
+        for (int r = 0; r < 6; ++r) {                                   // first pass warms up
+            CK(cudaEventRecord(e0, nullptr));
+            fp64_peak_kernel<<<blocks, threads, 0, nullptr>>>(out, iters, 1.0000001, 1e-9);
+            CK(cudaGetLastError());
+            CK(cudaEventRecord(e1, nullptr));
+            CK(cudaEventSynchronize(e1));
+            float ms = 0.f;
+            CK(cudaEventElapsedTime(&ms, e0, e1));
+            if (r > 0 && ms < best) best = ms;
+        }
+        *tflops = 2.0 * 8.0 * (double)iters * threads * blocks / ((double)best * 1e-3) / 1e12;
+    });
+}
+
+int ljgpu_register_host(void* p, size_t bytes) {
+    if (!p) return fail(LJGPU_EINVAL, "null argument");
+    return guarded([&] { CK(cudaHostRegister(p, bytes, cudaHostRegisterPortable)); });
+}
+
+int ljgpu_unregister_host(void* p) {
+    return guarded([&] { if (p) CK(cudaHostUnregister(p)); });
 }
 
 int ljgpu_alloc_host(size_t bytes, void** out) {

@@ -154,8 +154,7 @@ struct TileArgs {
     unsigned slots;                        // tiles in flight per CTA (2..kBrickSlotsMax)
     unsigned ipb;                          // work items per brick: ceil(most home atoms of a brick / 32)
     // slab path over peer memory: wait until both neighbours have pushed this step's halo (null: no wait)
-    Mailbox* mail;
-    unsigned long long halo_seq;
+    Mailbox* mail;                         // (the sequence number to wait for is ctrl->halo_seq: the push of this step has already counted itself)
 };
 
 // What the staging warp leaves next to a tile for the computing warps.
@@ -202,8 +201,9 @@ tile_kernel(LJConst c, TileGrid g, TileArgs a, int guarded) {
             const bool lo_halo = a.mail && tg.z0 == g.hz0, hi_halo = a.mail && tg.z0 + tg.bd == g.hz0 + g.nhz;
             if (lo_halo || hi_halo) {    // slab over peer memory: only bricks whose tile reaches a halo layer wait for that neighbour's push
                 if (lane == 0) {
-                    if (lo_halo) wait_flag(&a.mail->halo_flag[0], a.halo_seq, &a.mail->error);
-                    if (hi_halo) wait_flag(&a.mail->halo_flag[1], a.halo_seq, &a.mail->error);
+                    const unsigned long long seq = a.ctrl->halo_seq;
+                    if (lo_halo) wait_flag(&a.mail->halo_flag[0], seq, &a.mail->error);
+                    if (hi_halo) wait_flag(&a.mail->halo_flag[1], seq, &a.mail->error);
                 }
                 __syncwarp();
             }
@@ -367,8 +367,21 @@ tile_kernel(LJConst c, TileGrid g, TileArgs a, int guarded) {
                     for (int u = 0; u < kTileGroup; ++u) {
                         const uint32_t w = cw[(part * kTileGroup + u) >> 1];
                         jj[u] = (u & 1) ? (w >> 16) : (w & 0xffffu);
+#ifdef LJ_EXP_NOLDS      /* timing experiment only (steps with dt == 0): no shared-memory gather */
+                        if (c.dt == 0.0) {
+                            const double fake = __hiloint2double(0x3ff00000 + (int)(jj[u] << 8), 0);
+                            dx[u] = fake; dy[u] = fake * 0.5; dz[u] = fake * 0.25;
+                        } else
+#endif
                         tile_ld(sxy, sz, jj[u], dx[u], dy[u], dz[u]);
                     }
+#ifdef LJ_EXP_NOFP       /* timing experiment only (steps with dt == 0): gather, almost no arithmetic */
+                    if (c.dt == 0.0) {
+#pragma unroll
+                        for (int u = 0; u < kTileGroup; ++u) { ax += dx[u]; ay += dy[u]; az += dz[u]; }
+                        continue;
+                    }
+#endif
 #pragma unroll
                     for (int u = 0; u < kTileGroup; ++u) {
                         dx[u] = pix - dx[u]; dy[u] = piy - dy[u]; dz[u] = piz - dz[u];

@@ -41,6 +41,9 @@ template <class T> inline cudaError_t cudaMalloc(T** p, size_t bytes) {
 template <class T> inline cudaError_t cudaMallocHost(T** p, size_t bytes) { return cudaMalloc(p, bytes); }
 inline cudaError_t cudaFree(void* p) { std::free(p); return cudaSuccess; }
 inline cudaError_t cudaFreeHost(void* p) { std::free(p); return cudaSuccess; }
+enum { cudaHostRegisterPortable = 1 };
+inline cudaError_t cudaHostRegister(void*, size_t, unsigned) { return cudaSuccess; }
+inline cudaError_t cudaHostUnregister(void*) { return cudaSuccess; }
 inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { std::memmove(d, s, n); return cudaSuccess; }
 inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t = nullptr) { std::memmove(d, s, n); return cudaSuccess; }
 inline cudaError_t cudaMemset(void* d, int v, size_t n) { std::memset(d, v, n); return cudaSuccess; }
@@ -68,6 +71,8 @@ inline cudaError_t cudaStreamBeginCapture(cudaStream_t, cudaStreamCaptureMode) {
 inline cudaError_t cudaStreamEndCapture(cudaStream_t, cudaGraph_t* g) { *g = nullptr; return cudaErrorNotSupported; }
 inline cudaError_t cudaGraphInstantiate(cudaGraphExec_t*, cudaGraph_t, unsigned long long) { return cudaErrorNotSupported; }
 inline cudaError_t cudaGraphLaunch(cudaGraphExec_t, cudaStream_t) { return cudaErrorNotSupported; }
+struct cudaGraphExecUpdateResultInfo { int result; };
+inline cudaError_t cudaGraphExecUpdate(cudaGraphExec_t, cudaGraph_t, cudaGraphExecUpdateResultInfo*) { return cudaErrorNotSupported; }
 inline cudaError_t cudaGraphDestroy(cudaGraph_t) { return cudaSuccess; }
 inline cudaError_t cudaGraphExecDestroy(cudaGraphExec_t) { return cudaSuccess; }
 // all "devices" share one address space: the handle carries the pointer itself

@@ -56,6 +56,8 @@ def main():
             assert err < tol, (tag, err)
 
         check("step 0")
+        assert np.array_equal(g.get_list_counts(), o.neighbor_counts())          # the list every "device" walks
+        assert np.array_equal(g.get_neighbor_counts(cfg["rcut"] + cfg["shell"], True), o.neighbor_counts())
         for s in range(1, steps + 1):
             o.integrate(s, DT)
             g.integrate(s, DT)
@@ -71,9 +73,35 @@ def main():
         assert np.array_equal(cells, ol.oracle_cell_ids_of(cfg, x, y, z)[0])
         vx, vy, vz = g.get_velocities_soa()
         assert np.array_equal(g.get_speed_histogram(), ol.oracle_speed_histogram(vx, vy, vz))
+        counts_mid = g.get_neighbor_counts(cfg["rcut"], True)                    # collective; mid-life of a list
+        if rank == 0:
+            assert np.array_equal(counts_mid, ol.oracle_pair_counts(cfg["cell_length"], x, y, z, cfg["rcut"]))
+        bar.wait()              # nobody steps on while rank 0 counts: a device waits ~2 s for its peers, then reports them gone
 
-        o.run(steps + 1, long_steps, DT)                       # across re-binnings and migrations
-        g.integrate_n(steps + 1, long_steps, DT)
+        # publication: every "device" delivers its slice of the original-order frame into one frame shared by all ranks
+        bar.wait()
+        if rank == 0:
+            shared["frames"] = [np.zeros(3 * n_atoms), np.zeros(3 * n_atoms)]
+        bar.wait()
+        fr = shared["frames"]
+        ptrs = [[f.ctypes.data + k * n_atoms * 8 for k in range(3)] for f in fr]
+        first_pub = steps + 1
+        for s in range(first_pub, first_pub + 4):
+            o.integrate(s, DT)
+            g.integrate_publish(s, DT, *ptrs[s & 1])
+        g.publish_wait()
+        bar.wait()
+        last = first_pub + 3
+        want = g.get_positions_soa()
+        f = fr[last & 1]
+        for k in range(3):
+            assert np.array_equal(f[k * n_atoms:(k + 1) * n_atoms], want[k]), "published frame differs from the getter"
+        check(f"step {last} (after publishing)")
+        bar.wait()
+        steps_done = last
+
+        o.run(steps_done + 1, long_steps, DT)                  # across re-binnings and migrations
+        g.integrate_n(steps_done + 1, long_steps, DT)
         ek, ep, _ = g.get_energies()
         oek, oep, _ = o.energies()
         assert abs(ek - oek) < 1e-8 * abs(oek) and abs(ep - oep) < 1e-8 * abs(oep), (ek, oek, ep, oep)
@@ -97,7 +125,7 @@ def main():
             bar.wait()
             s = lj.LennardJonesSimulation(params, state, force_kernel=lj.KERNEL_VERLET, device=rank, slab=(rank, world, shared["uid"]))
             s.integrate_n(1, long_steps, DT)
-            out = (s.get_energies(), s.get_positions_soa(), s.get_velocities_soa(), s.get_layout()["n_ghosts"])
+            out = (s.get_energies(), s.get_positions_soa(), s.get_velocities_soa(), s.get_layout()["inner_list_steps"])
             bar.wait()
             s.close()
             return out

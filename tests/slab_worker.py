@@ -60,6 +60,11 @@ def main():
         assert err < tol, (tag, err)
 
     check("step 0")
+    # the list every device walks, atom by atom, against the reference's list of the same positions, and the bit-exact
+    # neighbour-count probe on the slab path (collective: every device assembles the whole system)
+    assert np.array_equal(g.get_list_counts(), o.neighbor_counts())
+    assert np.array_equal(g.get_neighbor_counts(cfg["rcut"] + cfg["shell"], True), o.neighbor_counts())
+    assert np.array_equal(g.get_neighbor_counts(cfg["rcut"], False), o.incutoff_counts())
     for s in range(1, steps + 1):
         o.integrate(s, DT)
         g.integrate(s, DT)
@@ -76,6 +81,35 @@ def main():
     assert np.array_equal(cells, ol.oracle_cell_ids_of(cfg, x, y, z)[0])
     vx, vy, vz = g.get_velocities_soa()
     assert np.array_equal(g.get_speed_histogram(), ol.oracle_speed_histogram(vx, vy, vz))
+    counts_mid = g.get_neighbor_counts(cfg["rcut"] + cfg["shell"], True)     # collective; atoms have moved since the binning
+    if rank == 0 and n_atoms <= 65536:      # (the brute-force reference count is O(N^2))
+        assert np.array_equal(counts_mid, ol.oracle_pair_counts(cfg["cell_length"], x, y, z, cfg["rcut"] + cfg["shell"]))
+    dist.barrier()              # nobody steps on while rank 0 counts: a device waits ~2 s for its peers, then reports them gone
+
+    # publication, the reference's per-step call pattern (integrate + publish_state): every device delivers its slice of
+    # the original-order frame into ONE frame shared by all ranks; the frame must equal the collective getter bit for bit
+    frames = lj.SharedFrames(n_atoms, world, rank, dist)
+    ptrs = frames.pointers()
+    pub_first = steps + 1
+    for s in range(pub_first, pub_first + 6):
+        o.integrate(s, DT)
+        g.integrate_publish(s, DT, *ptrs[s & 1])
+        if s > pub_first:                      # the delivery of step s - 1 is complete now, on this rank ...
+            dist.barrier()                     # ... and after the barrier on every rank
+            want = prev_positions
+            got = frames.xyz((s - 1) & 1)
+            for a, b in zip(got, want):
+                assert np.array_equal(a, b), ("published frame", s - 1)
+            dist.barrier()                     # nobody overwrites the frame while somebody compares
+        prev_positions = g.get_positions_soa()
+    g.publish_wait()
+    dist.barrier()
+    for a, b in zip(frames.xyz((pub_first + 5) & 1), prev_positions):
+        assert np.array_equal(a, b), "last published frame"
+    check(f"step {pub_first + 5} (after publishing)")
+    dist.barrier()
+    frames.close()
+    steps = pub_first + 5
 
     # across re-binnings and migrations
     o.run(steps + 1, long_steps, DT)
@@ -107,7 +141,7 @@ def main():
         s = lj.LennardJonesSimulation(params, state, force_kernel=lj.KERNEL_VERLET, device=local,
                                       slab=(rank, world, vid[0]))
         s.integrate_n(1, long_steps, DT)
-        out = (s.get_energies(), s.get_positions_soa(), s.get_velocities_soa(), s.get_layout()["n_ghosts"])
+        out = (s.get_energies(), s.get_positions_soa(), s.get_velocities_soa(), s.get_layout()["inner_list_steps"])
         dist.barrier()
         s.close()
         return out

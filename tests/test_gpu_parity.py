@@ -29,6 +29,20 @@ def make_pair(lj, cfg, kernel, state=None):
     return o, g
 
 
+def check_step_strict(o, g, tol=TOL, what=""):
+    """The plain bar of BASELINE.json: energies and EVERY atom's force within `tol` relative of the reference's
+    values, no allowance for the reference's own summation error (in a liquid there is none to speak of)."""
+    ek, ep, et = g.get_energies()
+    oek, oep, oet = o.energies()
+    assert abs(ep - oep) < tol * abs(oep), f"{what} epot {ep!r} vs {oep!r}"
+    if oek != 0.0:
+        assert abs(ek - oek) < tol * abs(oek), f"{what} ekin {ek!r} vs {oek!r}"
+        assert abs(et - oet) < tol * (abs(oek) + abs(oep)), f"{what} etot {et!r} vs {oet!r}"
+    fo = o.forces()
+    err = ol.force_rel_error(g.get_forces_soa(), fo)          # denominator max(|f_i|, f_rms): no pair-sum floor
+    assert err.max() < tol, f"{what} force rel err {err.max()}"
+
+
 def check_step(o, g, tol=TOL, what=""):
     """Energies and forces of the GPU against the oracle at `tol` relative.
 
@@ -92,6 +106,97 @@ def test_n65536_window(lj, kernel):
         o.integrate(s, DT)
         g.integrate(s, DT)
         check_step(o, g, what=f"n65536 step {s}")
+
+
+@pytest.mark.parametrize("n,melt,kernels", [(65536, 1500, (2, 3)), (1048576, 600, (3,))], ids=["n65536", "n1048576"])
+def test_liquid_window_strict_1e12(lj, n, melt, kernels):
+    """Liquid-state 10-step windows at the two large BASELINE sizes with the PLAIN 1e-12 bound on energies and on
+    every atom's force.  The device melts the reference's start lattice itself (the CPU integrator needs 0.7 s per
+    step at N = 2^20); the melted state is then handed to the reference algorithm (oracle restatement, pinned bit for
+    bit to the compiled reference) and to fresh device simulations, and both integrate the same 10 steps."""
+    cfg = ol.config(n)
+    params = lj.LennardJonesParameters(**cfg)
+    lj.host_rng_reset()
+    melt_sim = lj.LennardJonesSimulation(params, lj.host_initialize(params), force_kernel=3)
+    melt_sim.integrate_n(1, melt, DT)
+    assert melt_sim.get_timers()["rebuilds"] >= 5
+    st = melt_sim.get_positions_soa() + melt_sim.get_velocities_soa()
+    t_kin = 2.0 * melt_sim.get_ekin() / (3.0 * (n - 1))
+    assert 0.8 < t_kin < 1.3                       # molten and thermostatted, not the lattice any more
+    melt_sim.close()
+    for kernel in kernels:
+        o, g = make_pair(lj, cfg, kernel, state=st)
+        check_step_strict(o, g, what=f"liquid n={n} kernel {kernel} step 0")
+        for s in range(1, 11):
+            o.integrate(s, DT)
+            g.integrate(s, DT)
+            if n <= 65536 or s in (1, 5, 10):
+                check_step_strict(o, g, what=f"liquid n={n} kernel {kernel} step {s}")
+        if kernel == 3:
+            # the list the force kernel walks, atom by atom, against the reference's list (same positions: step 0 lists
+            # were both built from `st`; no re-binning can have happened within 10 steps of a fresh list)
+            assert g.get_timers()["rebuilds"] == o.rebuild_count() == 1
+            assert np.array_equal(g.get_list_counts(), o.neighbor_counts())
+        g.close(); o.close()
+
+
+def test_product_list_counts_match_reference(lj):
+    """ljgpu_get_list_counts: per-atom lengths of the Verlet list the force kernel walks = the reference's per-atom
+    list lengths (lennardjonessimulation.cpp:543-550), on the start lattice, on a melted state, and after the device
+    has re-binned by itself (then against a fresh reference list built from the positions of that re-binning)."""
+    cfg = ol.config(32768)
+    o, g = make_pair(lj, cfg, 3)
+    assert np.array_equal(g.get_list_counts(), o.neighbor_counts())
+    o.run(1, 200, DT)
+    st = o.state()
+    o2 = ol.Oracle(cfg, state=st)
+    g.set_state(st)
+    assert np.array_equal(g.get_list_counts(), o2.neighbor_counts())
+    # step until the device has just re-binned (a batch of one step at a time so that we can catch the moment)
+    r0 = g.get_timers()["rebuilds"]
+    for s in range(1, 200):
+        g.integrate(s, DT)
+        if g.get_timers()["rebuilds"] > r0:
+            break
+    else:
+        pytest.fail("no re-binning within 200 steps")
+    x, y, z = g.get_positions_soa()                 # the positions the list was just built from (wrapped)
+    want = ol.oracle_pair_counts(cfg["cell_length"], x, y, z, cfg["rcut"] + cfg["shell"])
+    got = g.get_list_counts()
+    # identical unless a pair sits within an ulp of (rcut + shell)^2 (FMA-contracted d2 in the list build); report, do not hide
+    assert np.count_nonzero(got != want) == 0, np.flatnonzero(got != want)[:10]
+    inner = g.get_list_counts(inner=False)
+    assert inner.shape == got.shape
+    g.integrate_n(s + 1, 3, DT)                     # the first step after a re-binning prunes
+    inner = g.get_list_counts(inner=True)
+    assert np.all(inner <= g.get_list_counts()) and inner.sum() < g.get_list_counts().sum()
+
+
+def test_probes_do_not_disturb_the_integrator(lj):
+    """The neighbour-count / cell-id / list-count probes only read: a run that probes every few steps equals an
+    unprobed run bit for bit, re-binning at the same steps."""
+    cfg = ol.config(16384)
+    o = equilibrated_state(cfg, 150)
+    st = o.state()
+    params = lj.LennardJonesParameters(**cfg)
+    a = lj.LennardJonesSimulation(params, st, force_kernel=3)
+    b = lj.LennardJonesSimulation(params, st, force_kernel=3)
+    for s in range(1, 91):
+        a.integrate(s, DT)
+        b.integrate(s, DT)
+        if s % 7 == 0:
+            b.get_neighbor_counts(cfg["rcut"] + cfg["shell"], True)
+            b.get_cell_ids()
+            b.get_list_counts()
+        assert a.get_timers()["rebuilds"] == b.get_timers()["rebuilds"], s
+    assert a.get_timers()["rebuilds"] >= 2
+    assert a.get_energies() == b.get_energies()
+    for u, v in zip(a.get_positions_soa() + a.get_forces_soa(), b.get_positions_soa() + b.get_forces_soa()):
+        assert np.array_equal(u, v)
+    # and the probe itself is right in the middle of a list's life (atoms have left the cells they were binned into)
+    x, y, z = b.get_positions_soa()
+    want = ol.oracle_pair_counts(cfg["cell_length"], x, y, z, cfg["rcut"])
+    assert np.array_equal(b.get_neighbor_counts(cfg["rcut"], True), want)
 
 
 def equilibrated_state(cfg, steps):
@@ -308,8 +413,8 @@ def test_pruned_inner_list_is_bit_identical_to_outer_list(lj, monkeypatch):
     b = lj.LennardJonesSimulation(params, st, force_kernel=3)
     a.integrate_n(1, 120, DT)
     b.integrate_n(1, 120, DT)
-    assert b.get_layout()["n_ghosts"] > 60          # most steps were served by the inner list
-    assert a.get_layout()["n_ghosts"] == 0
+    assert b.get_layout()["inner_list_steps"] > 60          # most steps were served by the inner list
+    assert a.get_layout()["inner_list_steps"] == 0
     assert a.get_energies() == b.get_energies()
     for u, v in zip(a.get_forces_soa() + a.get_positions_soa(), b.get_forces_soa() + b.get_positions_soa()):
         assert np.array_equal(u, v)
