@@ -176,6 +176,25 @@ int ljgpu_get_speed_histogram(ljgpu_sim* s, uint32_t nbins, double vmax, uint64_
 int ljgpu_maxwell_boltzmann(double kT, double mass, int32_t nr_particles, uint32_t nbins,
                             double vmax, double* expected);
 
+/* GraphWidget statistics on the device (src/simulator/graphwidget.cpp:139-203, :235-248).  The integrator keeps the series
+ * the widget plots: the energies of every `stride`-th step (ThreadIntegrate::run emits them every 1000 iterations,
+ * threadintegrate.cpp:57-62; default stride 1000, ring of the last 8192 samples; setting the stride starts a new series).
+ * ljgpu_get_graph_stats: minimum, maximum (the chart's axis range), mean and standard deviation (the average line and the
+ * +-sigma band; variance over n - 1, 0 when not finite) of the kinetic [0], potential [1] and total [2] energy series.
+ * reference_truncation != 0 reproduces the reference's std::accumulate(..., 0) - an int accumulator that truncates every
+ * partial sum (:147, :169, :191, :236); 0 sums in double. */
+typedef struct ljgpu_graph_stats {
+    double   mean[3], stddev[3], min[3], max[3];
+    uint32_t n_samples, reserved;
+} ljgpu_graph_stats;
+int ljgpu_set_sample_stride(ljgpu_sim* s, uint32_t stride);
+int ljgpu_get_graph_stats(ljgpu_sim* s, int reference_truncation, ljgpu_graph_stats* out);
+/* Speed histogram (as ljgpu_get_speed_histogram) together with the Maxwell-Boltzmann overlay the widget draws over it
+ * (graphwidget.cpp:55-73: f(v) N binsize at the left bin edges, at the thermostat's kT) and their chi-square over the
+ * bins_used bins that expect more than five atoms - all evaluated on the device. */
+int ljgpu_get_speed_statistics(ljgpu_sim* s, uint32_t nbins, double vmax, uint64_t* counts, double* expected,
+                               double* chi2, uint32_t* bins_used);
+
 /* Parity probes of build_neighbor_list (lennardjonessimulation.cpp:441-551) on the published
  * positions, bit-exact with the reference's comparisons:
  *   cell_of_atom[i] = iz*nx*ny + iy*nx + ix with ix = min((unsigned)(x/dx), nx-1)   (:447-476)

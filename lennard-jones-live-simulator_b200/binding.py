@@ -19,7 +19,7 @@ EXPORTED_SYMBOLS = [
     "ljgpu_get_energies", "ljgpu_get_energy_history", "ljgpu_get_speed_histogram",
     "ljgpu_maxwell_boltzmann", "ljgpu_get_cell_ids", "ljgpu_get_neighbor_counts", "ljgpu_get_list_counts",
     "ljgpu_write_movie_frame", "ljgpu_set_profiling", "ljgpu_get_timers", "ljgpu_reset_timers",
-    "ljgpu_get_layout", "ljgpu_step_n_timed", "ljgpu_get_list_stats", "ljgpu_alloc_host", "ljgpu_free_host", "ljgpu_measure_fp64_peak", "ljgpu_register_host", "ljgpu_unregister_host",
+    "ljgpu_get_layout", "ljgpu_step_n_timed", "ljgpu_get_list_stats", "ljgpu_alloc_host", "ljgpu_free_host", "ljgpu_measure_fp64_peak", "ljgpu_register_host", "ljgpu_unregister_host", "ljgpu_set_sample_stride", "ljgpu_get_graph_stats", "ljgpu_get_speed_statistics",
     "ljgpu_slab_layers", "ljgpu_slab_unique_id", "ljgpu_create_slab", "ljgpu_slab_info",
     "ljgpu_step_publish", "ljgpu_publish_wait",
 ]
@@ -119,6 +119,12 @@ class SharedFrames:
         self._shm = []
 
 
+class GraphStats(C.Structure):
+    """struct ljgpu_graph_stats (include/ljgpu.h)."""
+    _fields_ = [("mean", C.c_double * 3), ("stddev", C.c_double * 3), ("min", C.c_double * 3), ("max", C.c_double * 3),
+                ("n_samples", C.c_uint32), ("reserved", C.c_uint32)]
+
+
 class LJParams(C.Structure):
     """struct ljgpu_params (include/ljgpu.h)."""
     _fields_ = [
@@ -186,6 +192,9 @@ def load_library():
     lib.ljgpu_get_list_stats.argtypes = [vp, dp, C.POINTER(C.c_uint32)]
     lib.ljgpu_measure_fp64_peak.argtypes = [C.c_int, dp]
     lib.ljgpu_register_host.argtypes = [vp, C.c_size_t]
+    lib.ljgpu_set_sample_stride.argtypes = [vp, C.c_uint32]
+    lib.ljgpu_get_graph_stats.argtypes = [vp, C.c_int, C.POINTER(GraphStats)]
+    lib.ljgpu_get_speed_statistics.argtypes = [vp, C.c_uint32, C.c_double, vp, vp, dp, C.POINTER(C.c_uint32)]
     lib.ljgpu_unregister_host.argtypes = [vp]
     lib.ljgpu_step_publish.argtypes = [vp, C.c_uint32, C.c_double, vp, vp, vp]
     lib.ljgpu_publish_wait.argtypes = [vp]
@@ -439,6 +448,28 @@ class LennardJonesSimulation:
         out = np.empty(self.n, dtype=np.uint32)
         _check(self._lib, self._lib.ljgpu_get_neighbor_counts(self._h, cutoff, 1 if inclusive else 0, _ptr(out)))
         return out
+
+    def set_sample_stride(self, stride):
+        """Every `stride`-th step's energies enter the series the GraphWidget plots (default 1000); starts a new series."""
+        _check(self._lib, self._lib.ljgpu_set_sample_stride(self._h, int(stride)))
+
+    def get_graph_stats(self, reference_truncation=False):
+        """GraphWidget's running statistics of the sampled energy series, computed on the device:
+        {"n": samples, "ekin" / "epot" / "etot": {"mean", "stddev", "min", "max"}}."""
+        st = GraphStats()
+        _check(self._lib, self._lib.ljgpu_get_graph_stats(self._h, 1 if reference_truncation else 0, C.byref(st)))
+        out = {"n": int(st.n_samples)}
+        for k, name in enumerate(("ekin", "epot", "etot")):
+            out[name] = {"mean": st.mean[k], "stddev": st.stddev[k], "min": st.min[k], "max": st.max[k]}
+        return out
+
+    def get_speed_statistics(self, nbins=100, vmax=10.0):
+        """Speed histogram, Maxwell-Boltzmann overlay and their chi-square, all from the device."""
+        counts = np.zeros(nbins, dtype=np.uint64)
+        expected = np.zeros(nbins, dtype=np.float64)
+        chi2, used = C.c_double(), C.c_uint32()
+        _check(self._lib, self._lib.ljgpu_get_speed_statistics(self._h, nbins, vmax, _ptr(counts), _ptr(expected), C.byref(chi2), C.byref(used)))
+        return counts, expected, chi2.value, int(used.value)
 
     def get_list_counts(self, inner=False):
         """Per-atom lengths of the list the force kernel walks: the list of the last re-binning (the reference's

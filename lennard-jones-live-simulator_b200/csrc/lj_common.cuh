@@ -79,6 +79,10 @@ struct LJConst {
     unsigned nzl;                 // number of owned cell layers
 };
 
+constexpr int kHistCap = 4096;    // entries in the energy history ring
+constexpr int kSampleCap = 8192;  // entries in the ring of sampled energies (one per sample_stride steps: the GraphWidget's series)
+struct HistEntry { double ekin, epot; unsigned int step; unsigned int pad; };
+
 // Device-resident control block: accumulators, published energies, batch bookkeeping.
 struct StepCtrl {
     double pred_sum;              // sum |v + a f|^2 : kinetic sum the NEXT kick1 will see
@@ -94,6 +98,7 @@ struct StepCtrl {
     unsigned int max_tile;        // largest shared-memory tile (atoms) over all home blocks
     unsigned int max_home;        // most home atoms in one block
     unsigned long long hist_head; // energy history ring: entries written so far
+    unsigned long long sample_head; // sampled-energy ring (GraphWidget series): entries written so far
     // pruned inner list (single-device Verlet path): valid while drift_bound <= prune_half
     unsigned long long vmax2;     // bits of max_i |v_i|^2 of the current step's drift velocities
     double drift_bound;           // sum over the steps since the pruning of max_i |v_i| dt
@@ -104,6 +109,10 @@ struct StepCtrl {
     // slab path over peer memory: sequence numbers of the halo pushes and of the mailbox all-reduces done so far.  They live on
     // the device (not in kernel arguments) so that a captured CUDA graph of a step stays valid from step to step.
     unsigned long long halo_seq, red_seq;
+    // the energy series the GraphWidget plots: every sample_stride-th step's energies (threadintegrate.cpp:57-62: every 1000
+    // iterations) are appended to `samples` by the kernel that publishes the step
+    HistEntry* samples;
+    unsigned int sample_stride, pad1;
 };
 
 // Slab path, peer-memory exchange: every device owns one mailbox that its peers write over NVLink.
@@ -118,8 +127,6 @@ struct Mailbox {
     unsigned int pad;
 };
 
-constexpr int kHistCap = 4096;    // entries in the energy history ring
-struct HistEntry { double ekin, epot; unsigned int step; unsigned int pad; };
 
 
 // ---------------------------------------------------------------------------------------------

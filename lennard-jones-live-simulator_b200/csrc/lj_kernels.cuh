@@ -403,6 +403,10 @@ __device__ __forceinline__ void publish_step(const LJConst& c, StepCtrl* __restr
     ctrl->ekin = ekin; ctrl->epot = epot; ctrl->etot = xadd(ekin, epot);
     HistEntry& h = hist[ctrl->hist_head % kHistCap];
     h.ekin = ekin; h.epot = epot; h.step = ctrl->next_step; h.pad = 0;
+    if (ctrl->sample_stride && h.step % ctrl->sample_stride == 0u) {       // signal_ekin / _epot / _etot cadence, threadintegrate.cpp:57-62
+        ctrl->samples[ctrl->sample_head % kSampleCap] = h;
+        ctrl->sample_head += 1;
+    }
     ctrl->next_step += 1;
     ctrl->hist_head += 1;
     ctrl->steps_done += 1;
@@ -874,6 +878,60 @@ __global__ void __launch_bounds__(kBlock)
 gather_pos_kernel(unsigned n, const uint32_t* __restrict__ perm, const double4* __restrict__ in, double4* __restrict__ out) {
     const unsigned i = blockIdx.x * kBlock + threadIdx.x;
     if (i < n) out[i] = in[perm[i]];
+}
+
+// GraphWidget statistics on the device (graphwidget.cpp:139-203, :235-248): minimum, maximum, mean and standard deviation
+// of the sampled kinetic / potential / total energy series.  One lane per series walks the ring oldest-first with the
+// reference's operations in the reference's order (no contraction), so the numbers equal a host evaluation bit for bit.
+// reference_truncation reproduces the reference's std::accumulate(..., 0): an int accumulator truncates every partial sum
+// (:147, :169, :191, :236); otherwise the sum is done in double, as the plot evidently intends.
+struct SeriesStatsOut { double mean[3], stddev[3], vmin[3], vmax[3]; unsigned int n; unsigned int pad; };
+__global__ void series_stats_kernel(const StepCtrl* __restrict__ ctrl, int reference_truncation, SeriesStatsOut* __restrict__ out) {
+    const unsigned k = threadIdx.x;
+    if (k >= 3) return;
+    const unsigned long long head = ctrl->sample_head;
+    const unsigned n = (unsigned)(head < (unsigned long long)kSampleCap ? head : (unsigned long long)kSampleCap);
+    const HistEntry* ring = ctrl->samples;
+    auto value = [&](unsigned idx) {
+        const HistEntry& e = ring[(head - n + idx) % kSampleCap];
+        return k == 0 ? e.ekin : (k == 1 ? e.epot : xadd(e.ekin, e.epot));
+    };
+    if (k == 0) { out->n = n; out->pad = 0; }
+    if (n == 0) { out->mean[k] = 0.0; out->stddev[k] = 0.0; out->vmin[k] = 0.0; out->vmax[k] = 0.0; return; }
+    double sum = 0.0, lo = value(0), hi = lo;
+    int isum = 0;
+    for (unsigned idx = 0; idx < n; ++idx) {
+        const double v = value(idx);
+        if (reference_truncation) isum = (int)xadd((double)isum, v); else sum = xadd(sum, v);
+        lo = v < lo ? v : lo; hi = v > hi ? v : hi;
+    }
+    const double avg = xdiv(reference_truncation ? (double)isum : sum, (double)n);
+    double var = 0.0;
+    for (unsigned idx = 0; idx < n; ++idx) { const double d = xsub(value(idx), avg); var = xadd(var, xmul(d, d)); }
+    var = xdiv(var, (double)(n - 1));                       // graphwidget.cpp:241
+    if (!(var - var == 0.0)) var = 0.0;                     // not finite (one sample): graphwidget.cpp:243-245
+    out->mean[k] = avg; out->stddev[k] = xsqrt(var); out->vmin[k] = lo; out->vmax[k] = hi;
+}
+
+// Maxwell-Boltzmann overlay of the speed histogram (graphwidget.cpp:55-73: f(v) N binsize at the left bin edges) and the
+// chi-square of the device histogram against it over the bins that expect more than five atoms.
+__global__ void __launch_bounds__(256)
+speed_mb_kernel(unsigned nbins, double vmax, double kT, double mass, double natoms,
+                const unsigned long long* __restrict__ counts, double* __restrict__ expected, double* __restrict__ chi2_out) {
+    __shared__ double red[32];
+    __shared__ double red2[32];
+    double chi = 0.0, used = 0.0;
+    const double binsize = vmax / (double)nbins;
+    const double pref = 4.0 * 3.14159265358979323846 * pow(mass / (2.0 * 3.14159265358979323846 * kT), 1.5);
+    for (unsigned b = threadIdx.x; b < nbins; b += blockDim.x) {
+        const double v = binsize * (double)b;
+        const double e = pref * v * v * exp(-mass * v * v / (2.0 * kT)) * natoms * binsize;
+        expected[b] = e;
+        if (e > 5.0) { const double d = (double)counts[b] - e; chi += d * d / e; used += 1.0; }
+    }
+    chi = block_sum(chi, red);
+    used = block_sum(used, red2);
+    if (threadIdx.x == 0) { chi2_out[0] = chi; chi2_out[1] = used; }
 }
 
 // FP64 roofline denominator, measured in place (ljgpu_measure_fp64_peak): eight independent DFMA chains per thread.

@@ -164,7 +164,8 @@ struct ljgpu_sim {
     double* apf[3] = {nullptr, nullptr, nullptr}; unsigned nsplit = 1, jchunk = 0;
 
     StepCtrl* ctrl = nullptr; StepCtrl* h_ctrl = nullptr;
-    HistEntry* hist = nullptr;
+    HistEntry* hist = nullptr; HistEntry* samples = nullptr;
+    SeriesStatsOut* d_stats = nullptr; double* d_mb = nullptr;       // device statistics of the GraphWidget series / speed histogram
 
     // scratch of the neighbour-count probe (allocated on first use): the probe bins a COPY of the published positions,
     // so it never touches the integrator's own binning, lists or displacement accumulators
@@ -312,7 +313,7 @@ ljgpu_sim::~ljgpu_sim() {
     dfree(cstart); dfree(cend); dfree(ccount);
     dfree(nl); dfree(nl_count); dfree(nl_in); dfree(nl_in_count); dfree(tsrc); dfree(toff);
     dfree(partial_epot); dfree(kick_sums); dfree(partial_pred);
-    dfree(ctrl); dfree(hist); dfree(out3); dfree(out_u32); dfree(hist_counts);
+    dfree(ctrl); dfree(hist); dfree(samples); dfree(d_stats); dfree(d_mb); dfree(out3); dfree(out_u32); dfree(hist_counts);
     dfree(probe_pos); dfree(probe_sorted); dfree(probe_keys); dfree(probe_vals); dfree(probe_cstart); dfree(probe_cend); dfree(probe_ccount);
     if (st_copy) { cudaStreamSynchronize(st_copy); cudaStreamDestroy(st_copy); }
     for (int b = 0; b < 2; ++b) {
@@ -393,6 +394,13 @@ void ljgpu_sim::allocate() {
     CK(cudaMallocHost(&h_ctrl, sizeof(StepCtrl))); std::memset(h_ctrl, 0, sizeof(StepCtrl));
     CK(cudaMallocHost(&h_scalar, 64));
     CK(cudaMalloc(&hist, sizeof(HistEntry) * kHistCap)); CK(cudaMemset(hist, 0, sizeof(HistEntry) * kHistCap));
+    CK(cudaMalloc(&samples, sizeof(HistEntry) * kSampleCap)); CK(cudaMemset(samples, 0, sizeof(HistEntry) * kSampleCap));
+    CK(cudaMalloc(&d_stats, sizeof(SeriesStatsOut))); CK(cudaMalloc(&d_mb, sizeof(double) * (kMaxBins + 2)));
+    {   // the sampled series: every 1000th step, as ThreadIntegrate::run emits them (threadintegrate.cpp:57-62)
+        StepCtrl init{};
+        init.samples = samples; init.sample_stride = 1000u;
+        CK(cudaMemcpy(ctrl, &init, sizeof(StepCtrl), cudaMemcpyHostToDevice));
+    }
     CK(cudaMalloc(&out3, 3 * N * 8));
     CK(cudaMalloc(&out_u32, N * 4));
     CK(cudaMalloc(&hist_counts, kMaxBins * sizeof(unsigned long long)));
@@ -1507,6 +1515,48 @@ int ljgpu_get_speed_histogram(ljgpu_sim* s, uint32_t nbins, double vmax, uint64_
         static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "");
         CK(cudaMemcpyAsync(counts, s->hist_counts, nbins * sizeof(uint64_t), cudaMemcpyDeviceToHost, s->st));
         s->sync();
+    });
+}
+
+int ljgpu_set_sample_stride(ljgpu_sim* s, uint32_t stride) {
+    return with_sim(s, [&] {
+        s->sync();
+        CK(cudaMemcpyAsync(&s->ctrl->sample_stride, &stride, sizeof(uint32_t), cudaMemcpyHostToDevice, s->st));
+        CK(cudaMemsetAsync(&s->ctrl->sample_head, 0, sizeof(unsigned long long), s->st));     // a new series
+        s->sync();
+    });
+}
+
+int ljgpu_get_graph_stats(ljgpu_sim* s, int reference_truncation, ljgpu_graph_stats* out) {
+    if (!out) return fail(LJGPU_EINVAL, "null argument");
+    static_assert(sizeof(ljgpu_graph_stats) == sizeof(SeriesStatsOut), "same layout on both sides of the ABI");
+    return with_sim(s, [&] {
+        series_stats_kernel<<<1, 32, 0, s->st>>>(s->ctrl, reference_truncation, s->d_stats);
+        s->check_launch("series_stats");
+        CK(cudaMemcpyAsync(out, s->d_stats, sizeof(SeriesStatsOut), cudaMemcpyDeviceToHost, s->st));
+        s->sync();
+    });
+}
+
+int ljgpu_get_speed_statistics(ljgpu_sim* s, uint32_t nbins, double vmax, uint64_t* counts, double* expected,
+                               double* chi2, uint32_t* bins_used) {
+    if (!counts || !expected || !chi2 || !bins_used) return fail(LJGPU_EINVAL, "null argument");
+    if (nbins == 0 || nbins > (uint32_t)kMaxBins || !(vmax > 0)) return fail(LJGPU_EINVAL, "nbins must be 1..1024 and vmax positive");
+    return with_sim(s, [&] {
+        CK(cudaMemsetAsync(s->hist_counts, 0, nbins * sizeof(unsigned long long), s->st));
+        const unsigned blocks = std::max(1u, std::min(cdiv(s->n, 256), 148u * 8u));
+        speed_histogram_kernel<<<blocks, 256, 0, s->st>>>(s->n, s->v[0], s->v[1], s->v[2], nbins, vmax, s->hist_counts);
+        s->check_launch("speed_histogram");
+        if (s->slab.on)
+            NCK(ljnccl::api().AllReduce(s->hist_counts, s->hist_counts, nbins, ljnccl::kUint64, ljnccl::kSum, s->slab.comm, s->st));
+        speed_mb_kernel<<<1, 256, 0, s->st>>>(nbins, vmax, s->p.kT, s->p.mass, (double)s->nglobal, s->hist_counts, s->d_mb + 2, s->d_mb);
+        s->check_launch("speed_mb");
+        double res[2] = {0.0, 0.0};
+        CK(cudaMemcpyAsync(counts, s->hist_counts, nbins * sizeof(uint64_t), cudaMemcpyDeviceToHost, s->st));
+        CK(cudaMemcpyAsync(expected, s->d_mb + 2, nbins * sizeof(double), cudaMemcpyDeviceToHost, s->st));
+        CK(cudaMemcpyAsync(res, s->d_mb, 2 * sizeof(double), cudaMemcpyDeviceToHost, s->st));
+        s->sync();
+        *chi2 = res[0]; *bins_used = (uint32_t)res[1];
     });
 }
 

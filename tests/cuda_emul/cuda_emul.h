@@ -310,6 +310,8 @@ template <class T> inline T __ldg(const T* p) { return *p; }
 inline long long clock64() { return std::chrono::steady_clock::now().time_since_epoch().count(); }
 inline void __nanosleep(unsigned) { if (ljemul::t_run) { ++ljemul::t_run->progress; ljemul::yield_fiber(); } }   // waiting for another "device" is not a deadlock
 using std::floor;
+using std::pow;
+using std::exp;
 using std::fma;
 using std::sqrt;
 using std::fmax;

@@ -291,6 +291,57 @@ def test_speed_histogram_bit_exact(lj):
     assert np.array_equal(g.get_speed_histogram(16, 1.5), ol.oracle_speed_histogram(vx, vy, vz, 16, 1.5))
 
 
+def test_graph_widget_statistics_on_the_device(lj):
+    """(f)3: GraphWidget's running mean / sigma band / axis range of the sampled energy series and the Maxwell-Boltzmann
+    overlay of the speed histogram are evaluated on the device; the series statistics must equal a host evaluation of
+    graphwidget.cpp:139-203, :235-248 (host/graphstats.h restates it) bit for bit, in both summation modes."""
+    cfg = ol.config(4096)
+    _, g = make_pair(lj, cfg, 3)
+    g.set_sample_stride(10)                      # the reference samples every 1000 iterations; 10 keeps the test short
+    g.integrate_n(1, 1205, DT)
+    steps, ek, ep = g.get_energy_history(1205)
+    pick = [k for k, s_ in enumerate(steps) if s_ % 10 == 0]
+    assert len(pick) == 120
+    series = {"ekin": ek[pick], "epot": ep[pick], "etot": ek[pick] + ep[pick]}
+
+    def host_stats(values, truncate):
+        if truncate:
+            acc = 0
+            for v in values:
+                acc = int(acc + float(v))          # std::accumulate(..., 0): int accumulator, graphwidget.cpp:147
+            total = float(acc)
+        else:
+            total = 0.0
+            for v in values:
+                total = total + float(v)
+        avg = total / len(values)
+        var = 0.0
+        for v in values:
+            d = float(v) - avg
+            var = var + d * d
+        var = var / (len(values) - 1)
+        return avg, float(np.sqrt(var))
+
+    for truncate in (False, True):
+        st = g.get_graph_stats(reference_truncation=truncate)
+        assert st["n"] == 120
+        for name, values in series.items():
+            avg, sd = host_stats(values, truncate)
+            assert st[name]["mean"] == avg and st[name]["stddev"] == sd, (name, truncate, st[name], avg, sd)
+            assert st[name]["min"] == values.min() and st[name]["max"] == values.max()
+    # speed histogram + Maxwell-Boltzmann overlay + chi-square
+    counts, expected, chi2, used = g.get_speed_statistics(100, 10.0)
+    assert np.array_equal(counts, g.get_speed_histogram(100, 10.0))
+    want = ol.oracle_maxwell_boltzmann(cfg["kT"], cfg["mass"], cfg["nr_particles"], 100, 10.0)
+    assert np.max(np.abs(expected - want)) <= 1e-12 * want.max()
+    mask = want > 5.0
+    assert used == int(mask.sum())
+    want_chi2 = float((((counts[mask].astype(np.float64) - want[mask]) ** 2) / want[mask]).sum())
+    assert abs(chi2 - want_chi2) < 1e-9 * max(1.0, want_chi2)
+    assert chi2 / used < 3.0                       # thermostatted liquid: the histogram follows the overlay
+    g.close()
+
+
 def test_changing_dt_and_tau_between_steps(lj):
     """dt is an argument of every integrate() call and tau is re-read every step by the reference."""
     cfg = ol.config(4096)
