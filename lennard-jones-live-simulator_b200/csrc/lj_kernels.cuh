@@ -703,45 +703,6 @@ __global__ void slab_publish_wait_kernel(Mailbox* mine, int world, unsigned long
     if ((int)threadIdx.x < world) wait_flag(&mine->pub_flag[threadIdx.x], seq, &mine->error);
 }
 
-// kick_drift_kernel with the halo push folded in (slab path over peer memory, LJGPU_SLAB_FUSED_PUSH=1): the threads
-// that move an atom of the first / last cell layer also store its new position into the neighbour's halo slot, and
-// the last block to finish publishes this device's fastest-atom value and raises the sequence flags - one launch
-// and one pass over the boundary atoms less than kick_drift + halo_push, and the flags go up earlier.
-__global__ void __launch_bounds__(kBlock)
-kick_drift_push_kernel(LJConst c, double dt, double a, StepCtrl* __restrict__ ctrl,
-                       double4* __restrict__ pos,
-                       double* __restrict__ dijx, double* __restrict__ dijy, double* __restrict__ dijz,
-                       double* __restrict__ vx, double* __restrict__ vy, double* __restrict__ vz,
-                       const double* __restrict__ fx, const double* __restrict__ fy, const double* __restrict__ fz,
-                       unsigned c_lo, unsigned c_hi, double4* __restrict__ down_dst, double4* __restrict__ up_dst,
-                       Mailbox* down_mail, Mailbox* up_mail, unsigned int* ticket) {
-    __shared__ double red[32];
-    __shared__ double red2[32];
-    if (ctrl->stop) return;
-    const unsigned i = blockIdx.x * kBlock + threadIdx.x;
-    double4 p;
-    kick_drift_body<true>(c, dt, a, ctrl, pos, dijx, dijy, dijz, vx, vy, vz, fx, fy, fz, i, p, red, red2);
-    if (i < c.n) {                                   // a one-layer slab pushes every atom both ways
-        if (i < c_lo) st_pos(down_dst + i, p);
-        if (i >= c.n - c_hi) st_pos(up_dst + (i - (c.n - c_hi)), p);
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        if (atomicAdd(ticket, 1u) == gridDim.x - 1) {          // last block: every store and every vmax2 update is fenced
-            *ticket = 0;
-            const double v2 = __longlong_as_double((long long)*(volatile unsigned long long*)&ctrl->vmax2);
-            down_mail->nb_vmax2[1] = v2;
-            up_mail->nb_vmax2[0] = v2;
-            __threadfence_system();
-            const unsigned long long seq = ctrl->halo_seq + 1ull;
-            ctrl->halo_seq = seq;
-            st_sys_u64(&down_mail->halo_flag[1], seq);
-            st_sys_u64(&up_mail->halo_flag[0], seq);
-        }
-    }
-}
-
 // Local reductions + all-reduce through the mailboxes + publication, one launch: the constructor's energy
 // (what = 1, epot only) and the predicted kinetic sum (what = 2).  The per-step variant lives in kick2_kernel<true>.
 __global__ void __launch_bounds__(kFinalizeThreads)

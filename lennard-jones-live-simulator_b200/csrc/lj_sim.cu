@@ -7,6 +7,8 @@
 #include "../../include/ljgpu.h"
 
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include <chrono>
 #include <cstdlib>
 #include <cmath>
@@ -119,6 +121,11 @@ struct HostTrace {
 
 struct ljgpu_sim {
     std::mutex mu;
+    // A query from another thread (the GUI's get_velocities_copy ...) must not wait for a whole ljgpu_step_n call: callers
+    // announce themselves in `waiting`, and the stepping loop hands the lock over between two batches (a batch is a few
+    // dozen steps: the state is complete and consistent there).
+    std::atomic<int> waiting{0};
+    std::unique_lock<std::mutex>* held = nullptr;       // the lock of the call that is executing (set by with_sim)
     ljgpu_params p{};
     int mode = 0;
     int device = 0;
@@ -132,6 +139,12 @@ struct ljgpu_sim {
     size_t cap_atoms = 0, pos_cap = 0;
     Slab slab;
     bool failed = false;            // a call on this handle threw: NCCL state is undefined
+    // slab path: a capacity check that fails on ONE device must not make it leave a sequence of collectives the others are
+    // still in.  The failing device records the reason, keeps every exchange well-formed (skips what does not fit), and all
+    // devices learn about it in agree() - one small all-reduce per re-binning - and throw the same error together.
+    unsigned slab_fail = 0;
+    void slab_note_failure(unsigned code) { if (!slab_fail) slab_fail = code; }
+    void agree();
 
     // state, device order (cell-sorted on the list paths, caller order on the all-pairs path)
     double4* pos = nullptr; double4* pos_tmp = nullptr;
@@ -553,8 +566,9 @@ void ljgpu_sim::migrate() {
     const unsigned n_down = hc[0], n_up = hc[1];
     const unsigned first_down = n_down ? hc[2] : n, first_up = n_up ? hc[3] : n;
     const unsigned n_stay = n - n_down - n_up;
-    if (n_down > slab.mover_cap || n_up > slab.mover_cap) throw LjError(LJGPU_ESTATE, "too many atoms crossing a slab face");
-    // counts first
+    // counts first.  A message that would not fit the mover buffers is dropped by BOTH ends of the link (each sees the
+    // same count against the same capacity), the failure is recorded and reported by agree().
+    if (n_down > slab.mover_cap || n_up > slab.mover_cap) slab_note_failure(1);
     slab.h_xchg[0] = n_down; slab.h_xchg[1] = n_up;
     CK(cudaMemcpyAsync(slab.xchg, slab.h_xchg, 8, cudaMemcpyHostToDevice, st));
     NCK(A.GroupStart());
@@ -565,19 +579,25 @@ void ljgpu_sim::migrate() {
     NCK(A.GroupEnd());
     CK(cudaMemcpyAsync(slab.h_xchg + 2, slab.xchg + 2, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    const unsigned from_up = slab.h_xchg[2], from_down = slab.h_xchg[3];
-    if (from_up > slab.mover_cap || from_down > slab.mover_cap) throw LjError(LJGPU_ESTATE, "too many atoms arriving over a slab face");
-    if ((size_t)n_stay + from_up + from_down > cap_atoms) throw LjError(LJGPU_ESTATE, "slab capacity exceeded after migration");
+    if (slab.h_xchg[2] > slab.mover_cap || slab.h_xchg[3] > slab.mover_cap) slab_note_failure(1);
+    auto fits = [&](unsigned k) { return k > slab.mover_cap ? 0u : k; };
+    const unsigned s_down = fits(n_down), s_up = fits(n_up);                      // what actually travels
+    unsigned from_up = fits(slab.h_xchg[2]), from_down = fits(slab.h_xchg[3]);
 
-    if (n_down) { pack_movers_kernel<<<cdiv(n_down, kBlock), kBlock, 0, st>>>(first_down, n_down, pos, v[0], v[1], v[2], f[0], f[1], f[2], orig, slab.sendbuf[0]); check_launch("pack_movers"); }
-    if (n_up)   { pack_movers_kernel<<<cdiv(n_up, kBlock), kBlock, 0, st>>>(first_up, n_up, pos, v[0], v[1], v[2], f[0], f[1], f[2], orig, slab.sendbuf[1]); check_launch("pack_movers"); }
+    if (s_down) { pack_movers_kernel<<<cdiv(s_down, kBlock), kBlock, 0, st>>>(first_down, s_down, pos, v[0], v[1], v[2], f[0], f[1], f[2], orig, slab.sendbuf[0]); check_launch("pack_movers"); }
+    if (s_up)   { pack_movers_kernel<<<cdiv(s_up, kBlock), kBlock, 0, st>>>(first_up, s_up, pos, v[0], v[1], v[2], f[0], f[1], f[2], orig, slab.sendbuf[1]); check_launch("pack_movers"); }
     // data; at least one record per message so both sides always post matching calls
     NCK(A.GroupStart());
-    NCK(A.Send(slab.sendbuf[0], (size_t)std::max(n_down, 1u) * kMoverDoubles, ljnccl::kFloat64, slab.down, slab.comm, st));
-    NCK(A.Send(slab.sendbuf[1], (size_t)std::max(n_up, 1u) * kMoverDoubles, ljnccl::kFloat64, slab.up, slab.comm, st));
+    NCK(A.Send(slab.sendbuf[0], (size_t)std::max(s_down, 1u) * kMoverDoubles, ljnccl::kFloat64, slab.down, slab.comm, st));
+    NCK(A.Send(slab.sendbuf[1], (size_t)std::max(s_up, 1u) * kMoverDoubles, ljnccl::kFloat64, slab.up, slab.comm, st));
     NCK(A.Recv(slab.recvbuf[1], (size_t)std::max(from_up, 1u) * kMoverDoubles, ljnccl::kFloat64, slab.up, slab.comm, st));
     NCK(A.Recv(slab.recvbuf[0], (size_t)std::max(from_down, 1u) * kMoverDoubles, ljnccl::kFloat64, slab.down, slab.comm, st));
     NCK(A.GroupEnd());
+    if ((size_t)n_stay + from_up + from_down > cap_atoms) {                       // arrivals that do not fit are not unpacked
+        slab_note_failure(2);
+        from_down = (unsigned)std::min<size_t>(from_down, cap_atoms - n_stay);
+        from_up = (unsigned)std::min<size_t>(from_up, cap_atoms - n_stay - from_down);
+    }
     // arrivals overwrite the tail that held my leavers (their data has been packed)
     if (from_down) { unpack_movers_kernel<<<cdiv(from_down, kBlock), kBlock, 0, st>>>(n_stay, from_down, slab.recvbuf[0], pos, v[0], v[1], v[2], f[0], f[1], f[2], orig); check_launch("unpack_movers"); }
     if (from_up)   { unpack_movers_kernel<<<cdiv(from_up, kBlock), kBlock, 0, st>>>(n_stay + from_down, from_up, slab.recvbuf[1], pos, v[0], v[1], v[2], f[0], f[1], f[2], orig); check_launch("unpack_movers"); }
@@ -614,9 +634,16 @@ void ljgpu_sim::halo_setup() {
     slab.c_lo = 0; slab.c_hi = 0;
     for (uint32_t q : lo) slab.c_lo += q;
     for (uint32_t q : hi) slab.c_hi += q;
-    if ((size_t)n + slab.h_lo + slab.h_hi > pos_cap) throw LjError(LJGPU_ESTATE, "halo does not fit the position buffer");
+    bool halo_fits = (size_t)n + slab.h_lo + slab.h_hi <= pos_cap;
+    if (const char* e = std::getenv("LJGPU_TEST_FAIL_RANK"))        // fault injection for the tests: this device "runs out of halo space"
+        if (std::atoi(e) == slab.rank && rebuilds >= 1) halo_fits = false;
+    if (!halo_fits) {     // keep going with empty halo layers; the neighbours are told below not to push into them
+        slab_note_failure(3);
+        slab.h_lo = slab.h_hi = 0;
+        for (int k = 0; k < 2; ++k) { CK(cudaMemsetAsync(slab.hcount[k], 0, (size_t)nc2 * 4, st)); CK(cudaMemsetAsync(slab.hoff[k], 0, (size_t)nc2 * 4, st)); }
+    }
     if (slab.p2p) {     // where my boundary layers land in the neighbours' position arrays
-        slab.h_xchg[10] = n; slab.h_xchg[11] = slab.h_lo;
+        slab.h_xchg[10] = halo_fits ? n : 0xffffffffu; slab.h_xchg[11] = slab.h_lo;      // n = all ones: do not push to me
         CK(cudaMemcpyAsync(slab.xchg + 10, slab.h_xchg + 10, 8, cudaMemcpyHostToDevice, st));
         NCK(A.GroupStart());
         NCK(A.Send(slab.xchg + 10, 2, ljnccl::kUint32, slab.down, slab.comm, st));
@@ -628,6 +655,11 @@ void ljgpu_sim::halo_setup() {
         CK(cudaStreamSynchronize(st));
         slab.nb_n[0] = slab.h_xchg[12]; slab.nb_hlo[0] = slab.h_xchg[13];
         slab.nb_n[1] = slab.h_xchg[14]; slab.nb_hlo[1] = slab.h_xchg[15];
+        if (slab.nb_n[0] == 0xffffffffu || slab.nb_n[1] == 0xffffffffu) {      // a neighbour has no room for my boundary layer
+            slab_note_failure(3);
+            slab.nb_n[0] = slab.nb_n[1] = 0; slab.nb_hlo[0] = slab.nb_hlo[1] = 0;
+            slab.c_lo = slab.c_hi = 0;                                          // nothing is pushed until everybody has thrown
+        }
     }
     halo_cells_kernel<<<cdiv(nc2, kBlock), kBlock, 0, st>>>(nc2, 0, n, slab.hcount[0], slab.hoff[0], cstart, ccount);
     check_launch("halo_cells");
@@ -728,6 +760,22 @@ void ljgpu_sim::setup_p2p() {
     slab.p2p = true;
 }
 
+// Slab path: one all-reduce (max) of the devices' failure codes; when any device failed, ALL of them throw the same
+// LJGPU_ESTATE error here, so nobody is left waiting in a collective for a device that has gone away.
+void ljgpu_sim::agree() {
+    slab.h_xchg[8] = slab_fail;
+    CK(cudaMemcpyAsync(slab.xchg + 8, slab.h_xchg + 8, 4, cudaMemcpyHostToDevice, st));
+    NCK(ljnccl::api().AllReduce(slab.xchg + 8, slab.xchg + 8, 1, ljnccl::kUint32, ljnccl::kMax, slab.comm, st));
+    CK(cudaMemcpyAsync(slab.h_xchg + 8, slab.xchg + 8, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const unsigned code = slab.h_xchg[8];
+    if (!code) return;
+    static const char* what[] = {"", "too many atoms crossing a slab face at once", "a slab holds more atoms than its capacity after migration",
+                                 "a halo layer does not fit the position buffer", "a brick holds more home atoms than the brick kernel's work items cover",
+                                 "a cell neighbourhood does not fit in shared memory (density too inhomogeneous)"};
+    throw LjError(LJGPU_ESTATE, std::string("slab path: ") + what[std::min(code, 5u)] + (slab_fail == code ? " (on this device)" : " (reported by another device)"));
+}
+
 // Re-binning: the reference's list rebuild (.cpp:441-551) on the device layout: sort by cell, dij = 0
 // (.cpp:484-486), tile tables, and on the Verlet path the list itself.
 void ljgpu_sim::rebuild() {
@@ -761,14 +809,19 @@ void ljgpu_sim::rebuild() {
     // launch shapes only grow (a few spare shared-memory records cost nothing; a changed shape costs a graph capture)
     tcap = std::max(tcap, ((h_ctrl->max_tile + 63) / 64) * 64);
     tile_ipb = std::max(tile_ipb, (h_ctrl->max_home + 31) / 32);
-    if (tile_ipb > (unsigned)kBrickItemsMax) throw LjError(LJGPU_ESTATE, "a brick holds more home atoms than the brick kernel's work items cover");
+    if (tile_ipb > (unsigned)kBrickItemsMax) {
+        if (!slab.on) throw LjError(LJGPU_ESTATE, "a brick holds more home atoms than the brick kernel's work items cover");
+        slab_note_failure(4); tile_ipb = kBrickItemsMax;
+    }
     nb_force = nblocks_tile * tile_ipb;
     // as many tiles in flight per CTA as fit beside the kernel's static shared memory (the ring never needs more than four)
     tile_slots = (unsigned)std::min<size_t>(kBrickSlotsMax, (size_t)(220 * 1024) / ((size_t)tcap * kTileRecBytes));
     if (const char* e = std::getenv("LJGPU_BRICK_SLOTS")) tile_slots = std::max(2u, std::min(tile_slots, (unsigned)std::atoi(e)));   // tuning knob
-    if (tile_slots < 2)
-        throw LjError(LJGPU_ESTATE, "a cell neighbourhood does not fit in shared memory (density too inhomogeneous)");
-    if (h_ctrl->max_tile > 65535) throw LjError(LJGPU_ESTATE, "tile too large for 16-bit list indices");
+    if (tile_slots < 2 || h_ctrl->max_tile > 65535) {
+        if (!slab.on) throw LjError(LJGPU_ESTATE, "a cell neighbourhood does not fit in shared memory (density too inhomogeneous)");
+        slab_note_failure(5);
+    }
+    if (slab.on) agree();                   // every device throws here, or none does
     set_tile_attributes(this);
 
     lap("tile_table");
@@ -929,16 +982,7 @@ void ljgpu_sim::enqueue_step(bool prune_now, double dt) {
     c.dt_over_tau = dt / p.tau;                                          // .cpp:375
     c.dt = dt;
     cudaEvent_t ev = stage_begin();
-    static const bool fused_push_env = std::getenv("LJGPU_SLAB_FUSED_PUSH") != nullptr;
-    const bool fused_push = fused_push_env && slab.on && slab.p2p && list_mode();
-    if (fused_push) {
-        double4* down_dst = slab.peer_pos[0] + slab.nb_n[0] + slab.nb_hlo[0];
-        double4* up_dst = slab.peer_pos[1] + slab.nb_n[1];
-        kick_drift_push_kernel<<<nb_atoms(), kBlock, 0, st>>>(c, dt, a, ctrl, pos, dij[0], dij[1], dij[2],
-                                                              v[0], v[1], v[2], f[0], f[1], f[2],
-                                                              slab.c_lo, slab.c_hi, down_dst, up_dst,
-                                                              slab.peer_mail[slab.down], slab.peer_mail[slab.up], slab.push_ticket);
-    } else if (list_mode())
+    if (list_mode())
         kick_drift_kernel<true><<<nb_atoms(), kBlock, 0, st>>>(c, dt, a, ctrl, pos, dij[0], dij[1], dij[2],
                                                                v[0], v[1], v[2], f[0], f[1], f[2]);
     else
@@ -946,7 +990,7 @@ void ljgpu_sim::enqueue_step(bool prune_now, double dt) {
                                                                 v[0], v[1], v[2], f[0], f[1], f[2]);
     check_launch("kick_drift");
     stage_end(ST_KICK_DRIFT, ev);
-    if (slab.on && !fused_push) halo_exchange();
+    if (slab.on) halo_exchange();
     if (prune_now) {       // this step's force pass walks the outer list and emits the inner one
         cudaEvent_t pv = stage_begin();
         launch_tile<TILE_FORCE_PRUNE>(this, 1);
@@ -1098,6 +1142,14 @@ void ljgpu_sim::run_steps(unsigned first, unsigned nsteps, double dt) {
         if (done) dirty_since_rebuild = true;
         if (h_ctrl->stop) { HostTrace::Scope hs(htrace, HostTrace::REBUILD); rebuild(); }
         else if (done != batch) throw LjError(LJGPU_ESTATE, "step batch ended early without a rebuild request");
+        // between two batches the state is complete: let a waiting query in (not on slabs - every call there is collective,
+        // a query from another thread would have to be made on every rank at the same point anyway)
+        if (remaining && !slab.on && held && waiting.load(std::memory_order_acquire) > 0) {
+            held->unlock();
+            while (waiting.load(std::memory_order_acquire) > 0) std::this_thread::yield();
+            held->lock();
+            CK(cudaSetDevice(device));
+        }
     }
 }
 
@@ -1259,14 +1311,19 @@ int guarded(F&& fn) {
 }
 
 template <class F>
-int with_sim(ljgpu_sim* s, F&& fn) {
+int with_sim(ljgpu_sim* s, F&& fn, bool collective_state = false) {
     if (!s) return fail(LJGPU_EINVAL, "null simulation handle");
     const int rc = guarded([&] {
-        std::lock_guard<std::mutex> lk(s->mu);
+        s->waiting.fetch_add(1, std::memory_order_acq_rel);
+        std::unique_lock<std::mutex> lk(s->mu);
+        s->waiting.fetch_sub(1, std::memory_order_acq_rel);
+        struct Held { ljgpu_sim* s; ~Held() { s->held = nullptr; } } h{s};
+        s->held = &lk;
         CK(cudaSetDevice(s->device));
         fn();
     });
-    if (rc == LJGPU_ECUDA || rc == LJGPU_ENCCL || rc == LJGPU_ESTATE) s->failed = true;
+    // (an LJGPU_ESTATE refusal of a query leaves the handle usable; a failed step or re-binning does not)
+    if (rc == LJGPU_ECUDA || rc == LJGPU_ENCCL || (rc == LJGPU_ESTATE && collective_state)) s->failed = true;
     return rc;
 }
 
@@ -1397,7 +1454,7 @@ void ljgpu_destroy(ljgpu_sim* s) { delete s; }
 int ljgpu_set_state(ljgpu_sim* s, const double* x, const double* y, const double* z,
                     const double* vx, const double* vy, const double* vz) {
     if (!x || !y || !z || !vx || !vy || !vz) return fail(LJGPU_EINVAL, "null argument");
-    return with_sim(s, [&] { s->upload_state(x, y, z, vx, vy, vz); s->initial_forces(); });
+    return with_sim(s, [&] { s->upload_state(x, y, z, vx, vy, vz); s->initial_forces(); }, true);
 }
 
 int ljgpu_update_params(ljgpu_sim* s, const ljgpu_params* p) {
@@ -1425,12 +1482,12 @@ int ljgpu_update_params(ljgpu_sim* s, const ljgpu_params* p) {
 }
 
 int ljgpu_step(ljgpu_sim* s, uint32_t step, double dt) {
-    return with_sim(s, [&] { s->run_steps(step, 1, dt); });
+    return with_sim(s, [&] { s->run_steps(step, 1, dt); }, true);
 }
 
 int ljgpu_step_publish(ljgpu_sim* s, uint32_t step, double dt, double* x, double* y, double* z) {
     if (!x || !y || !z) return fail(LJGPU_EINVAL, "null argument");
-    return with_sim(s, [&] { s->step_publish(step, dt, x, y, z); });
+    return with_sim(s, [&] { s->step_publish(step, dt, x, y, z); }, true);
 }
 
 int ljgpu_publish_wait(ljgpu_sim* s) {
@@ -1438,7 +1495,7 @@ int ljgpu_publish_wait(ljgpu_sim* s) {
 }
 
 int ljgpu_step_n(ljgpu_sim* s, uint32_t first, uint32_t n, double dt) {
-    return with_sim(s, [&] { s->run_steps(first, n, dt); });
+    return with_sim(s, [&] { s->run_steps(first, n, dt); }, true);
 }
 
 int ljgpu_step_n_timed(ljgpu_sim* s, uint32_t first, uint32_t n, double dt, double* device_ms) {
@@ -1456,7 +1513,7 @@ int ljgpu_step_n_timed(ljgpu_sim* s, uint32_t first, uint32_t n, double dt, doub
         float ms = 0.f;
         CK(cudaEventElapsedTime(&ms, ev.a, ev.b));
         *device_ms = ms;
-    });
+    }, true);
 }
 
 int ljgpu_get_positions(ljgpu_sim* s, double* x, double* y, double* z) {

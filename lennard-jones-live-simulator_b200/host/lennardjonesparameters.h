@@ -4,8 +4,20 @@
 //   (:52-58); set_param(name, value) inserts or overwrites (:66-68).  Values may be int, double or a
 //   numeric string, because the reference's New-simulation dialog stores strings
 //   (dialognewsimulation.cpp:73-78) and QVariant::value<T>() converts on read.
-// With LJGPU_WITH_QT defined the reference's own header can be used instead (same class name).
+//
+// LJGPU_WITH_QT: building inside the reference's Qt tree.  Then this header only forwards to the reference's OWN
+// lennardjonesparameters.h (QMap<QString, QVariant>, get_param<T>(const QString&), set_param(const QString&, const
+// QVariant&)), named by the build through -DLJGPU_QT_PARAMETERS_HEADER="<path>", so MainWindow (mainwindow.cpp:67-77)
+// and DialogNewSimulation (dialognewsimulation.cpp:73-78) keep filling a QVariant map without edits; the adapter class
+// needs nothing but get_param<double|int>(name), which both classes provide.  (tests/test_abi.py compiles the adapter
+// this way against the reference's header.)
 #pragma once
+#if defined(LJGPU_WITH_QT)
+#ifndef LJGPU_QT_PARAMETERS_HEADER
+#error "LJGPU_WITH_QT needs -DLJGPU_QT_PARAMETERS_HEADER=\"<reference>/src/simulator/lennardjonesparameters.h\""
+#endif
+#include LJGPU_QT_PARAMETERS_HEADER
+#else
 #include <cmath>
 #include <cstdlib>
 #include <map>
@@ -54,3 +66,4 @@ private:
         else return static_cast<T>(d);
     }
 };
+#endif  // LJGPU_WITH_QT

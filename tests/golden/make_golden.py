@@ -88,7 +88,51 @@ def one(name):
     print(json.dumps({name: out}))
 
 
+LIQUID_N, LIQUID_MELT, LIQUID_WINDOW, LIQUID_SAMPLE = 1048576, 300, 10, 256
+
+
+def liquid():
+    """BASELINE configs[3] at full size in a LIQUID state, from the reference's own code: 300 integrate() calls melt
+    the start lattice (6 list rebuilds), then a 10-step window.  Written to liquid_n1048576.json (energies of steps
+    300..310, bit-exact hex) and liquid_n1048576_sample.npz (positions and forces of every 256th atom - 4096 atoms - at
+    steps 300 and 310).  The device test starts from the same lattice, integrates the same 300 steps and must land on
+    these numbers to ~1e-11: 0.3 time units amplify the last-bit differences of the two force sums only mildly.
+    Takes about four minutes of CPU time (the reference needs 0.5-0.7 s per step at this size)."""
+    cfg = ol.config(LIQUID_N)
+    sim = ol.RefSim(cfg)
+    out = {"config": cfg, "dt": DT, "melt_steps": LIQUID_MELT, "window": LIQUID_WINDOW, "sample_every": LIQUID_SAMPLE, "energies": []}
+    sim.run(1, LIQUID_MELT, DT)
+    arrays = {}
+
+    def sample(tag):
+        for name, arr in zip(("x", "y", "z"), sim.positions()):
+            arrays[f"{name}_{tag}"] = arr[::LIQUID_SAMPLE].copy()
+        for name, arr in zip(("fx", "fy", "fz"), sim.forces()):
+            arrays[f"{name}_{tag}"] = arr[::LIQUID_SAMPLE].copy()
+
+    ek, ep, et = sim.energies()
+    out["energies"].append({"step": LIQUID_MELT, "ekin": hx(ek), "epot": hx(ep), "etot": hx(et)})
+    sample(LIQUID_MELT)
+    for s in range(LIQUID_MELT + 1, LIQUID_MELT + LIQUID_WINDOW + 1):
+        sim.integrate(s, DT)
+        ek, ep, et = sim.energies()
+        out["energies"].append({"step": s, "ekin": hx(ek), "epot": hx(ep), "etot": hx(et)})
+    sample(LIQUID_MELT + LIQUID_WINDOW)
+    cells, dims = sim.cell_ids()
+    out["final_crc_cell_ids"] = crc(cells)
+    f = np.stack(sim.forces(), axis=1)
+    out["force_rms_final"] = hx(np.sqrt((f ** 2).sum(axis=1).mean()))
+    out["generator"] = "tests/golden/make_golden.py --liquid (oracle/_ref/libljref.so = the reference's sources compiled unmodified)"
+    with open(os.path.join(HERE, "liquid_n1048576.json"), "w") as fh:
+        json.dump(out, fh, indent=1)
+    np.savez_compressed(os.path.join(HERE, "liquid_n1048576_sample.npz"), **arrays)
+    print("wrote liquid_n1048576.json / liquid_n1048576_sample.npz", file=sys.stderr)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "--liquid":
+        liquid()
+        return
     if len(sys.argv) > 1:
         one(sys.argv[1])
         return

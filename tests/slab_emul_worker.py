@@ -55,6 +55,17 @@ def main():
             err = ol.force_rel_error(g.get_forces_soa(), o.forces(), o.force_abs_sums()).max()
             assert err < tol, (tag, err)
 
+        if os.environ.get("LJGPU_TEST_FAIL_RANK"):
+            # fault injection: one device "runs out of halo space" at its second re-binning - EVERY device must come back
+            # with the same LJGPU_ESTATE error instead of waiting forever for the one that gave up
+            try:
+                g.integrate_n(1, 400, DT)
+                shared["out"][rank] = "no error"
+            except lj.LJGpuError as e:
+                shared["out"][rank] = str(e)
+            bar.wait()
+            g.close()
+            return
         check("step 0")
         assert np.array_equal(g.get_list_counts(), o.neighbor_counts())          # the list every "device" walks
         assert np.array_equal(g.get_neighbor_counts(cfg["rcut"] + cfg["shell"], True), o.neighbor_counts())
@@ -157,6 +168,11 @@ def main():
             print(f"--- rank {rank} ---\n{tb}", file=sys.stderr)
         sys.stderr.flush()
         os._exit(1)                                             # ranks stuck in a collective cannot be joined
+    if os.environ.get("LJGPU_TEST_FAIL_RANK"):
+        msgs = shared["out"]
+        assert all(isinstance(m, str) and "slab path: a halo layer does not fit" in m for m in msgs), msgs
+        print(f"SLAB EMUL FAILED TOGETHER world={world}: {msgs[0]}")
+        return
     rebuilds, used, info = shared["out"][0]
     print(f"SLAB EMUL OK world={world} N={n_atoms} rebuilds={rebuilds} inner_steps={used} info={info}")
 

@@ -107,3 +107,20 @@ def test_argument_validation_happens_before_device_use(lj, ljlib):
     rc = ljlib.ljgpu_create(C.byref(st), *[a.ctypes.data_as(C.c_void_p) for a in arrs], C.byref(h))
     assert rc == -1 and b"27-cell stencil" in ljlib.ljgpu_last_error()
     assert ljlib.ljgpu_create(None, *[None] * 6, C.byref(h)) == -1
+
+
+def test_adapter_compiles_against_the_references_qt_parameter_map(tmp_path):
+    """LJGPU_WITH_QT: the drop-in class built against the reference's OWN lennardjonesparameters.h (QMap<QString, QVariant>;
+    Qt types from oracle/shim here) - what MainWindow / DialogNewSimulation fill.  Runs where /root/reference exists."""
+    ref = "/root/reference/src/simulator"
+    if not os.path.exists(os.path.join(ref, "lennardjonesparameters.h")):
+        pytest.skip("reference sources not present (GPU box)")
+    pkg = os.path.join(ROOT, "lennard-jones-live-simulator_b200")
+    exe = str(tmp_path / "test_qt_switch")
+    cmd = ["g++", "-std=c++17", "-O1", "-DLJGPU_WITH_QT", f'-DLJGPU_QT_PARAMETERS_HEADER="{ref}/lennardjonesparameters.h"',
+           "-I", os.path.join(ROOT, "oracle", "shim"), "-I", os.path.join(pkg, "host"), "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "tests", "cpp", "test_qt_switch.cpp"), os.path.join(pkg, "host", "lennardjonessimulation.cpp"),
+           os.path.join(ref, "lennardjonesparameters.cpp"), "-L", pkg, "-lljgpu", f"-Wl,-rpath,{pkg}", "-lpthread", "-o", exe]
+    subprocess.run(cmd, check=True, timeout=300)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "QT SWITCH OK" in out.stdout, out.stdout + out.stderr

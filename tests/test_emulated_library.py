@@ -21,6 +21,7 @@ SKIP = [
     "test_liquid_window_strict_1e12[n65536]",
     "test_liquid_window_strict_1e12[n1048576]",
     "test_product_list_counts_match_reference",
+    "test_full_size_liquid_against_reference_golden_vectors",
 ]
 
 
@@ -56,6 +57,18 @@ def test_slab_path_on_the_emulated_library(world, nccl_loop):
     cmd = [sys.executable, os.path.join(HERE, "slab_emul_worker.py"), str(world), "32768", "5", "80", "200", "2"]
     out = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=1200)
     assert out.returncode == 0 and "SLAB EMUL OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
+
+
+def test_slab_failure_on_one_device_is_reported_by_all():
+    """A capacity check that fails on one device (injected: LJGPU_TEST_FAIL_RANK) must end the collective call on every
+    device with the same error, not leave the others waiting in a collective."""
+    import build_emul_lib
+    lib = build_emul_lib.build()
+    env = dict(os.environ, LJGPU_LIBRARY=lib, LJGPU_NO_GRAPH="1", LJGPU_TEST_FAIL_RANK="1",
+               LD_LIBRARY_PATH=os.path.join(HERE, "cuda_emul", "_build") + os.pathsep + os.environ.get("LD_LIBRARY_PATH", ""))
+    cmd = [sys.executable, os.path.join(HERE, "slab_emul_worker.py"), "3", "32768", "5", "80", "150", "2"]
+    out = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0 and "SLAB EMUL FAILED TOGETHER" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
 
 
 def test_edge_cases_on_the_emulated_library():

@@ -517,6 +517,50 @@ def test_full_size_n1048576_against_reference_golden_vectors(lj):
     assert np.max(np.abs(x[:8] - np.array([float.fromhex(h) for h in g["final"]["first8"]["x"]]))) < 1e-12
 
 
+def test_full_size_liquid_against_reference_golden_vectors(lj):
+    """BASELINE configs[3] at full size in a LIQUID state against numbers written by the reference's own code
+    (tests/golden/make_golden.py --liquid: 300 integrate() calls melt the start lattice - six list rebuilds - then a
+    10-step window; energies of steps 300..310 and positions + forces of every 256th atom at steps 300 and 310).  The
+    device starts from the same lattice and integrates the same 310 steps on its own.  0.3 time units amplify the
+    last-bit differences between the two implementations' force sums only mildly, so the trajectories are still the
+    same to ~1e-11: energies 1e-10 relative, sampled positions 1e-9, sampled forces 1e-8 of the rms force."""
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    with open(os.path.join(here, "liquid_n1048576.json")) as fh:
+        g = json.load(fh)
+    sample = np.load(os.path.join(here, "liquid_n1048576_sample.npz"))
+    cfg = g["config"]
+    params = lj.LennardJonesParameters(**cfg)
+    lj.host_rng_reset()
+    sim = lj.LennardJonesSimulation(params, lj.host_initialize(params))
+    every, melt, window = g["sample_every"], g["melt_steps"], g["window"]
+    frms = float.fromhex(g["force_rms_final"])
+    L = cfg["cell_length"]
+
+    def check_sample(step):
+        for name, arr in zip(("x", "y", "z"), sim.get_positions_soa()):
+            d = np.abs(arr[::every] - sample[f"{name}_{step}"])
+            d = np.minimum(d, np.abs(L - d))
+            assert d.max() < 1e-9, (step, name, d.max())
+        for name, arr in zip(("fx", "fy", "fz"), sim.get_forces_soa()):
+            d = np.abs(arr[::every] - sample[f"{name}_{step}"])
+            assert d.max() < 1e-8 * frms, (step, name, d.max())
+
+    sim.integrate_n(1, melt, g["dt"])
+    worst = 0.0
+    for rec in g["energies"]:
+        if rec["step"] > melt:
+            sim.integrate(rec["step"], g["dt"])
+        ek, ep, _ = sim.get_energies()
+        worst = max(worst, rel(ek, float.fromhex(rec["ekin"])), rel(ep, float.fromhex(rec["epot"])))
+        if rec["step"] == melt:
+            check_sample(melt)
+    check_sample(melt + window)
+    assert worst < 1e-10, worst
+    assert sim.get_timers()["rebuilds"] >= 6
+    assert _crc(sim.get_cell_ids()[0]) == g["final_crc_cell_ids"]
+    sim.close()
+
+
 def test_nve_energy_conservation_and_thermostat(lj):
     """Physics checks valid for both implementations (SURVEY.md section 4): Berendsen pulls T to kT;
     with tau = 1e300 lambda rounds to exactly 1 (NVE through the unchanged API) and the total energy is
