@@ -257,37 +257,6 @@ __device__ __forceinline__ void cp_async16(unsigned saddr, const void* g) {
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 #endif
 
-// Bulk asynchronous copies (the TMA engine's 1-D form, SASS UBLKCP): one thread hands the copy engine a contiguous
-// global range of 16 n bytes and a shared-memory destination, both 16-byte aligned; completion is signalled on an
-// mbarrier as a byte count.  The brick kernel stages a tile with two such copies per cell - no per-atom instructions.
-#ifdef LJ_EMUL
-__device__ __forceinline__ void mbar_init(unsigned long long*, unsigned) {}
-__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long*, unsigned) {}
-__device__ __forceinline__ bool mbar_try_wait(unsigned long long*, unsigned) { return true; }
-__device__ __forceinline__ void bulk_g2s(unsigned saddr, const void* g, unsigned bytes, unsigned long long*) { ljemul::smem_copy(saddr, g, bytes); }
-__device__ __forceinline__ void fence_proxy_async_smem() {}
-#else
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned parity) {
-    unsigned ok;
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok) : "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
-    return ok != 0u;
-}
-__device__ __forceinline__ void bulk_g2s(unsigned saddr, const void* g, unsigned bytes, unsigned long long* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 :: "r"(saddr), "l"(g), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
-}
-// orders what this thread has done or observed through the generic proxy (its own stores to the slot's padding; a
-// neighbour device's halo stores it has acquired through the mailbox flag) before later async-proxy (bulk copy) accesses
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async;" ::: "memory"); }
-#endif
-
 // Monotonic counters in shared memory with release / acquire semantics at CTA scope: how the staging warp and the
 // computing warps of the brick kernel hand tiles over (a counter, unlike an mbarrier phase bit, cannot alias when a
 // waiter is several hand-overs ahead).

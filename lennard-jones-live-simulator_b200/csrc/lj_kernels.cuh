@@ -75,7 +75,6 @@ __device__ __forceinline__ void kick_drift_body(const LJConst& c, double dt, dou
                   double* __restrict__ dijx, double* __restrict__ dijy, double* __restrict__ dijz,
                   double* __restrict__ vx, double* __restrict__ vy, double* __restrict__ vz,
                   const double* __restrict__ fx, const double* __restrict__ fy, const double* __restrict__ fz,
-                  double2* __restrict__ img_xy, double* __restrict__ img_z,
                   unsigned i, double4& p, double* red, double* red2) {
     // lambda = sqrt(1 + dt/tau * (ekin0/ekin - 1)),  ekin = 0.5*m*sum   (.cpp:354, :373-375)
     const double ek = xmul(xmul(0.5, c.mass), ctrl->pred_sum);
@@ -95,9 +94,6 @@ __device__ __forceinline__ void kick_drift_body(const LJConst& c, double dt, dou
         p.x = xadd(p.x, incx); p.y = xadd(p.y, incy); p.z = xadd(p.z, incz);
         vx[i] = ux; vy[i] = uy; vz[i] = uz;
         st_pos(pos + i, p);
-        if (TRACK_DISP) {      // list paths: the brick kernel stages its tiles from this image with bulk copies ((x, y) | z)
-            img_xy[i] = make_double2(p.x, p.y); img_z[i] = p.z;
-        }
         if (TRACK_DISP) v2 = fma(uz, uz, fma(uy, uy, ux * ux));
         if (TRACK_DISP) {
             const double ax = xadd(dijx[i], incx), ay = xadd(dijy[i], incy), az = xadd(dijz[i], incz);
@@ -132,13 +128,12 @@ kick_drift_kernel(LJConst c, double dt, double a, StepCtrl* __restrict__ ctrl,
                   double4* __restrict__ pos,
                   double* __restrict__ dijx, double* __restrict__ dijy, double* __restrict__ dijz,
                   double* __restrict__ vx, double* __restrict__ vy, double* __restrict__ vz,
-                  const double* __restrict__ fx, const double* __restrict__ fy, const double* __restrict__ fz,
-                  double2* __restrict__ img_xy, double* __restrict__ img_z) {
+                  const double* __restrict__ fx, const double* __restrict__ fy, const double* __restrict__ fz) {
     __shared__ double red[32];
     __shared__ double red2[32];
     if (ctrl->stop) return;
     double4 p;
-    kick_drift_body<TRACK_DISP>(c, dt, a, ctrl, pos, dijx, dijy, dijz, vx, vy, vz, fx, fy, fz, img_xy, img_z,
+    kick_drift_body<TRACK_DISP>(c, dt, a, ctrl, pos, dijx, dijy, dijz, vx, vy, vz, fx, fy, fz,
                                 blockIdx.x * kBlock + threadIdx.x, p, red, red2);
 }
 
@@ -662,18 +657,16 @@ slab_reduce_kernel(LJConst c, StepCtrl* __restrict__ ctrl,
 }
 
 // Halo push: my two boundary layers are contiguous slot ranges; write them straight into the halo slots of
-// the ring neighbours' tile images (peer pointers: (x, y) records and z column), then publish the step sequence in
-// their mailboxes.
+// the ring neighbours' position arrays (peer pointers), then publish the step sequence in their mailboxes.
 __global__ void __launch_bounds__(256)
-halo_push_kernel(StepCtrl* __restrict__ ctrl, const double2* __restrict__ img_xy, const double* __restrict__ img_z,
-                 unsigned n, unsigned c_lo, unsigned c_hi,
-                 double2* __restrict__ down_xy, double* __restrict__ down_z, double2* __restrict__ up_xy, double* __restrict__ up_z,
+halo_push_kernel(StepCtrl* __restrict__ ctrl, const double4* __restrict__ pos, unsigned n, unsigned c_lo, unsigned c_hi,
+                 double4* __restrict__ down_dst, double4* __restrict__ up_dst,
                  Mailbox* down_mail, Mailbox* up_mail, unsigned int* ticket) {
     if (ctrl->stop) return;
     const unsigned total = c_lo + c_hi;
     for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < total; k += gridDim.x * blockDim.x) {
-        if (k < c_lo) { down_xy[k] = img_xy[k]; down_z[k] = img_z[k]; }
-        else { const unsigned q = k - c_lo, s = (n - c_hi) + q; up_xy[q] = img_xy[s]; up_z[q] = img_z[s]; }
+        if (k < c_lo) st_pos(down_dst + k, ld_pos(pos + k));
+        else st_pos(up_dst + (k - c_lo), ld_pos(pos + (n - c_hi) + (k - c_lo)));
     }
     __threadfence_system();
     __syncthreads();
@@ -773,7 +766,7 @@ __global__ void slab_publish_kernel(LJConst c, StepCtrl* __restrict__ ctrl, Hist
 
 __global__ void __launch_bounds__(kBlock)
 permute_kernel(unsigned n, const uint32_t* __restrict__ perm, const double4* __restrict__ pos_tmp,
-               double4* __restrict__ pos, double2* __restrict__ img_xy, double* __restrict__ img_z,
+               double4* __restrict__ pos,
                const double* __restrict__ vxi, const double* __restrict__ vyi, const double* __restrict__ vzi,
                const double* __restrict__ fxi, const double* __restrict__ fyi, const double* __restrict__ fzi,
                const uint32_t* __restrict__ origi,
@@ -783,9 +776,7 @@ permute_kernel(unsigned n, const uint32_t* __restrict__ perm, const double4* __r
     const unsigned i = blockIdx.x * kBlock + threadIdx.x;
     if (i >= n) return;
     const unsigned s = perm[i];
-    const double4 q = pos_tmp[s];
-    pos[i] = q;
-    img_xy[i] = make_double2(q.x, q.y); img_z[i] = q.z;
+    pos[i] = pos_tmp[s];
     vxo[i] = vxi[s]; vyo[i] = vyi[s]; vzo[i] = vzi[s];
     fxo[i] = fxi[s]; fyo[i] = fyi[s]; fzo[i] = fzi[s];
     origo[i] = origi[s];

@@ -74,7 +74,7 @@ struct Slab {
     Mailbox* mail = nullptr;              // mine (peers write into it)
     Mailbox* peer_mail[kMaxPeers] = {nullptr};
     Mailbox** d_peer_mail = nullptr;      // device copy of the pointer table
-    double* peer_img[2] = {nullptr, nullptr};     // tile images (img: (x, y) records | z column) of my lower / upper neighbour
+    double4* peer_pos[2] = {nullptr, nullptr};    // position arrays of my lower / upper neighbour
     void* ipc_opened[3 * kMaxPeers + 2] = {nullptr};  // mappings to close
     int n_ipc_opened = 0;
     unsigned nb_n[2] = {0, 0}, nb_hlo[2] = {0, 0};   // owned atoms and lower-halo size of the two neighbours
@@ -148,12 +148,6 @@ struct ljgpu_sim {
 
     // state, device order (cell-sorted on the list paths, caller order on the all-pairs path)
     double4* pos = nullptr; double4* pos_tmp = nullptr;
-    // list paths: the positions once more as the brick kernel stages them - pos_cap (x, y) records, then the z column -
-    // own atoms followed by the two halo layers on a slab.  Written by kick/drift, the permutation and the halo push.
-    double* img = nullptr;
-    double2* img_xy() const { return reinterpret_cast<double2*>(img); }
-    double* img_z() const { return img + 2 * pos_cap; }
-    static double2* img_xy_of(double* base) { return reinterpret_cast<double2*>(base); }
     double* dij[3] = {nullptr, nullptr, nullptr};      // accumulated displacement since the last binning (.h:94)
     double* v[3] = {nullptr, nullptr, nullptr};
     double* f[3] = {nullptr, nullptr, nullptr};
@@ -167,7 +161,7 @@ struct ljgpu_sim {
     SortScratch scr;
 
     // shared-memory tiles (lj_tile.cuh) and the Verlet list of 16-bit tile indices
-    uint32_t *tsrc = nullptr, *toff = nullptr, *trun = nullptr;
+    uint32_t *tsrc = nullptr, *toff = nullptr;
     unsigned bxd = kTileBX, byd = kTileBY, bzd = kTileBZ;      // brick size in cells
     unsigned nbx = 0, nby = 0, nbz = 0, nblocks_tile = 0, tcap = 0, tile_slots = 2, tile_ipb = 1;
     int num_sms = 148;
@@ -285,7 +279,7 @@ struct ljgpu_sim {
     unsigned nb_atoms() const { return std::max(1u, cdiv(n, kBlock)); }
     TileGrid tile_grid() const {
         return TileGrid{nc, ncz, slab.on ? 0u : 1u, slab.on ? 1u : 0u, slab.on ? slab.nzl : nc,
-                        bxd, byd, bzd, nbx, nby, nbz, nblocks_tile, tsrc, toff, trun};
+                        bxd, byd, bzd, nbx, nby, nbz, nblocks_tile, tsrc, toff};
     }
 
     void setup_constants();
@@ -326,11 +320,11 @@ ljgpu_sim::~ljgpu_sim() {
     if (st) cudaStreamSynchronize(st);
     // after a failure the peers may be inside a collective this rank will never join: abort, do not wait
     if (slab.comm) { if (failed) ljnccl::api().CommAbort(slab.comm); else ljnccl::api().CommDestroy(slab.comm); }
-    dfree(pos); dfree(pos_tmp); dfree(img);
+    dfree(pos); dfree(pos_tmp);
     for (int k = 0; k < 3; ++k) { dfree(dij[k]); dfree(v[k]); dfree(f[k]); dfree(v_alt[k]); dfree(f_alt[k]); dfree(apf[k]); }
     dfree(orig); dfree(orig_alt); dfree(keys); dfree(vals);
     dfree(cstart); dfree(cend); dfree(ccount);
-    dfree(nl); dfree(nl_count); dfree(nl_in); dfree(nl_in_count); dfree(tsrc); dfree(toff); dfree(trun);
+    dfree(nl); dfree(nl_count); dfree(nl_in); dfree(nl_in_count); dfree(tsrc); dfree(toff);
     dfree(partial_epot); dfree(kick_sums); dfree(partial_pred);
     dfree(ctrl); dfree(hist); dfree(samples); dfree(d_stats); dfree(d_mb); dfree(out3); dfree(out_u32); dfree(hist_counts);
     dfree(probe_pos); dfree(probe_sorted); dfree(probe_keys); dfree(probe_vals); dfree(probe_cstart); dfree(probe_cend); dfree(probe_ccount);
@@ -402,8 +396,8 @@ void ljgpu_sim::allocate() {
     }
     const size_t A = cap_atoms;
     const unsigned nbmax = cdiv(A, kBlock);
-    CK(cudaMalloc(&pos, A * sizeof(double4)));
-    CK(cudaMemset(pos, 0, A * sizeof(double4)));
+    CK(cudaMalloc(&pos, pos_cap * sizeof(double4)));
+    CK(cudaMemset(pos, 0, pos_cap * sizeof(double4)));
     for (int k = 0; k < 3; ++k) {
         CK(cudaMalloc(&v[k], A * 8)); CK(cudaMalloc(&f[k], A * 8));
         CK(cudaMemset(f[k], 0, A * 8));
@@ -428,8 +422,6 @@ void ljgpu_sim::allocate() {
 
     if (list_mode()) {
         CK(cudaMalloc(&pos_tmp, A * sizeof(double4)));
-        CK(cudaMalloc(&img, (3 * pos_cap + 2) * 8));            // (+2: a cell's z column is copied as its 16-byte-aligned envelope)
-        CK(cudaMemset(img, 0, (3 * pos_cap + 2) * 8));
         for (int k = 0; k < 3; ++k) {
             CK(cudaMalloc(&dij[k], A * 8)); CK(cudaMalloc(&v_alt[k], A * 8)); CK(cudaMalloc(&f_alt[k], A * 8));
         }
@@ -456,7 +448,6 @@ void ljgpu_sim::allocate() {
             }
         }
         CK(cudaMalloc(&tsrc, (size_t)nblocks_tile * kTileCellsMax * 4));
-        CK(cudaMalloc(&trun, (size_t)nblocks_tile * kTileCellsMax * 4));
         CK(cudaMalloc(&toff, (size_t)nblocks_tile * (kTileCellsMax + 1) * 4));
         nb_force = nblocks_tile * kBrickItemsMax;                  // one partial per (brick, work item): room for the most items a brick may have
     } else {
@@ -554,7 +545,7 @@ void ljgpu_sim::sort_by_cell() {
         cell_bounds_kernel<<<nb_atoms(), kBlock, 0, st>>>(n, keys, cstart, cend);
         check_launch("cell_bounds");
     }
-    permute_kernel<<<nb_atoms(), kBlock, 0, st>>>(n, vals, pos_tmp, pos, img_xy(), img_z(),
+    permute_kernel<<<nb_atoms(), kBlock, 0, st>>>(n, vals, pos_tmp, pos,
                                                   v[0], v[1], v[2], f[0], f[1], f[2], orig,
                                                   v_alt[0], v_alt[1], v_alt[2], f_alt[0], f_alt[1], f_alt[2], orig_alt);
     check_launch("permute");
@@ -683,28 +674,21 @@ void ljgpu_sim::halo_exchange() {
     cudaEvent_t ev = stage_begin();
     if (slab.p2p) {
         // my first layer -> lower neighbour's UPPER halo slots; my last layer -> upper neighbour's LOWER halo slots
-        // (every device sizes its image with the same pos_cap: same N, world and cell grid)
-        const size_t down_at = (size_t)slab.nb_n[0] + slab.nb_hlo[0], up_at = slab.nb_n[1];
+        double4* down_dst = slab.peer_pos[0] + slab.nb_n[0] + slab.nb_hlo[0];
+        double4* up_dst = slab.peer_pos[1] + slab.nb_n[1];
         const unsigned total = slab.c_lo + slab.c_hi;
         const unsigned blocks = std::max(1u, std::min(cdiv(total, 256), 296u));
-        halo_push_kernel<<<blocks, 256, 0, st>>>(ctrl, img_xy(), img_z(), n, slab.c_lo, slab.c_hi,
-                                                 img_xy_of(slab.peer_img[0]) + down_at, slab.peer_img[0] + 2 * pos_cap + down_at,
-                                                 img_xy_of(slab.peer_img[1]) + up_at, slab.peer_img[1] + 2 * pos_cap + up_at,
+        halo_push_kernel<<<blocks, 256, 0, st>>>(ctrl, pos, n, slab.c_lo, slab.c_hi, down_dst, up_dst,
                                                  slab.peer_mail[slab.down], slab.peer_mail[slab.up], slab.push_ticket);
         check_launch("halo_push");
         stage_end(ST_HALO, ev);
         return;
     }
     NCK(A.GroupStart());
-    double* xy = img; double* z = img_z();       // (x, y) records count two doubles per atom
-    NCK(A.Send(xy, (size_t)std::max(slab.c_lo, 1u) * 2, ljnccl::kFloat64, slab.down, slab.comm, st));
-    NCK(A.Send(z, (size_t)std::max(slab.c_lo, 1u), ljnccl::kFloat64, slab.down, slab.comm, st));
-    NCK(A.Send(xy + 2 * (size_t)(n - slab.c_hi), (size_t)std::max(slab.c_hi, 1u) * 2, ljnccl::kFloat64, slab.up, slab.comm, st));
-    NCK(A.Send(z + (n - slab.c_hi), (size_t)std::max(slab.c_hi, 1u), ljnccl::kFloat64, slab.up, slab.comm, st));
-    NCK(A.Recv(xy + 2 * ((size_t)n + slab.h_lo), (size_t)std::max(slab.h_hi, 1u) * 2, ljnccl::kFloat64, slab.up, slab.comm, st));
-    NCK(A.Recv(z + n + slab.h_lo, (size_t)std::max(slab.h_hi, 1u), ljnccl::kFloat64, slab.up, slab.comm, st));
-    NCK(A.Recv(xy + 2 * (size_t)n, (size_t)std::max(slab.h_lo, 1u) * 2, ljnccl::kFloat64, slab.down, slab.comm, st));
-    NCK(A.Recv(z + n, (size_t)std::max(slab.h_lo, 1u), ljnccl::kFloat64, slab.down, slab.comm, st));
+    NCK(A.Send(pos, (size_t)std::max(slab.c_lo, 1u) * 4, ljnccl::kFloat64, slab.down, slab.comm, st));
+    NCK(A.Send(pos + (n - slab.c_hi), (size_t)std::max(slab.c_hi, 1u) * 4, ljnccl::kFloat64, slab.up, slab.comm, st));
+    NCK(A.Recv(pos + n + slab.h_lo, (size_t)std::max(slab.h_hi, 1u) * 4, ljnccl::kFloat64, slab.up, slab.comm, st));
+    NCK(A.Recv(pos + n, (size_t)std::max(slab.h_lo, 1u) * 4, ljnccl::kFloat64, slab.down, slab.comm, st));
     NCK(A.GroupEnd());
     stage_end(ST_HALO, ev);
 }
@@ -747,7 +731,7 @@ void ljgpu_sim::setup_p2p() {
     struct Handles { cudaIpcMemHandle_t pos, mail, pub[2]; };
     static_assert(sizeof(Handles) == 256, "four 64-byte IPC handles");
     Handles mine;
-    CK(cudaIpcGetMemHandle(&mine.pos, img));
+    CK(cudaIpcGetMemHandle(&mine.pos, pos));
     CK(cudaIpcGetMemHandle(&mine.mail, slab.mail));
     for (int b = 0; b < 2; ++b) CK(cudaIpcGetMemHandle(&mine.pub[b], slab.pub_slice[b]));
     Handles* d_all = nullptr;
@@ -769,8 +753,8 @@ void ljgpu_sim::setup_p2p() {
         for (int b = 0; b < 2; ++b)
             slab.peer_pub[b][r] = r == slab.rank ? slab.pub_slice[b] : static_cast<double*>(open(all[r].pub[b]));
     }
-    slab.peer_img[0] = static_cast<double*>(open(all[slab.down].pos));
-    slab.peer_img[1] = slab.up == slab.down ? slab.peer_img[0] : static_cast<double*>(open(all[slab.up].pos));
+    slab.peer_pos[0] = static_cast<double4*>(open(all[slab.down].pos));
+    slab.peer_pos[1] = slab.up == slab.down ? slab.peer_pos[0] : static_cast<double4*>(open(all[slab.up].pos));
     CK(cudaMalloc(&slab.d_peer_mail, sizeof(Mailbox*) * kMaxPeers));
     CK(cudaMemcpy(slab.d_peer_mail, slab.peer_mail, sizeof(Mailbox*) * kMaxPeers, cudaMemcpyHostToDevice));
     slab.p2p = true;
@@ -819,7 +803,7 @@ void ljgpu_sim::rebuild() {
 
     CK(cudaMemsetAsync(&ctrl->max_tile, 0, sizeof(unsigned), st));
     CK(cudaMemsetAsync(&ctrl->max_home, 0, sizeof(unsigned), st));
-    tile_table_kernel<<<cdiv(nblocks_tile, 4), 128, 0, st>>>(tile_grid(), cstart, ccount, tsrc, toff, trun, ctrl);
+    tile_table_kernel<<<cdiv(nblocks_tile, 4), 128, 0, st>>>(tile_grid(), cstart, ccount, tsrc, toff, ctrl);
     check_launch("tile_table");
     fetch_ctrl();
     // launch shapes only grow (a few spare shared-memory records cost nothing; a changed shape costs a graph capture)
@@ -856,7 +840,7 @@ static size_t tile_smem(const ljgpu_sim* s) { return (size_t)s->tcap * kTileRecB
 
 template <int MODE, bool UNIT_SIGMA>
 static void launch_tile2(ljgpu_sim* s, int guarded) {
-    TileArgs a{s->img_xy(), s->img_z(), s->nl, s->nl_count, s->prune_skin > 0.0 ? s->nl_in : nullptr, s->nl_in_count,
+    TileArgs a{s->pos, s->nl, s->nl_count, s->prune_skin > 0.0 ? s->nl_in : nullptr, s->nl_in_count,
                s->f[0], s->f[1], s->f[2], s->partial_epot, s->ctrl, s->capq, s->tcap, s->tile_slots, s->tile_ipb,
                s->slab.p2p ? s->slab.mail : nullptr};
     const unsigned grid = std::max(1u, std::min(s->nblocks_tile, s->tile_grid_ctas[MODE][UNIT_SIGMA ? 1 : 0]));
@@ -1000,10 +984,10 @@ void ljgpu_sim::enqueue_step(bool prune_now, double dt) {
     cudaEvent_t ev = stage_begin();
     if (list_mode())
         kick_drift_kernel<true><<<nb_atoms(), kBlock, 0, st>>>(c, dt, a, ctrl, pos, dij[0], dij[1], dij[2],
-                                                               v[0], v[1], v[2], f[0], f[1], f[2], img_xy(), img_z());
+                                                               v[0], v[1], v[2], f[0], f[1], f[2]);
     else
         kick_drift_kernel<false><<<nb_atoms(), kBlock, 0, st>>>(c, dt, a, ctrl, pos, nullptr, nullptr, nullptr,
-                                                                v[0], v[1], v[2], f[0], f[1], f[2], nullptr, nullptr);
+                                                                v[0], v[1], v[2], f[0], f[1], f[2]);
     check_launch("kick_drift");
     stage_end(ST_KICK_DRIFT, ev);
     if (slab.on) halo_exchange();
@@ -1039,8 +1023,8 @@ ljgpu_sim::GraphKey ljgpu_sim::graph_key(bool prune_now, double dt) const {
     std::memset(&k, 0, sizeof k);                      // padding included: keys are compared bytewise
     const void* ptrs[20] = {pos, v[0], v[1], v[2], f[0], f[1], f[2], dij[0], dij[1], dij[2],
                             nl, nl_in, nl_count, nl_in_count, tsrc, toff,
-                            slab.p2p ? (const void*)(slab.peer_img[0] + slab.nb_n[0] + slab.nb_hlo[0]) : nullptr,     // where my halo pushes land
-                            slab.p2p ? (const void*)(slab.peer_img[1] + slab.nb_n[1]) : nullptr, img, nullptr};
+                            slab.p2p ? (const void*)(slab.peer_pos[0] + slab.nb_n[0] + slab.nb_hlo[0]) : nullptr,     // where my halo pushes land
+                            slab.p2p ? (const void*)(slab.peer_pos[1] + slab.nb_n[1]) : nullptr, nullptr, nullptr};
     std::memcpy(k.ptr, ptrs, sizeof ptrs);
     k.shape[0] = n; k.shape[1] = tile_grid_ctas[TILE_FORCE_LIST][1]; k.shape[2] = tcap; k.shape[3] = capq; k.shape[4] = nblocks_tile; k.shape[5] = nb_force; k.shape[6] = tile_slots; k.shape[7] = tile_ipb;
     k.shape[8] = slab.c_lo; k.shape[9] = slab.c_hi;

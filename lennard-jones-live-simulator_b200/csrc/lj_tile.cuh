@@ -44,8 +44,7 @@ constexpr int kBrickWarps = LJ_BRICK_WARPS;                           // computi
 #ifndef LJ_BRICK_STAGERS
 #define LJ_BRICK_STAGERS 4
 #endif
-constexpr int kBrickStagers = LJ_BRICK_STAGERS;                       // staging warps per CTA: each stages every kBrickStagers-th brick
-constexpr double kFarAway = 1.0e150;                                  // coordinate of a padding slot: never within any cutoff
+constexpr int kBrickStagers = LJ_BRICK_STAGERS;                       // staging warps per CTA (they share the rows of a tile)
 constexpr int kBrickThreads = 32 * (kBrickWarps + kBrickStagers);
 constexpr int kBrickSlotsMax = 4;                                     // tiles in flight per CTA (fewer when tiles are large)
 constexpr int kBrickItemsMax = 32;                                    // work items (32 home atoms each) per brick
@@ -61,6 +60,32 @@ __device__ __forceinline__ void tile_ld(const double* sxy, const double* sz, uns
     z = sz[j];
 }
 
+// A list under construction: eight 16-bit entries are collected in registers (the quad is shifted down by one entry, the new
+// one enters at the top: after eight pushes the first entry sits in half-word 0, so the walk sees the entries in the order
+// they were found and a filtered list sums in the same order as its parent - bit-identical forces) and leave as ONE 128-bit
+// store.  Entry-by-entry 16-bit stores cost a 32-byte L2 sector write each: 84 M of them per list build at N = 2^20.
+struct QuadPacker {
+    uint4 q;
+    unsigned cnt;
+    __device__ __forceinline__ void push(unsigned j, uint4* __restrict__ row, unsigned capq) {
+        q.x = __funnelshift_r(q.x, q.y, 16); q.y = __funnelshift_r(q.y, q.z, 16);
+        q.z = __funnelshift_r(q.z, q.w, 16); q.w = (q.w >> 16) | (j << 16);
+        ++cnt;
+        if ((cnt & 7u) == 0u && cnt <= 8u * capq) row[(size_t)((cnt >> 3) - 1u) * 32] = q;
+    }
+    // the unused tail of the last quad points at the atom itself
+    __device__ __forceinline__ void finish(unsigned self, uint4* __restrict__ row, unsigned capq) {
+        unsigned k = cnt;
+        if (k > 8u * capq || (k & 7u) == 0u) return;
+        const unsigned at = k >> 3;
+        for (; k & 7u; ++k) {
+            q.x = __funnelshift_r(q.x, q.y, 16); q.y = __funnelshift_r(q.y, q.z, 16);
+            q.z = __funnelshift_r(q.z, q.w, 16); q.w = (q.w >> 16) | (self << 16);
+        }
+        row[(size_t)at * 32] = q;
+    }
+};
+
 struct TileGrid {
     unsigned nc;                 // cells per axis in x and y (periodic)
     unsigned ncz;                // cell layers of the local table (nc, or owned layers + 2 halo layers on a slab)
@@ -70,8 +95,7 @@ struct TileGrid {
     unsigned nbx, nby, nbz;      // bricks per axis
     unsigned nblocks;            // bricks
     const uint32_t* __restrict__ tsrc;   // [nblocks][kTileCellsMax]     first global slot of each tile cell
-    const uint32_t* __restrict__ toff;   // [nblocks][kTileCellsMax + 1] tile-local offset | atoms << 16 of each tile cell; [ntc] = footprint
-    const uint32_t* __restrict__ trun;   // [nblocks][kTileCellsMax]     atoms of the run of consecutive cells that starts here (else 0)
+    const uint32_t* __restrict__ toff;   // [nblocks][kTileCellsMax + 1] tile-local offset of each tile cell
 };
 
 struct TileGeom { unsigned x0, y0, z0, bw, bh, bd, W, H; };
@@ -93,25 +117,15 @@ __device__ __forceinline__ TileGeom tile_geometry(unsigned b, const TileGrid& g)
 }
 
 // Re-binning: per brick, where each tile cell's atoms live (global slot) and where they go in the tile.
-//
-// Tile-local offsets are laid out for the bulk-copy staging: consecutive tile cells whose atoms are consecutive in the
-// cell-sorted global arrays form a RUN (an x-row of the tile, unless it straddles the periodic seam in x), a run's atoms
-// are consecutive in the tile too, and every run starts at a tile index of the same parity as its first global slot
-// (one padding slot before and / or after a run where needed).  So the 8-byte z column of a cell can be copied as the
-// enclosing 16-byte-aligned range: the extra element on either side is either the same atom that the neighbouring
-// cell's copy delivers, or lands in a padding slot.  toff[t] = start | count << 16; toff[ntc] = the tile's footprint;
-// trun[t] = atoms of the run that starts at cell t (0: the cell continues a run, or the run is empty) - the staging
-// warp issues one pair of bulk copies per run, ~32 per tile.
 __global__ void __launch_bounds__(128)
 tile_table_kernel(TileGrid g, const uint32_t* __restrict__ cstart, const uint32_t* __restrict__ ccount,
-                  uint32_t* __restrict__ tsrc, uint32_t* __restrict__ toff, uint32_t* __restrict__ trun, StepCtrl* __restrict__ ctrl) {
+                  uint32_t* __restrict__ tsrc, uint32_t* __restrict__ toff, StepCtrl* __restrict__ ctrl) {
     const int lane = threadIdx.x & 31;
     const unsigned b = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (b >= g.nblocks) return;
     const TileGeom t = tile_geometry(b, g);
     const unsigned nc = g.nc, ntc = t.W * t.H * (t.bd + 2);
-    unsigned foot = 0, next_src = 0xffffffffu, home = 0;      // warp-uniform: footprint so far, global slot that would continue the run
-    unsigned run_first = 0, run_len = 0;                      // warp-uniform: the current run's first cell and its atoms so far
+    unsigned run = 0, home = 0;
     for (unsigned t0 = 0; t0 < ntc; t0 += 32) {
         const unsigned k = t0 + lane;
         unsigned cnt = 0, src = 0;
@@ -124,34 +138,22 @@ tile_table_kernel(TileGrid g, const uint32_t* __restrict__ cstart, const uint32_
             cnt = ccount[cid]; src = cstart[cid];
             is_home = tx >= 1 && tx <= t.bw && ty >= 1 && ty <= t.bh && tz >= 1 && tz <= t.bd;
         }
-        if (k < ntc) trun[(size_t)b * kTileCellsMax + k] = 0;     // (lane 0 then stores the totals at the runs' first cells)
-        __syncwarp();
-        unsigned start = 0;
-        const unsigned m = min(32u, ntc - t0);
-        for (unsigned j = 0; j < m; ++j) {                    // the cells of this chunk in order (uniform over the warp)
-            const unsigned cj = __shfl_sync(0xffffffffu, cnt, j), sj = __shfl_sync(0xffffffffu, src, j);
-            if (sj != next_src) {                                 // a new run: even boundary, then the parity of its first slot
-                if (lane == 0 && t0 + j > 0) trun[(size_t)b * kTileCellsMax + run_first] = run_len;
-                run_first = t0 + j; run_len = 0;
-                foot = ((foot + 1u) & ~1u) + (sj & 1u);
-            }
-            if ((unsigned)lane == j) start = foot;
-            foot += cj; run_len += cj; next_src = sj + cj;
-        }
+        unsigned inc = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
         if (k < ntc) {
             tsrc[(size_t)b * kTileCellsMax + k] = src;
-            toff[(size_t)b * (kTileCellsMax + 1) + k] = start | (cnt << 16);
+            toff[(size_t)b * (kTileCellsMax + 1) + k] = run + inc - cnt;
         }
+        run += __shfl_sync(0xffffffffu, inc, 31);
         unsigned hc = is_home ? cnt : 0u;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) hc += __shfl_xor_sync(0xffffffffu, hc, o);
         home += hc;
     }
     if (lane == 0) {
-        trun[(size_t)b * kTileCellsMax + run_first] = run_len;
-        foot = (foot + 1u) & ~1u;
-        toff[(size_t)b * (kTileCellsMax + 1) + ntc] = foot;
-        atomicMax(&ctrl->max_tile, foot);
+        toff[(size_t)b * (kTileCellsMax + 1) + ntc] = run;
+        atomicMax(&ctrl->max_tile, run);
         atomicMax(&ctrl->max_home, home);
     }
 }
@@ -165,8 +167,7 @@ enum { TILE_FORCE_LIST = 0, TILE_FORCE_CELL = 1, TILE_LIST_COUNT = 2, TILE_LIST_
        TILE_FORCE_PRUNE = 5 /* force pass over the outer list that also emits the pruned inner list */ };
 
 struct TileArgs {
-    const double2* __restrict__ xy;        // the tile image of the positions in global memory: (x, y) records ...
-    const double* __restrict__ z;          // ... and the z column, cell-sorted like the state (written by kick/drift, permute, halo push)
+    const double4* __restrict__ pos;
     uint32_t* __restrict__ nl32;           // list words (fill: written as uint16 halves)
     uint32_t* __restrict__ nl_count;
     uint32_t* __restrict__ in32;           // pruned inner list, same layout (null: none)
@@ -199,60 +200,43 @@ tile_kernel(LJConst c, TileGrid g, TileArgs a, int guarded) {
     __shared__ uint32_t s_off[kBrickSlotsMax][kTileCellsMax + 1];
     __shared__ uint32_t s_src[kBrickSlotsMax][kTileCellsMax];
     __shared__ BrickHeader s_hdr[kBrickSlotsMax];
-    __shared__ unsigned s_filled;                       // bricks staged so far (written by the staging warps in brick order, release)
-    __shared__ unsigned s_ticketed;                     // bricks that have their ticket (the staging warps take tickets in brick order)
+    __shared__ unsigned s_filled;                       // bricks staged so far (written by the staging warp, release)
     __shared__ unsigned s_drained[kBrickSlotsMax];      // how many bricks have been worked off in each slot (release)
     __shared__ unsigned s_done[kBrickSlotsMax];         // work items of the slot's brick that are finished
     __shared__ unsigned s_item;                         // next work item of this CTA
-    __shared__ uint32_t s_end[kBrickSlotsMax][kTileCellsMax];       // one past the last atom of each tile cell (padding may follow)
-    __shared__ unsigned long long s_bar[kBrickSlotsMax];                // mbarriers: the bulk copies of a slot's tile
+    __shared__ unsigned s_ticket[2];                    // the brick the staging warps work on next (double-buffered by k & 1)
     __shared__ unsigned s_total;                        // bricks this CTA got before the queue ran dry (release; ~0u until then)
     if (guarded && a.ctrl->stop) return;
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int s = 0; s < kBrickSlotsMax; ++s) { s_drained[s] = 0; s_done[s] = 0; }
-        s_item = 0; s_filled = 0; s_ticketed = 0; s_total = 0xffffffffu;
-#pragma unroll
-        for (int s = 0; s < kBrickSlotsMax; ++s) mbar_init(&s_bar[s], 1u);
+        s_item = 0; s_filled = 0; s_total = 0xffffffffu;
     }
     __syncthreads();
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const size_t slot_doubles = (size_t)a.tcap * 3;
     // Bricks are handed out by a device-wide counter (ctrl->brick_next): bricks differ in size (partial bricks at the box
     // edge, density fluctuations), and with a fixed brick -> CTA assignment the slowest SM ran 13 % longer than the
-    // average one (ncu: sm__cycles_active min / avg / max 368 k / 433 k / 492 k).  Results do not depend on who runs a
-    // brick: forces are per atom, energy partials are indexed by (brick, item).
+    // average one (ncu: sm__cycles_active min / avg / max 368 k / 433 k / 492 k; with the queue 372 k / 399 k / 414 k).
+    // Results do not depend on who runs a brick: forces are per atom, energy partials are indexed by (brick, item).
 
     if (warp >= (unsigned)kBrickWarps) {
-        // ---- staging warps: fill the ring ahead of the computing warps.  Per brick: one ticket, the brick's table, then
-        // two bulk copies per run of consecutive tile cells ((x, y) records and the z column, straight out of the
-        // cell-sorted image arrays), issued by the lanes in parallel and counted on the slot's mbarrier - no per-atom
-        // instructions at all.  Staging a tile is a chain of latencies (ticket, table, copy engine: ~7 us, measured), so
-        // kBrickStagers warps work on consecutive bricks at the same time; tickets are taken and tiles are published
-        // in brick order (s_ticketed / s_filled), so the computing warps still see the CTA's bricks as 0, 1, 2, ...
-        unsigned long long* bar = &s_bar[0];
+        // ---- staging warps: fill the ring ahead of the computing warps (the first one also reads the brick's tables) ----
         const unsigned stager = warp - (unsigned)kBrickWarps;
-        for (unsigned k = stager;; k += (unsigned)kBrickStagers) {
+        for (unsigned k = 0;; ++k) {
             const unsigned slot = k % a.slots, use = k / a.slots;
-            bool over = false;
-            // every work item of the brick that was in the slot is finished, and it is my turn to take a ticket
-            while (ld_acquire_smem(&s_drained[slot]) < use || ld_acquire_smem(&s_ticketed) != k) {
-                if (ld_acquire_smem(&s_total) != 0xffffffffu) { over = true; break; }       // an earlier brick found the queue dry
-                spin_pause();
-            }
-            if (over) break;
-            unsigned b = 0;
-            if (lane == 0) b = atomicAdd(&a.ctrl->brick_next, 1u);
-            b = __shfl_sync(0xffffffffu, b, 0);
-            if (b >= g.nblocks) {           // the queue is dry: tell everybody how many bricks there were
-                if (lane == 0) {
+            while (ld_acquire_smem(&s_drained[slot]) < use) spin_pause();  // every work item of the brick that was there is finished
+            if (lane == 0 && stager == 0) s_ticket[k & 1u] = atomicAdd(&a.ctrl->brick_next, 1u);
+            if (kBrickStagers > 1) named_barrier_sync(3, 32u * kBrickStagers); else __syncwarp();
+            const unsigned b = s_ticket[k & 1u];
+            if (b >= g.nblocks) {           // the queue is dry: tell the computing warps how many bricks there were
+                if (lane == 0 && stager == 0) {
                     st_release_smem(&s_total, k);
                     // the last CTA to get here re-arms the queue for the next launch (nobody takes a ticket after its dry one)
                     if (atomicAdd(&a.ctrl->brick_dry, 1u) + 1u == gridDim.x) { a.ctrl->brick_dry = 0u; a.ctrl->brick_next = 0u; }
                 }
                 break;
             }
-            if (lane == 0) st_release_smem(&s_ticketed, k + 1u);
             const TileGeom tg = tile_geometry(b, g);
             const bool lo_halo = a.mail && tg.z0 == g.hz0, hi_halo = a.mail && tg.z0 + tg.bd == g.hz0 + g.nhz;
             if (lo_halo || hi_halo) {    // slab over peer memory: only bricks whose tile reaches a halo layer wait for that neighbour's push
@@ -264,81 +248,61 @@ tile_kernel(LJConst c, TileGrid g, TileArgs a, int guarded) {
                 __syncwarp();
             }
             const unsigned W = tg.W, H = tg.H, ntc = W * H * (tg.bd + 2);
-            // the brick's table: per tile cell its first global slot, its first tile index and its atom count
-            constexpr int kPerLane = (kTileCellsMax + 31) / 32;
-            unsigned c_src[kPerLane], c_off[kPerLane], c_cnt[kPerLane], c_run[kPerLane];
-            unsigned bytes = 0;
-#pragma unroll
-            for (int q = 0; q < kPerLane; ++q) {
-                const unsigned t = lane + 32u * q;
-                c_cnt[q] = 0; c_off[q] = 0; c_src[q] = 0; c_run[q] = 0;
-                if (t < ntc) {
-                    const unsigned w = g.toff[(size_t)b * (kTileCellsMax + 1) + t];
-                    c_src[q] = g.tsrc[(size_t)b * kTileCellsMax + t];
-                    c_run[q] = g.trun[(size_t)b * kTileCellsMax + t];
-                    c_off[q] = w & 0xffffu; c_cnt[q] = w >> 16;
-                    s_off[slot][t] = c_off[q]; s_end[slot][t] = c_off[q] + c_cnt[q]; s_src[slot][t] = c_src[q];
-                    if (c_run[q]) bytes += c_run[q] * 16u + (((c_src[q] + c_run[q] + 1u) & ~1u) - (c_src[q] & ~1u)) * 8u;
-                } else if (t == ntc) {
-                    s_off[slot][t] = g.toff[(size_t)b * (kTileCellsMax + 1) + t];      // the footprint
-                }
+            for (unsigned t = lane + 32u * stager; t <= ntc; t += 32u * kBrickStagers) {
+                s_off[slot][t] = g.toff[(size_t)b * (kTileCellsMax + 1) + t];
+                if (t < ntc) s_src[slot][t] = g.tsrc[(size_t)b * kTileCellsMax + t];
             }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) bytes += __shfl_xor_sync(0xffffffffu, bytes, o);
-            __syncwarp();
-            if (lane == 0) {
-                mbar_arrive_expect_tx(bar + slot, bytes);
+            if (kBrickStagers > 1) named_barrier_sync(1, 32u * kBrickStagers); else __syncwarp();
+            if (lane == 0 && stager == 0) {
+                s_hdr[slot].brick = b;
                 BrickHeader& h = s_hdr[slot];
-                h.brick = b;
                 h.W = W; h.H = H; h.bw = tg.bw; h.bh = tg.bh; h.bd = tg.bd;
                 h.lo_halo = lo_halo ? 1u : 0u; h.hi_halo = hi_halo ? 1u : 0u;
                 unsigned run = 0, q = 0;
                 for (unsigned hz = 1; hz <= tg.bd; ++hz)
                     for (unsigned hy = 1; hy <= tg.bh; ++hy) {
-                        const unsigned r = (hz * H + hy) * W;           // the home cells of a row are one run: last end - first start
+                        const unsigned r = (hz * H + hy) * W;
                         h.hstart[q++] = run;
-                        run += s_end[slot][r + tg.bw] - s_off[slot][r + 1];
+                        run += s_off[slot][r + 1 + tg.bw] - s_off[slot][r + 1];
                     }
                 for (; q <= (unsigned)kHomeRowsMax; ++q) h.hstart[q] = run;
                 h.hn = run;
             }
-            __syncwarp();
-            // my generic-proxy writes to this slot's padding (previous use) come before the copy engine's writes
-            fence_proxy_async_smem();
-            const unsigned sxy_base = smem_addr(sm + slot * slot_doubles);
-            const unsigned sz_base = sxy_base + a.tcap * 16u;
-#pragma unroll
-            for (int q = 0; q < kPerLane; ++q) {
-                if (c_run[q]) {       // one pair of copies per run of consecutive cells
-                    const unsigned src = c_src[q], off = c_off[q], cnt = c_run[q];
-                    bulk_g2s(sxy_base + off * 16u, a.xy + src, cnt * 16u, bar + slot);
-                    // z: the enclosing 16-byte-aligned range (tile index and global slot have the same parity)
-                    const unsigned lo = src & 1u, n2 = ((src + cnt + 1u) & ~1u) - (src - lo);
-                    bulk_g2s(sz_base + (off - lo) * 8u, a.z + (src - lo), n2 * 8u, bar + slot);
-                }
-            }
-            while (!mbar_try_wait(bar + slot, use & 1u)) { }
-            // padding slots (between runs, before the first and after the last one) must never look like a neighbour:
-            // the cell-stencil and list-build modes scan index ranges that include them
+            // one tile x-row (W consecutive tile cells, ~100 atoms at liquid density) at a time, lanes stride over
+            // the row's atoms.  An atom's global slot is its tile index plus the (source - offset) difference of its
+            // cell, picked by comparing against the row's W-1 inner cell offsets held in registers.
+            // Asynchronous global->shared copies (LDGSTS): (x, y) are the first 16 bytes of the 32-byte global
+            // record, z the next 8.
             {
-                double2* sxy = reinterpret_cast<double2*>(sm + slot * slot_doubles);
-                double* sz = sm + slot * slot_doubles + (size_t)a.tcap * 2;
+                constexpr int kW = kTileBX + 2;
+                const unsigned nrows = H * (tg.bd + 2);
+                const unsigned sxy_base = smem_addr(sm + slot * slot_doubles);
+                const unsigned sz_base = sxy_base + a.tcap * 16u;
+                for (unsigned r = stager; r < nrows; r += (unsigned)kBrickStagers) {
+                    const unsigned t0 = r * W;
+                    unsigned offk[kW], delk[kW];
 #pragma unroll
-                for (int q = 0; q < kPerLane; ++q) {
-                    const unsigned t = lane + 32u * q;
-                    if (t < ntc) {
-                        const unsigned e1 = s_off[slot][t + 1];
-                        for (unsigned pp = c_off[q] + c_cnt[q]; pp < e1; ++pp) { sxy[pp] = make_double2(kFarAway, kFarAway); sz[pp] = kFarAway; }
-                        if (t == 0) for (unsigned pp = 0; pp < c_off[q]; ++pp) { sxy[pp] = make_double2(kFarAway, kFarAway); sz[pp] = kFarAway; }
+                    for (int kk = 0; kk < kW; ++kk) {
+                        const bool on = (unsigned)kk < W;
+                        const unsigned o = on ? s_off[slot][t0 + kk] : 0xffffffffu;
+                        offk[kk] = o;
+                        delk[kk] = on ? s_src[slot][t0 + kk] - o : 0u;      // modulo 2^32: li + delk = source slot
+                    }
+                    const unsigned o1 = s_off[slot][t0 + W];
+                    for (unsigned li = offk[0] + lane; li < o1; li += 32) {
+                        unsigned d = delk[0];
+#pragma unroll
+                        for (int kk = 1; kk < kW; ++kk) d = (li >= offk[kk]) ? delk[kk] : d;
+                        const double* gp = reinterpret_cast<const double*>(a.pos + (li + d));
+                        cp_async16(sxy_base + li * 16u, gp);
+                        cp_async8(sz_base + li * 8u, gp + 2);
                     }
                 }
+                cp_async_wait_all();
             }
-            __syncwarp();
-            // the copies have landed (mbarrier phase observed), table and padding are written: publish the tile, in order
-            if (lane == 0) {
-                while (ld_acquire_smem(&s_filled) != k) spin_pause();
-                st_release_smem(&s_filled, k + 1u);
-            }
+            // every staging lane's copies have landed, its table words are written: publish the tile
+            if (kBrickStagers > 1) named_barrier_sync(2, 32u * kBrickStagers); else __syncwarp();
+            if (lane == 0 && stager == 0) st_release_smem(&s_filled, k + 1u);
         }
         return;
     }
@@ -404,10 +368,10 @@ tile_kernel(LJConst c, TileGrid g, TileArgs a, int guarded) {
         double ax = 0.0, ay = 0.0, az = 0.0, e = 0.0;
         unsigned nacc = 0, cnt = 0;
         // entry k of slot i is half-word k&7 of quad k>>3; quads of one slot are 32 lanes x 8 half-words apart
-        unsigned short* __restrict__ in16 = (MODE == TILE_FORCE_PRUNE)
-            ? reinterpret_cast<unsigned short*>(a.in32) + (((size_t)(i >> 5) * a.capq) * 32 + (i & 31u)) * 8 : nullptr;
-        unsigned short* __restrict__ fill16 = (MODE == TILE_LIST_FILL)
-            ? reinterpret_cast<unsigned short*>(a.nl32) + (((size_t)(i >> 5) * a.capq) * 32 + (i & 31u)) * 8 : nullptr;
+        // the list this pass writes (pruning: the inner list; build: the outer list): quad q of slot i, see the layout above
+        uint4* __restrict__ out_row = (MODE == TILE_FORCE_PRUNE || MODE == TILE_LIST_FILL)
+            ? reinterpret_cast<uint4*>(MODE == TILE_FORCE_PRUNE ? a.in32 : a.nl32) + ((size_t)(i >> 5) * a.capq) * 32 + (i & 31u) : nullptr;
+        QuadPacker pk; pk.q = make_uint4(0u, 0u, 0u, 0u); pk.cnt = 0;
 
 #define LJ_TILE_PAIR(J)                                                                     \
         {                                                                                   \
@@ -505,10 +469,7 @@ tile_kernel(LJConst c, TileGrid g, TileArgs a, int guarded) {
                         nacc += in ? 1u : 0u;
                         if (MODE == TILE_FORCE_PRUNE) {
                             // by-product: the entries still within rcut + s_in form the inner list of the coming steps
-                            if (d2[u] <= c.prune_cut2 && jj[u] != li) {
-                                in16[(size_t)(cnt >> 3) * 256 + (cnt & 7u)] = (unsigned short)jj[u];   // quad stride: 32 lanes x 8 entries
-                                ++cnt;
-                            }
+                            if (d2[u] <= c.prune_cut2 && jj[u] != li) pk.push(jj[u], out_row, a.capq);
                         }
                     }
                 }
@@ -555,9 +516,8 @@ tile_kernel(LJConst c, TileGrid g, TileArgs a, int guarded) {
                         for (int u = 0; u < 4; ++u) {
                             const unsigned j = jb + u;
                             if (j < j1 && d2[u] <= c.list_cut2 && j != li) {
-                                if (MODE == TILE_LIST_FILL && cnt < 8 * a.capq)     // plain 16-bit stores: measured cheaper than packing quads in registers
-                                    fill16[(size_t)(cnt >> 3) * 256 + (cnt & 7u)] = (unsigned short)j;
-                                ++cnt;
+                                if (MODE == TILE_LIST_FILL) pk.push(j, out_row, a.capq);   // (entries beyond the capacity are counted, not stored)
+                                else ++cnt;
                             }
                         }
                     }
@@ -567,16 +527,14 @@ tile_kernel(LJConst c, TileGrid g, TileArgs a, int guarded) {
 #undef LJ_TILE_PAIR
 
         if (MODE == TILE_FORCE_PRUNE) {
-            for (unsigned kk = cnt; kk & 7u; ++kk)            // the unused tail of the last quad points at the atom itself
-                in16[(size_t)(kk >> 3) * 256 + (kk & 7u)] = (unsigned short)li;
-            a.in_count[i] = cnt;
+            pk.finish(li, out_row, a.capq);
+            a.in_count[i] = pk.cnt;
         }
         if (MODE == TILE_FORCE_LIST || MODE == TILE_FORCE_CELL || MODE == TILE_FORCE_PRUNE) {
             a.fx[i] = ax * c.prefctr; a.fy[i] = ay * c.prefctr; a.fz[i] = az * c.prefctr;
             etot += fma(-(double)nacc, c.ecut, e);
         } else {
-            if (MODE == TILE_LIST_FILL)                      // the unused tail of the last quad points at the atom itself
-                for (unsigned kk = min(cnt, 8 * a.capq); kk & 7u; ++kk) fill16[(size_t)(kk >> 3) * 256 + (kk & 7u)] = (unsigned short)li;
+            if (MODE == TILE_LIST_FILL) { pk.finish(li, out_row, a.capq); cnt = pk.cnt; }
             a.nl_count[i] = MODE == TILE_LIST_FILL ? min(cnt, 8 * a.capq) : cnt;
             maxcnt = max(maxcnt, cnt);
         }

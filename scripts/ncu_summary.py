@@ -15,7 +15,10 @@ want = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio', 'smsp__average_warps_issue_stalled_wait_per_issue_active.ratio',
         'smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio', 'smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio',
         'smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio', 'smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio',
-        'smsp__thread_inst_executed_per_inst_executed.ratio', 'sm__cycles_elapsed.max']
+        'smsp__thread_inst_executed_per_inst_executed.ratio', 'sm__cycles_elapsed.max',
+        'sm__cycles_active.min', 'sm__cycles_active.avg', 'sm__cycles_active.max',
+        'l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed', 'l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld.sum',
+        'l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_ld.sum', 'smsp__warps_eligible.avg.per_cycle_active', 'sm__inst_executed_pipe_tma.avg.pct_of_peak_sustained_active']
 seen = {}
 for i, r in enumerate(data):
     nm = r[ki].split('(')[0]

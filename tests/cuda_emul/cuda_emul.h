@@ -273,6 +273,7 @@ inline int __any_sync(unsigned, int pred) {
 
 inline int __ffs(unsigned v) { return v ? __builtin_ctz(v) + 1 : 0; }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned shift) { shift &= 31u; return shift ? (lo >> shift) | (hi << (32u - shift)) : lo; }
 template <class T> inline unsigned __match_any_sync(unsigned, T v) {
     unsigned m = 0;
     for (int l = 0; l < 32; ++l) if (ljemul::warp_exchange(v, l) == v) m |= 1u << l;

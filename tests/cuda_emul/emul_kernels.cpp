@@ -18,7 +18,6 @@ struct Problem {
     unsigned n, nc;
     LJConst c;
     std::vector<double4> pos;           // sorted by cell
-    std::vector<double2> img_xy; std::vector<double> img_z;      // the same positions as the brick kernel stages them
     std::vector<uint32_t> orig, cstart, ccount;
 };
 
@@ -51,12 +50,10 @@ Problem bin(unsigned n, double L, double rcut, double shell, double sigma, doubl
     std::iota(p.orig.begin(), p.orig.end(), 0u);
     std::stable_sort(p.orig.begin(), p.orig.end(), [&](uint32_t a, uint32_t b) { return key[a] < key[b]; });
     p.pos.resize(n);
-    p.img_xy.resize(n); p.img_z.assign((size_t)n + 2, 0.0);
     p.cstart.assign(ncell, 0); p.ccount.assign(ncell, 0);
     for (unsigned s = 0; s < n; ++s) {
         const uint32_t i = p.orig[s];
         p.pos[s] = double4{x[i], y[i], z[i], 0.0};
-        p.img_xy[s] = double2{x[i], y[i]}; p.img_z[s] = z[i];
         if (p.ccount[key[i]]++ == 0) p.cstart[key[i]] = s;
     }
     return p;
@@ -79,14 +76,14 @@ extern "C" int ljemul_forces(unsigned ctas, unsigned n, double L, double rcut, d
     if (bx < 1 || by < 1 || bz < 1 || bx > (unsigned)kTileBX || by > 2 || bz > 2) return -1;
     if (bx + 2 > nc || by + 2 > nc || bz + 2 > nc) return -2;              // a tile must not contain a cell twice
     const unsigned nbx = cdivu(nc, bx), nby = cdivu(nc, by), nbz = cdivu(nc, bz), nblocks = nbx * nby * nbz;
-    std::vector<uint32_t> tsrc((size_t)nblocks * kTileCellsMax), toff((size_t)nblocks * (kTileCellsMax + 1)), trun((size_t)nblocks * kTileCellsMax);
-    TileGrid g{nc, nc, 1u, 0u, nc, bx, by, bz, nbx, nby, nbz, nblocks, tsrc.data(), toff.data(), trun.data()};
+    std::vector<uint32_t> tsrc((size_t)nblocks * kTileCellsMax), toff((size_t)nblocks * (kTileCellsMax + 1));
+    TileGrid g{nc, nc, 1u, 0u, nc, bx, by, bz, nbx, nby, nbz, nblocks, tsrc.data(), toff.data()};
     StepCtrl ctrl;
     std::memset(&ctrl, 0, sizeof ctrl);
     std::vector<double> f[3] = {std::vector<double>(n), std::vector<double>(n), std::vector<double>(n)};
     std::vector<double> partial;
 
-    ljemul::launch(cdivu(nblocks, 4), 128, 0, [&] { tile_table_kernel(g, p.cstart.data(), p.ccount.data(), tsrc.data(), toff.data(), trun.data(), &ctrl); });
+    ljemul::launch(cdivu(nblocks, 4), 128, 0, [&] { tile_table_kernel(g, p.cstart.data(), p.ccount.data(), tsrc.data(), toff.data(), &ctrl); });
     if (ctrl.max_tile > 65535) return -3;
     const unsigned tcap = ((ctrl.max_tile + 63) / 64) * 64;
     const unsigned slots = 3, ipb = (ctrl.max_home + 31) / 32;
@@ -98,7 +95,7 @@ extern "C" int ljemul_forces(unsigned ctas, unsigned n, double L, double rcut, d
     out_info[0] = nblocks; out_info[1] = ctrl.max_tile; out_info[2] = ctrl.max_home; out_info[3] = grid;
 
     auto run = [&](int mode, uint32_t* nl, uint32_t* nl_in, unsigned capq) {
-        TileArgs a{p.img_xy.data(), p.img_z.data(), nl, slot_count.data(), nl_in, slot_in_count.data(), f[0].data(), f[1].data(), f[2].data(),
+        TileArgs a{p.pos.data(), nl, slot_count.data(), nl_in, slot_in_count.data(), f[0].data(), f[1].data(), f[2].data(),
                    partial.data(), &ctrl, capq, tcap, slots, ipb, nullptr};
         ljemul::launch(grid, kBrickThreads, smem, [&] {
             switch (mode) {
