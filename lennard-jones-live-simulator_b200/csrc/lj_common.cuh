@@ -312,6 +312,8 @@ int radix_sort_pairs(uint32_t* keys, uint32_t* vals, size_t n, int key_bits, Sor
                      cudaStream_t st);
 // In-place exclusive prefix sum of n uint32; total written to *total_out (device pointer, may be null).
 int exclusive_scan_u32(uint32_t* data, size_t n, uint32_t* total_out, SortScratch& scr, cudaStream_t st);
+// The first CUDA error the two helpers above met on this thread since the last call (cudaSuccess if none), cleared.
+int sort_take_error();            // (a cudaError_t value)
 void sort_scratch_free(SortScratch& scr);
 
 } // namespace ljgpu

@@ -139,6 +139,7 @@ struct ljgpu_sim {
     size_t cap_atoms = 0, pos_cap = 0;
     Slab slab;
     bool failed = false;            // a call on this handle threw: NCCL state is undefined
+    bool energies_fresh = false;    // h_ctrl holds the energies of the last completed step (run_steps ends with a fetch): a query needs no device round trip
     // slab path: a capacity check that fails on ONE device must not make it leave a sequence of collectives the others are
     // still in.  The failing device records the reason, keeps every exchange well-formed (skips what does not fit), and all
     // devices learn about it in agree() - one small all-reduce per re-binning - and throw the same error together.
@@ -487,6 +488,7 @@ static unsigned host_layer(double z, double L, double invL, double edge, unsigne
 
 void ljgpu_sim::upload_state(const double* x, const double* y, const double* z,
                              const double* vx, const double* vy, const double* vz) {
+    energies_fresh = false;
     // everything but the slab sequence counters at the end of the block: the peers' mailboxes remember the sequence numbers
     CK(cudaMemsetAsync(ctrl, 0, offsetof(StepCtrl, halo_seq), st));
     pred_valid = false;
@@ -539,6 +541,7 @@ void ljgpu_sim::sort_by_cell() {
     check_launch("wrap_key");
     int bits = 1; while ((1ull << bits) < (unsigned long long)ncell) ++bits;
     launches += radix_sort_pairs(keys, vals, n, bits, scr, st);
+    CK((cudaError_t)sort_take_error());
     CK(cudaMemsetAsync(cstart, 0, (size_t)ncell * 4, st));
     CK(cudaMemsetAsync(cend, 0, (size_t)ncell * 4, st));
     if (n) {
@@ -623,6 +626,7 @@ void ljgpu_sim::halo_setup() {
     for (int k = 0; k < 2; ++k) {
         CK(cudaMemcpyAsync(slab.hoff[k], slab.hcount[k], (size_t)nc2 * 4, cudaMemcpyDeviceToDevice, st));
         launches += exclusive_scan_u32(slab.hoff[k], nc2, slab.xchg + 4 + k, scr, st);
+        CK((cudaError_t)sort_take_error());
     }
     // my own boundary layer sizes: slots [0, c_lo) and [n - c_hi, n)
     CK(cudaMemcpyAsync(slab.h_xchg + 4, slab.xchg + 4, 8, cudaMemcpyDeviceToHost, st));
@@ -1001,7 +1005,9 @@ void ljgpu_sim::enqueue_step(bool prune_now, double dt) {
         launch_force(true);
     }
     ev = stage_begin();
-    const unsigned nb2 = std::max(1u, std::min(cdiv(n, 2 * kKick2Block), (unsigned)num_sms * (2048u / kKick2Block)));   // at most one resident wave
+    // at most one resident wave, and every thread the same number of rounds (two atoms per round): no ragged last round
+    const unsigned pairs2 = std::max(1u, n / 2), wave2 = (unsigned)num_sms * 2048u;
+    const unsigned nb2 = cdiv(pairs2, cdiv(pairs2, wave2) * kKick2Block);
     if (!slab.on) {
         kick2_kernel<0><<<nb2, kKick2Block, 0, st>>>(c, a, ctrl, hist, v[0], v[1], v[2], f[0], f[1], f[2], partial_epot, nb_force, kick_sums, SlabRed{});
         check_launch("kick2");
@@ -1120,6 +1126,7 @@ void ljgpu_sim::launch_step(double dt) {
 // of the per-step all-reduce, so every device stops at the same step and issues the same NCCL calls.
 void ljgpu_sim::run_steps(unsigned first, unsigned nsteps, double dt) {
     unsigned step = first, remaining = nsteps;
+    energies_fresh = false;
     while (remaining) {
         if (!pred_valid || pred_dt != dt) launch_predict(dt);
         unsigned batch;
@@ -1151,6 +1158,7 @@ void ljgpu_sim::run_steps(unsigned first, unsigned nsteps, double dt) {
             CK(cudaSetDevice(device));
         }
     }
+    energies_fresh = nsteps > 0;        // (a re-binning after the last fetch does not touch the published energies)
 }
 
 // Neighbour-count parity probe (include/ljgpu.h): bins a copy of the published (wrapped) positions of the WHOLE
@@ -1185,6 +1193,7 @@ void ljgpu_sim::probe_neighbor_counts(double cut2, int inclusive, uint32_t* host
     check_launch("probe_key");
     int bits = 1; while ((1ull << bits) < (unsigned long long)ncell_g) ++bits;
     launches += radix_sort_pairs(probe_keys, probe_vals, N, bits, scr, st);
+    CK((cudaError_t)sort_take_error());
     CK(cudaMemsetAsync(probe_cstart, 0, (size_t)ncell_g * 4, st));
     CK(cudaMemsetAsync(probe_cend, 0, (size_t)ncell_g * 4, st));
     cell_bounds_kernel<<<nbN, kBlock, 0, st>>>((unsigned)N, probe_keys, probe_cstart, probe_cend);
@@ -1531,7 +1540,7 @@ int ljgpu_get_forces(ljgpu_sim* s, double* x, double* y, double* z) {
 
 int ljgpu_get_energies(ljgpu_sim* s, double* ekin, double* epot, double* etot) {
     return with_sim(s, [&] {
-        s->fetch_ctrl();
+        if (!s->energies_fresh) s->fetch_ctrl();
         if (ekin) *ekin = s->h_ctrl->ekin;
         if (epot) *epot = s->h_ctrl->epot;
         if (etot) *etot = s->h_ctrl->etot;

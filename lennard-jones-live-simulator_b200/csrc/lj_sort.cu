@@ -132,6 +132,11 @@ radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
     }
 }
 
+// First CUDA error seen by the helpers of this file on the calling thread; the caller collects it with
+// sort_take_error() and turns it into LJGPU_ECUDA (lj_sim.cu: CK).  After an error the helpers launch nothing more.
+thread_local cudaError_t t_err = cudaSuccess;
+#define SCK(x) do { const cudaError_t e_ = (x); if (e_ != cudaSuccess && t_err == cudaSuccess) t_err = e_; } while (0)
+
 size_t scan_tmp_need(size_t n) {
     size_t need = 0, m = n;
     while (m > 1) { m = (m + kScanTile - 1) / kScanTile; need += m; }
@@ -140,10 +145,11 @@ size_t scan_tmp_need(size_t n) {
 
 void ensure(uint32_t*& p, size_t& cap, size_t need) {
     if (need <= cap) return;
-    if (p) cudaFree(p);
+    if (p) SCK(cudaFree(p));
+    p = nullptr; cap = 0;
     size_t ncap = need + need / 4 + 64;
-    cudaMalloc(&p, ncap * sizeof(uint32_t));
-    cap = ncap;
+    SCK(cudaMalloc(&p, ncap * sizeof(uint32_t)));
+    if (p) cap = ncap;
 }
 
 // Recursive scan; `tmp` has room for all levels.  Returns kernels launched.
@@ -153,12 +159,15 @@ int scan_rec(uint32_t* data, size_t n, uint32_t* tmp, uint32_t* total_out, cudaS
     if (nb <= 1) {
         uint32_t* sums = total_out ? total_out : nullptr;
         scan_tile_kernel<<<1, kScanThreads, 0, st>>>(data, n, sums);
+        SCK(cudaGetLastError());
         return 1;
     }
     scan_tile_kernel<<<(unsigned)nb, kScanThreads, 0, st>>>(data, n, tmp);
+    SCK(cudaGetLastError());
     ++launches;
     launches += scan_rec(tmp, nb, tmp + nb, total_out, st);
     scan_add_kernel<<<(unsigned)nb, kScanThreads, 0, st>>>(data, n, tmp);
+    SCK(cudaGetLastError());
     ++launches;
     return launches;
 }
@@ -167,10 +176,11 @@ int scan_rec(uint32_t* data, size_t n, uint32_t* tmp, uint32_t* total_out, cudaS
 
 int exclusive_scan_u32(uint32_t* data, size_t n, uint32_t* total_out, SortScratch& scr, cudaStream_t st) {
     if (n == 0) {
-        if (total_out) cudaMemsetAsync(total_out, 0, sizeof(uint32_t), st);
+        if (total_out) SCK(cudaMemsetAsync(total_out, 0, sizeof(uint32_t), st));
         return 0;
     }
     ensure(scr.scan_tmp, scr.cap_scan, scan_tmp_need(n));
+    if (t_err != cudaSuccess) return 0;
     return scan_rec(data, n, scr.scan_tmp, total_out, st);
 }
 
@@ -178,33 +188,45 @@ int radix_sort_pairs(uint32_t* keys, uint32_t* vals, size_t n, int key_bits, Sor
                      cudaStream_t st) {
     if (n <= 1) return 0;
     if (scr.cap_items < n) {
-        if (scr.keys_alt) cudaFree(scr.keys_alt);
-        if (scr.vals_alt) cudaFree(scr.vals_alt);
-        scr.cap_items = n + n / 8 + 1024;
-        cudaMalloc(&scr.keys_alt, scr.cap_items * sizeof(uint32_t));
-        cudaMalloc(&scr.vals_alt, scr.cap_items * sizeof(uint32_t));
+        if (scr.keys_alt) SCK(cudaFree(scr.keys_alt));
+        if (scr.vals_alt) SCK(cudaFree(scr.vals_alt));
+        scr.keys_alt = scr.vals_alt = nullptr; scr.cap_items = 0;
+        const size_t want = n + n / 8 + 1024;
+        SCK(cudaMalloc(&scr.keys_alt, want * sizeof(uint32_t)));
+        SCK(cudaMalloc(&scr.vals_alt, want * sizeof(uint32_t)));
+        if (scr.keys_alt && scr.vals_alt) scr.cap_items = want;
     }
     const int nblocks = (int)((n + kSortTile - 1) / kSortTile);
     ensure(scr.hist, scr.cap_hist, (size_t)256 * nblocks);
+    if (t_err != cudaSuccess) return 0;
     int launches = 0;
     uint32_t *kin = keys, *vin = vals, *kout = scr.keys_alt, *vout = scr.vals_alt;
     const int passes = key_bits <= 0 ? 1 : (key_bits + 7) / 8;
     for (int p = 0; p < passes; ++p) {
         const int shift = 8 * p;
         radix_hist_kernel<<<nblocks, kSortThreads, 0, st>>>(kin, n, shift, nblocks, scr.hist);
+        SCK(cudaGetLastError());
         ++launches;
         launches += exclusive_scan_u32(scr.hist, (size_t)256 * nblocks, nullptr, scr, st);
         radix_scatter_kernel<<<nblocks, kSortThreads, 0, st>>>(kin, vin, kout, vout, scr.hist, n, shift, nblocks);
+        SCK(cudaGetLastError());
         ++launches;
+        if (t_err != cudaSuccess) return launches;
         uint32_t* t;
         t = kin; kin = kout; kout = t;
         t = vin; vin = vout; vout = t;
     }
     if (kin != keys) {
-        cudaMemcpyAsync(keys, kin, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st);
-        cudaMemcpyAsync(vals, vin, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st);
+        SCK(cudaMemcpyAsync(keys, kin, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+        SCK(cudaMemcpyAsync(vals, vin, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
     }
     return launches;
+}
+
+int sort_take_error() {
+    const cudaError_t e = t_err;
+    t_err = cudaSuccess;
+    return (int)e;
 }
 
 void sort_scratch_free(SortScratch& scr) {
