@@ -845,9 +845,14 @@ static size_t tile_smem(const ljgpu_sim* s) { return (size_t)s->tcap * kTileRecB
 template <int MODE, bool UNIT_SIGMA>
 static void launch_tile2(ljgpu_sim* s, int guarded) {
     TileArgs a{s->pos, s->nl, s->nl_count, s->prune_skin > 0.0 ? s->nl_in : nullptr, s->nl_in_count,
-               s->f[0], s->f[1], s->f[2], s->partial_epot, s->ctrl, s->capq, s->tcap, s->tile_slots, s->tile_ipb,
+               s->f[0], s->f[1], s->f[2], s->partial_epot, s->ctrl, s->capq, s->tcap, s->tile_slots, s->tile_ipb, 0u,
                s->slab.p2p ? s->slab.mail : nullptr};
     const unsigned grid = std::max(1u, std::min(s->nblocks_tile, s->tile_grid_ctas[MODE][UNIT_SIGMA ? 1 : 0]));
+    // how early the staging warps fetch the next brick (in work items still unclaimed): with many bricks per CTA a
+    // brick's worth hides the staging latency; with few, bricks go only to CTAs whose warps are already waiting
+    static const int la_env = std::getenv("LJGPU_BRICK_LOOKAHEAD") ? std::atoi(std::getenv("LJGPU_BRICK_LOOKAHEAD")) : -1;   // tuning knob: eighths of a brick
+    const unsigned eighths = la_env >= 0 ? (unsigned)la_env : (s->nblocks_tile >= 8u * grid ? 8u : 0u);
+    a.lookahead = s->tile_ipb * eighths / 8u;
     tile_kernel<MODE, UNIT_SIGMA><<<grid, kBrickThreads, tile_smem(s), s->st>>>(s->c, s->tile_grid(), a, guarded);
     s->check_launch("tile_kernel");
 }

@@ -179,6 +179,8 @@ struct TileArgs {
     unsigned tcap;                         // atoms per tile slot (shared-memory capacity)
     unsigned slots;                        // tiles in flight per CTA (2..kBrickSlotsMax)
     unsigned ipb;                          // work items per brick: ceil(most home atoms of a brick / 32)
+    unsigned lookahead;                    // a brick is requested once the computing warps have claimed all but this many of the work
+                                           // items before it (0: only when a warp already waits for it) - see the staging loop
     // slab path over peer memory: wait until both neighbours have pushed this step's halo (null: no wait)
     Mailbox* mail;                         // (the sequence number to wait for is ctrl->halo_seq: the push of this step has already counted itself)
 };
@@ -225,7 +227,12 @@ tile_kernel(LJConst c, TileGrid g, TileArgs a, int guarded) {
         const unsigned stager = warp - (unsigned)kBrickWarps;
         for (unsigned k = 0;; ++k) {
             const unsigned slot = k % a.slots, use = k / a.slots;
-            while (ld_acquire_smem(&s_drained[slot]) < use) spin_pause();  // every work item of the brick that was there is finished
+            // The slot is free (every work item of the brick that was there is finished) AND the computing warps are about to
+            // need another brick.  Taking tickets as early as the ring allows would hoard up to four bricks per CTA: at the end
+            // of the queue (and from the very start when there are only a few bricks per CTA) some SMs would then sit on
+            // several unstarted bricks while others idle.
+            while (ld_acquire_smem(&s_drained[slot]) < use ||
+                   (int)(k * a.ipb) - (int)ld_acquire_smem(&s_item) > (int)a.lookahead) spin_pause();
             if (lane == 0 && stager == 0) s_ticket[k & 1u] = atomicAdd(&a.ctrl->brick_next, 1u);
             if (kBrickStagers > 1) named_barrier_sync(3, 32u * kBrickStagers); else __syncwarp();
             const unsigned b = s_ticket[k & 1u];

@@ -96,7 +96,7 @@ extern "C" int ljemul_forces(unsigned ctas, unsigned n, double L, double rcut, d
 
     auto run = [&](int mode, uint32_t* nl, uint32_t* nl_in, unsigned capq) {
         TileArgs a{p.pos.data(), nl, slot_count.data(), nl_in, slot_in_count.data(), f[0].data(), f[1].data(), f[2].data(),
-                   partial.data(), &ctrl, capq, tcap, slots, ipb, nullptr};
+                   partial.data(), &ctrl, capq, tcap, slots, ipb, (ctas & 1u) ? ipb / 2 : 0u, nullptr};
         ljemul::launch(grid, kBrickThreads, smem, [&] {
             switch (mode) {
                 case TILE_LIST_COUNT:  tile_kernel<TILE_LIST_COUNT, false>(p.c, g, a, 0); break;

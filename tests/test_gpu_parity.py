@@ -589,3 +589,62 @@ def test_nve_energy_conservation_and_thermostat(lj):
     mask = expected > 5
     chi2 = float(((hist[mask] - expected[mask]) ** 2 / expected[mask]).sum() / mask.sum())
     assert chi2 < 2.5 and hist.argmax() in (12, 13, 14, 15)
+
+
+def test_long_run_statistics_match_the_reference(lj):
+    """Trajectories diverge chaotically after a few hundred steps, so over long runs the comparison is statistical
+    (BASELINE north star): the same start state is run for 12 000 steps by the reference's own integrator (compiled
+    reference when available, else its restatement) and on the GPU - 6000 steps under the Berendsen thermostat, then 6000
+    steps NVE (tau = 1e300) - and the time averages, the fluctuations, the total-energy drift and the accumulated speed
+    histograms must agree within their statistical errors."""
+    cfg = ol.config(2048)
+    n = cfg["nr_particles"]
+    ref = ol.RefSim(cfg) if ol.have_ref() else ol.Oracle(cfg)
+    g = lj.LennardJonesSimulation(lj.LennardJonesParameters(**cfg), ref.state(), force_kernel=3)
+
+    def run(sim, first, count, is_gpu):
+        ek = np.empty(count); ep = np.empty(count)
+        hist = np.zeros(100)
+        for k in range(count):
+            sim.integrate(first + k, DT)
+            e = sim.get_energies() if is_gpu else sim.energies()
+            ek[k], ep[k] = e[0], e[1]
+            if k % 200 == 199:
+                if is_gpu:
+                    hist += sim.get_speed_histogram(100, 10.0)
+                else:
+                    hist += ol.oracle_speed_histogram(*sim.velocities())
+        return ek / n, ep / n, hist
+
+    def block_err(a, nb=10):
+        b = a[:len(a) // nb * nb].reshape(nb, -1).mean(axis=1)
+        return b.std(ddof=1) / np.sqrt(nb)
+
+    out = {}
+    for name, sim, is_gpu in (("ref", ref, False), ("gpu", g, True)):
+        run(sim, 1, 2000, is_gpu)                                   # melt the lattice
+        ekT, epT, hT = run(sim, 2001, 4000, is_gpu)                 # thermostatted production
+        sim.set_param("tau", 1e300) if is_gpu else sim.set_tau(1e300)
+        ekE, epE, hE = run(sim, 6001, 6000, is_gpu)                 # NVE production
+        out[name] = (ekT, epT, hT, ekE, epE, hE)
+    r, q = out["ref"], out["gpu"]
+    # thermostatted averages: kinetic and potential energy per atom within 4 combined standard errors (and 1 %)
+    for a, b, what in ((r[0], q[0], "ekin"), (r[1], q[1], "epot")):
+        se = np.hypot(block_err(a), block_err(b))
+        assert abs(a.mean() - b.mean()) < 4.0 * se + 1e-3 * abs(a.mean()), (what, a.mean(), b.mean(), se)
+    # NVE: both conserve the total energy equally well - drift and fluctuation per atom
+    etr, etq = r[3] + r[4], q[3] + q[4]
+    drift_r = np.polyfit(np.arange(len(etr)), etr, 1)[0] * len(etr)
+    drift_q = np.polyfit(np.arange(len(etq)), etq, 1)[0] * len(etq)
+    assert abs(drift_r) < 2e-4 and abs(drift_q) < 2e-4, (drift_r, drift_q)
+    assert abs(drift_q - drift_r) < 2e-4
+    assert 0.5 < etq.std() / etr.std() < 2.0, (etq.std(), etr.std())
+    # temperatures of the NVE stretch (set by the same thermostatted ensemble) agree within the statistical error
+    se = np.hypot(block_err(r[3]), block_err(q[3]))
+    assert abs(r[3].mean() - q[3].mean()) < 4.0 * se + 0.01 * r[3].mean()
+    # speed distributions accumulated over the run: two-sample chi-square per populated bin ~ 1
+    hr, hq = r[2] + r[5], q[2] + q[5]
+    mask = (hr + hq) > 50
+    chi2 = float(((hr[mask] - hq[mask]) ** 2 / (hr[mask] + hq[mask])).sum() / mask.sum())
+    assert chi2 < 2.0, chi2
+    g.close()
