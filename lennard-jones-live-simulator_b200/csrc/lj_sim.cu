@@ -1804,3 +1804,20 @@ int ljgpu_free_host(void* p) {
 }
 
 } // extern "C"
+
+#ifdef LJ_BRICK_TRACE
+// developer build only: the brick kernel's timeline of its last TILE_FORCE_LIST launch, as raw TraceEvent records
+extern "C" int ljgpu_debug_trace_dump(const char* path) {
+    std::vector<ljgpu::TraceEvent> ev((size_t)160 * ljgpu::kTraceCap);
+    unsigned n[160];
+    if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+    if (cudaMemcpyFromSymbol(ev.data(), ljgpu::g_trace, ev.size() * sizeof(ljgpu::TraceEvent)) != cudaSuccess) return -2;
+    if (cudaMemcpyFromSymbol(n, ljgpu::g_trace_n, sizeof n) != cudaSuccess) return -3;
+    FILE* f = std::fopen(path, "wb");
+    if (!f) return -4;
+    std::fwrite(n, sizeof n, 1, f);
+    std::fwrite(ev.data(), sizeof(ljgpu::TraceEvent), ev.size(), f);
+    std::fclose(f);
+    return 0;
+}
+#endif

@@ -86,6 +86,23 @@ struct QuadPacker {
     }
 };
 
+#ifdef LJ_BRICK_TRACE   /* developer build only (scripts/brick_trace.py): a timeline of the brick kernel's last launch */
+constexpr unsigned kTraceCap = 2048;                       // events per CTA
+struct TraceEvent { unsigned long long t; unsigned kind, a, b, warp; };     // kind: 0 cta start, 1 ticket, 2 tile staged, 3 item start, 4 item end
+__device__ TraceEvent g_trace[160][kTraceCap];
+__device__ unsigned g_trace_n[160];
+__device__ __forceinline__ void trace_event(unsigned kind, unsigned a, unsigned b) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    if (blockIdx.x >= 160u) return;
+    const unsigned k = atomicAdd(&g_trace_n[blockIdx.x], 1u);
+    if (k < kTraceCap) g_trace[blockIdx.x][k] = TraceEvent{t, kind, a, b, threadIdx.x >> 5};
+}
+#define LJ_TRACE(kind, a, b) do { if (MODE == TILE_FORCE_LIST && (threadIdx.x & 31u) == 0u) trace_event(kind, a, b); } while (0)
+#else
+#define LJ_TRACE(kind, a, b) do { } while (0)
+#endif
+
 struct TileGrid {
     unsigned nc;                 // cells per axis in x and y (periodic)
     unsigned ncz;                // cell layers of the local table (nc, or owned layers + 2 halo layers on a slab)
@@ -217,6 +234,11 @@ tile_kernel(LJConst c, TileGrid g, TileArgs a, int guarded) {
     __syncthreads();
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const size_t slot_doubles = (size_t)a.tcap * 3;
+#ifdef LJ_BRICK_TRACE
+    if (MODE == TILE_FORCE_LIST && threadIdx.x == 0) g_trace_n[blockIdx.x] = 0;
+    __syncthreads();
+    if (warp == 0) LJ_TRACE(0, 0, 0);
+#endif
     // Bricks are handed out by a device-wide counter (ctrl->brick_next): bricks differ in size (partial bricks at the box
     // edge, density fluctuations), and with a fixed brick -> CTA assignment the slowest SM ran 13 % longer than the
     // average one (ncu: sm__cycles_active min / avg / max 368 k / 433 k / 492 k; with the queue 372 k / 399 k / 414 k).
@@ -236,6 +258,8 @@ tile_kernel(LJConst c, TileGrid g, TileArgs a, int guarded) {
             if (lane == 0 && stager == 0) s_ticket[k & 1u] = atomicAdd(&a.ctrl->brick_next, 1u);
             if (kBrickStagers > 1) named_barrier_sync(3, 32u * kBrickStagers); else __syncwarp();
             const unsigned b = s_ticket[k & 1u];
+
+            if (stager == 0) LJ_TRACE(1, k, b);
             if (b >= g.nblocks) {           // the queue is dry: tell the computing warps how many bricks there were
                 if (lane == 0 && stager == 0) {
                     st_release_smem(&s_total, k);
@@ -260,6 +284,7 @@ tile_kernel(LJConst c, TileGrid g, TileArgs a, int guarded) {
                 if (t < ntc) s_src[slot][t] = g.tsrc[(size_t)b * kTileCellsMax + t];
             }
             if (kBrickStagers > 1) named_barrier_sync(1, 32u * kBrickStagers); else __syncwarp();
+            if (stager == 0) LJ_TRACE(5, k, b);
             if (lane == 0 && stager == 0) {
                 s_hdr[slot].brick = b;
                 BrickHeader& h = s_hdr[slot];
@@ -305,11 +330,14 @@ tile_kernel(LJConst c, TileGrid g, TileArgs a, int guarded) {
                         cp_async8(sz_base + li * 8u, gp + 2);
                     }
                 }
+                if (stager == 0) LJ_TRACE(6, k, b);
                 cp_async_wait_all();
+                if (stager == 0) LJ_TRACE(7, k, b);
             }
             // every staging lane's copies have landed, its table words are written: publish the tile
             if (kBrickStagers > 1) named_barrier_sync(2, 32u * kBrickStagers); else __syncwarp();
             if (lane == 0 && stager == 0) st_release_smem(&s_filled, k + 1u);
+            if (stager == 0) LJ_TRACE(2, k, b);
         }
         return;
     }
@@ -342,6 +370,7 @@ tile_kernel(LJConst c, TileGrid g, TileArgs a, int guarded) {
         }
         if (dry) break;
         const BrickHeader& hd = s_hdr[slot];
+        if (chunk * 32u < hd.hn) LJ_TRACE(3, k, chunk);
         const uint32_t* __restrict__ soff = s_off[slot];
         const uint32_t* __restrict__ ssrc = s_src[slot];
         const double* __restrict__ sxy = sm + slot * slot_doubles;
@@ -554,6 +583,7 @@ tile_kernel(LJConst c, TileGrid g, TileArgs a, int guarded) {
             if (lane == 0) a.partial_epot[(size_t)b * a.ipb + chunk] = ew;
         }
         __syncwarp();                                    // every lane's reads of the slot are done
+        if (chunk * 32u < hd.hn) LJ_TRACE(4, k, chunk);
         if (lane == 0) {
             if (atomicAdd(&s_done[slot], 1u) + 1u == a.ipb) {      // the brick's last item: hand the slot back
                 s_done[slot] = 0;
