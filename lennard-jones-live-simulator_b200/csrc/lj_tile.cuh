@@ -455,7 +455,7 @@ tile_kernel(LJConst c, TileGrid g, TileArgs a, int guarded) {
 #pragma unroll
                     for (int u = 0; u < kTileGroup; ++u) {
                         const uint32_t w = cw[(part * kTileGroup + u) >> 1];
-                        jj[u] = (u & 1) ? (w >> 16) : (w & 0xffffu);
+                        jj[u] = __byte_perm(w, 0u, (u & 1) ? 0x4432u : 0x4410u);     // (one PRMT for either half-word)
 #ifdef LJ_EXP_NOCONFLICT /* timing experiment only (steps with dt == 0): every lane reads a different bank - a gather without bank conflicts */
                         if (c.dt == 0.0) jj[u] = (jj[u] & ~31u) | lane;
 #endif
@@ -494,7 +494,9 @@ tile_kernel(LJConst c, TileGrid g, TileArgs a, int guarded) {
                         // padding entries point at the atom itself (d2 == 0): excluded by index
                         const bool in = (d2[u] < c.rc2) && (jj[u] != li);
                         // one select, not a divergent branch: a rejected entry gets 1/d2 := 0, which turns both
-                        // terms below into exact +0 (same bits as selecting them afterwards, half the selects)
+                        // terms below into exact +0 (same bits as selecting them afterwards, half the selects).
+                        // (Predicating the accumulations instead - inline PTX, "@p fma" - was tried: ptxas turns every
+                        // predicated fp64 accumulation into the operation plus two FSEL, eight extra instructions per entry.)
                         const double inv = in ? fast_rcp(d2[u]) : 0.0;
                         const double s2 = UNIT_SIGMA ? inv : c.sigma2 * inv;
                         const double s6 = s2 * s2 * s2;

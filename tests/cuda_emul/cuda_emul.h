@@ -273,6 +273,7 @@ inline int __any_sync(unsigned, int pred) {
 
 inline int __ffs(unsigned v) { return v ? __builtin_ctz(v) + 1 : 0; }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline unsigned __byte_perm(unsigned a, unsigned b, unsigned sel) { unsigned long long v = ((unsigned long long)b << 32) | a; unsigned r = 0; for (int k = 0; k < 4; ++k) r |= (unsigned)((v >> (8 * ((sel >> (4 * k)) & 7u))) & 0xffull) << (8 * k); return r; }
 inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned shift) { shift &= 31u; return shift ? (lo >> shift) | (hi << (32u - shift)) : lo; }
 template <class T> inline unsigned __match_any_sync(unsigned, T v) {
     unsigned m = 0;
