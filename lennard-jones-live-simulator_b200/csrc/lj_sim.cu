@@ -851,7 +851,8 @@ static void launch_tile2(ljgpu_sim* s, int guarded) {
     // how early the staging warps fetch the next brick (in work items still unclaimed): with many bricks per CTA a
     // brick's worth hides the staging latency; with few, bricks go only to CTAs whose warps are already waiting
     static const int la_env = std::getenv("LJGPU_BRICK_LOOKAHEAD") ? std::atoi(std::getenv("LJGPU_BRICK_LOOKAHEAD")) : -1;   // tuning knob: eighths of a brick
-    const unsigned eighths = la_env >= 0 ? (unsigned)la_env : (s->nblocks_tile >= 8u * grid ? 8u : 0u);
+    // (measured at N = 2^17 ... 2^20, profiles/r03a_*, r03h_*: a full brick from ~12 bricks per CTA on, half a brick from ~4, none below)
+    const unsigned eighths = la_env >= 0 ? (unsigned)la_env : (s->nblocks_tile >= 12u * grid ? 8u : (s->nblocks_tile >= 4u * grid ? 4u : 0u));
     a.lookahead = s->tile_ipb * eighths / 8u;
     tile_kernel<MODE, UNIT_SIGMA><<<grid, kBrickThreads, tile_smem(s), s->st>>>(s->c, s->tile_grid(), a, guarded);
     s->check_launch("tile_kernel");
