@@ -128,6 +128,7 @@ struct Mailbox {
     unsigned long long pub_flag[kMaxPeers];          // [source rank] = sequence number of the publication whose atoms that rank has scattered into my frame slice
     unsigned int error;                              // a wait timed out (peer gone): results are invalid
     unsigned int pad;
+    unsigned long long timeout_cycles;               // how long a wait for a peer may take (SM clock cycles) before it is reported as gone
 };
 
 

@@ -347,11 +347,14 @@ __device__ __forceinline__ double ld_sys_f64(const double* p) {
 #endif
     return v;
 }
-// Spin until *flag >= seq; gives up after ~2 s (a peer died) so that no kernel can hang the device.
-__device__ __forceinline__ bool wait_flag(const unsigned long long* flag, unsigned long long seq, unsigned int* error) {
+// Spin until *flag >= seq.  A peer that is merely late (its host has not made the collective call yet) is waited for; a
+// peer that does not answer within mine->timeout_cycles (default ~30 s of SM clock, LJGPU_PEER_TIMEOUT_S) is reported
+// through mine->error instead of hanging the device for ever.
+__device__ __forceinline__ bool wait_flag(const unsigned long long* flag, unsigned long long seq, Mailbox* mine) {
     const long long t0 = clock64();
+    const long long limit = (long long)mine->timeout_cycles;
     while (ld_sys_u64(flag) < seq) {
-        if (clock64() - t0 > 4000000000ll) { atomicExch(error, 1u); return false; }
+        if (clock64() - t0 > limit) { atomicExch(&mine->error, 1u); return false; }
         __nanosleep(100);
     }
     __threadfence_system();
@@ -432,7 +435,7 @@ __device__ __forceinline__ void mailbox_allreduce(const double* tot, double* g, 
         slot[0] = tot[0]; slot[1] = tot[1]; slot[2] = tot[2]; slot[3] = tot[3];
         __threadfence_system();
         st_sys_u64(&dst->red_flag[par][rank], seq);
-        wait_flag(&mine->red_flag[par][threadIdx.x], seq, &mine->error);
+        wait_flag(&mine->red_flag[par][threadIdx.x], seq, mine);
     }
     __syncthreads();                                       // every deposit has arrived before anyone reads
     if ((int)threadIdx.x < world * 4) dep[threadIdx.x] = ld_sys_f64(&mine->red[par][threadIdx.x >> 2][threadIdx.x & 3]);
@@ -716,7 +719,7 @@ slab_publish_scatter_kernel(LJConst c, const double4* __restrict__ pos, const ui
 }
 // copy stream of a slice owner: wait until every device has scattered its atoms of publication `seq` into my slice
 __global__ void slab_publish_wait_kernel(Mailbox* mine, int world, unsigned long long seq) {
-    if ((int)threadIdx.x < world) wait_flag(&mine->pub_flag[threadIdx.x], seq, &mine->error);
+    if ((int)threadIdx.x < world) wait_flag(&mine->pub_flag[threadIdx.x], seq, mine);
 }
 
 // Local reductions + all-reduce through the mailboxes + publication, one launch: the constructor's energy

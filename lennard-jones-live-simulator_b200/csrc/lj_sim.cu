@@ -723,6 +723,12 @@ void ljgpu_sim::setup_p2p() {
     if (std::getenv("LJGPU_SLAB_NCCL") || slab.world > kMaxPeers) return;
     CK(cudaMalloc(&slab.mail, sizeof(Mailbox)));
     CK(cudaMemset(slab.mail, 0, sizeof(Mailbox)));
+    {   // a late peer is waited for, a dead one is not: ~30 s by default (ranks do unequal host work between collective calls)
+        const char* e = std::getenv("LJGPU_PEER_TIMEOUT_S");
+        const double secs = e ? std::max(0.1, std::atof(e)) : 30.0;
+        const unsigned long long cycles = (unsigned long long)(secs * 2.0e9);
+        CK(cudaMemcpy(&slab.mail->timeout_cycles, &cycles, sizeof cycles, cudaMemcpyHostToDevice));
+    }
     CK(cudaMalloc(&slab.push_ticket, sizeof(unsigned)));
     CK(cudaMemset(slab.push_ticket, 0, sizeof(unsigned)));
     CK(cudaMalloc(&slab.pub_ticket, sizeof(unsigned)));

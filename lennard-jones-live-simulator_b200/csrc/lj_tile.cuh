@@ -273,8 +273,8 @@ tile_kernel(LJConst c, TileGrid g, TileArgs a, int guarded) {
             if (lo_halo || hi_halo) {    // slab over peer memory: only bricks whose tile reaches a halo layer wait for that neighbour's push
                 if (lane == 0) {
                     const unsigned long long seq = a.ctrl->halo_seq;
-                    if (lo_halo) wait_flag(&a.mail->halo_flag[0], seq, &a.mail->error);
-                    if (hi_halo) wait_flag(&a.mail->halo_flag[1], seq, &a.mail->error);
+                    if (lo_halo) wait_flag(&a.mail->halo_flag[0], seq, a.mail);
+                    if (hi_halo) wait_flag(&a.mail->halo_flag[1], seq, a.mail);
                 }
                 __syncwarp();
             }

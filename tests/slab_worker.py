@@ -84,7 +84,7 @@ def main():
     counts_mid = g.get_neighbor_counts(cfg["rcut"] + cfg["shell"], True)     # collective; atoms have moved since the binning
     if rank == 0 and n_atoms <= 65536:      # (the brute-force reference count is O(N^2))
         assert np.array_equal(counts_mid, ol.oracle_pair_counts(cfg["cell_length"], x, y, z, cfg["rcut"] + cfg["shell"]))
-    dist.barrier()              # nobody steps on while rank 0 counts: a device waits ~2 s for its peers, then reports them gone
+    dist.barrier()              # nobody steps on while rank 0 counts (a device waits LJGPU_PEER_TIMEOUT_S, default 30 s, for its peers, then reports them gone)
 
     # publication, the reference's per-step call pattern (integrate + publish_state): every device delivers its slice of
     # the original-order frame into ONE frame shared by all ranks; the frame must equal the collective getter bit for bit
@@ -114,6 +114,7 @@ def main():
     # across re-binnings and migrations
     o.run(steps + 1, long_steps, DT)
     say("long run")
+    dist.barrier()              # the oracle's run takes a different time on every rank (tens of seconds at N = 262 144)
     g.integrate_n(steps + 1, long_steps, DT)
     say("long run done")
     ek, ep, _ = g.get_energies()
