@@ -817,7 +817,7 @@ void ljgpu_sim::rebuild() {
     check_launch("tile_table");
     fetch_ctrl();
     // launch shapes only grow (a few spare shared-memory records cost nothing; a changed shape costs a graph capture)
-    tcap = std::max(tcap, ((h_ctrl->max_tile + 63) / 64) * 64);
+    tcap = std::max(tcap, ((h_ctrl->max_tile + 32 + 63) / 64) * 64);     // (32 spare records: the list build reads whole rounds of candidates)
     tile_ipb = std::max(tile_ipb, (h_ctrl->max_home + 31) / 32);
     if (tile_ipb > (unsigned)kBrickItemsMax) {
         if (!slab.on) throw LjError(LJGPU_ESTATE, "a brick holds more home atoms than the brick kernel's work items cover");

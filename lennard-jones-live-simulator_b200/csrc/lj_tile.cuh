@@ -47,6 +47,10 @@ constexpr int kBrickWarps = LJ_BRICK_WARPS;                           // computi
 constexpr int kBrickStagers = LJ_BRICK_STAGERS;                       // staging warps per CTA (they share the rows of a tile)
 constexpr int kBrickThreads = 32 * (kBrickWarps + kBrickStagers);
 constexpr int kBrickSlotsMax = 4;                                     // tiles in flight per CTA (fewer when tiles are large)
+#ifndef LJ_FILL_BATCH
+#define LJ_FILL_BATCH 4
+#endif
+constexpr int kFillBatch = LJ_FILL_BATCH;                            // candidates per round of the list build (measured: 4 -> 1005 us per re-binning at N = 2^20, 8 -> 1093, 16 spills)
 constexpr int kBrickItemsMax = 32;                                    // work items (32 home atoms each) per brick
 
 // Shared-memory image of a tile: (x, y) pairs as 16-byte records followed by the z column.  The list walk is a
@@ -254,7 +258,7 @@ tile_kernel(LJConst c, TileGrid g, TileArgs a, int guarded) {
             // of the queue (and from the very start when there are only a few bricks per CTA) some SMs would then sit on
             // several unstarted bricks while others idle.
             while (ld_acquire_smem(&s_drained[slot]) < use ||
-                   (int)(k * a.ipb) - (int)ld_acquire_smem(&s_item) > (int)a.lookahead) spin_pause();
+                   (int)(k * a.ipb) - (int)ld_acquire_smem(&s_item) > (int)a.lookahead) spin_pause_long();
             if (lane == 0 && stager == 0) s_ticket[k & 1u] = atomicAdd(&a.ctrl->brick_next, 1u);
             if (kBrickStagers > 1) named_barrier_sync(3, 32u * kBrickStagers); else __syncwarp();
             const unsigned b = s_ticket[k & 1u];
@@ -525,38 +529,52 @@ tile_kernel(LJConst c, TileGrid g, TileArgs a, int guarded) {
                     for (unsigned j = j0; j < j1; ++j)
                         if (j != li) LJ_TILE_PAIR(j)
                 } else {
-                    // list build / count: four candidates per round, loads and distances batched
-                    for (unsigned jb = j0; jb < j1; jb += 4) {
-                        double d2[4];
-                        int far = 0;
+                    // list build / count.  Candidates are examined 32 at a time, kFillBatch per round with loads and distances
+                    // batched (the scan is bound by the latency of its dependent chain load -> difference -> square -> sum
+                    // -> compare per warp, like the list walk, but a candidate only keeps two registers alive, so many can be
+                    // in flight); acceptance goes into a bit mask and only the accepted ones are pushed afterwards.
+                    for (unsigned jc = j0; jc < j1; jc += 32) {
+                        unsigned mask = 0;
+                        const unsigned jend = min(jc + 32u, j1);
+                        // (a round may read up to kFillBatch - 1 records past j1: they exist - every slot has 32 spare records,
+                        // see tcap - and their bits are cleared below; the atom itself is dropped when the mask is drained)
+                        for (unsigned jb = jc; jb < jend; jb += kFillBatch) {
+                            double d2[kFillBatch];
+                            int far = 0;
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const unsigned j = min(jb + u, j1 - 1);
-                            double dx, dy, dz;
-                            tile_ld(sxy, sz, j, dx, dy, dz);
-                            dx = pix - dx; dy = piy - dy; dz = piz - dz;
-                            d2[u] = fma(dz, dz, fma(dy, dy, dx * dx));
-                            far = max(far, __double2hiint(d2[u]));
-                        }
-                        if (far >= far2_hi) {
-#pragma unroll
-                            for (int u = 0; u < 4; ++u)
-                                if (maybe_wrapped(d2[u], far2_hi)) {
-                                    const unsigned j = min(jb + u, j1 - 1);
-                                    double dx, dy, dz;
-                                    tile_ld(sxy, sz, j, dx, dy, dz);
-                                    dx = min_image(pix - dx, c.L, c.halfL); dy = min_image(piy - dy, c.L, c.halfL);
-                                    dz = min_image(piz - dz, c.L, c.halfL);
-                                    d2[u] = fma(dz, dz, fma(dy, dy, dx * dx));
-                                }
-                        }
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const unsigned j = jb + u;
-                            if (j < j1 && d2[u] <= c.list_cut2 && j != li) {
-                                if (MODE == TILE_LIST_FILL) pk.push(j, out_row, a.capq);   // (entries beyond the capacity are counted, not stored)
-                                else ++cnt;
+                            for (int u = 0; u < kFillBatch; ++u) {
+                                double dx, dy, dz;
+                                tile_ld(sxy, sz, jb + u, dx, dy, dz);
+                                dx = pix - dx; dy = piy - dy; dz = piz - dz;
+                                d2[u] = fma(dz, dz, fma(dy, dy, dx * dx));
+                                far = max(far, __double2hiint(d2[u]));
                             }
+                            if (far >= far2_hi) {
+#pragma unroll
+                                for (int u = 0; u < kFillBatch; ++u)
+                                    if (maybe_wrapped(d2[u], far2_hi)) {
+                                        double dx, dy, dz;
+                                        tile_ld(sxy, sz, jb + u, dx, dy, dz);
+                                        dx = min_image(pix - dx, c.L, c.halfL); dy = min_image(piy - dy, c.L, c.halfL);
+                                        dz = min_image(piz - dz, c.L, c.halfL);
+                                        d2[u] = fma(dz, dz, fma(dy, dy, dx * dx));
+                                    }
+                            }
+                            unsigned mb = 0;
+#pragma unroll
+                            for (int u = 0; u < kFillBatch; ++u) mb |= (d2[u] <= c.list_cut2) ? (1u << u) : 0u;
+                            mask |= mb << (jb - jc);
+                        }
+                        mask &= 0xffffffffu >> (32u - (jend - jc));          // candidates past the end of the row
+                        if (li - jc < 32u) mask &= ~(1u << (li - jc));         // the atom itself
+                        if (MODE == TILE_LIST_FILL) {
+                            while (mask) {                       // ascending j: the list keeps the order of the scan
+                                const unsigned bit = (unsigned)__ffs((int)mask) - 1u;
+                                mask &= mask - 1u;
+                                pk.push(jc + bit, out_row, a.capq);   // (entries beyond the capacity are counted, not stored)
+                            }
+                        } else {
+                            cnt += (unsigned)__popc(mask);
                         }
                     }
                 }

@@ -85,7 +85,7 @@ extern "C" int ljemul_forces(unsigned ctas, unsigned n, double L, double rcut, d
 
     ljemul::launch(cdivu(nblocks, 4), 128, 0, [&] { tile_table_kernel(g, p.cstart.data(), p.ccount.data(), tsrc.data(), toff.data(), &ctrl); });
     if (ctrl.max_tile > 65535) return -3;
-    const unsigned tcap = ((ctrl.max_tile + 63) / 64) * 64;
+    const unsigned tcap = ((ctrl.max_tile + 32 + 63) / 64) * 64;
     const unsigned slots = 3, ipb = (ctrl.max_home + 31) / 32;
     const size_t smem = (size_t)tcap * kTileRecBytes * slots;
     partial.assign((size_t)nblocks * ipb, 0.0);
