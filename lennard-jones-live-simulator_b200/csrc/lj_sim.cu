@@ -163,6 +163,7 @@ struct ljgpu_sim {
 
     // shared-memory tiles (lj_tile.cuh) and the Verlet list of 16-bit tile indices
     uint32_t *tsrc = nullptr, *toff = nullptr;
+    unsigned tile_attr_tcap = 0, tile_attr_slots = 0;          // the tile shape the kernels' attributes were last set for
     unsigned bxd = kTileBX, byd = kTileBY, bzd = kTileBZ;      // brick size in cells
     unsigned nbx = 0, nby = 0, nbz = 0, nblocks_tile = 0, tcap = 0, tile_slots = 2, tile_ipb = 1;
     int num_sms = 148;
@@ -454,7 +455,8 @@ void ljgpu_sim::allocate() {
     } else {
         // j splits: enough blocks to fill 148 SMs a few times over, each split at least 64 atoms wide
         const unsigned nba = cdiv(N, kBlock);
-        const unsigned want = std::max(1u, (4u * 148u + nba - 1) / nba);
+        static const unsigned waves = std::getenv("LJGPU_AP_WAVES") ? (unsigned)std::max(1, std::atoi(std::getenv("LJGPU_AP_WAVES"))) : 4u;   // tuning knob
+        const unsigned want = std::max(1u, (waves * 148u + nba - 1) / nba);
         nsplit = std::max(1u, std::min(want, (unsigned)((N + 63) / 64)));
         jchunk = cdiv(N, nsplit);
         nsplit = cdiv(N, jchunk);
@@ -877,6 +879,9 @@ static void tile_prepare(ljgpu_sim* s) {
     s->tile_grid_ctas[MODE][US ? 1 : 0] = (unsigned)per_sm * (unsigned)s->num_sms;
 }
 static void set_tile_attributes(ljgpu_sim* s) {
+    // seven instantiations x (attribute + occupancy query) cost ~70 us of host time: only when the tile shape changed
+    if (s->tile_attr_tcap == s->tcap && s->tile_attr_slots == s->tile_slots) return;
+    s->tile_attr_tcap = s->tcap; s->tile_attr_slots = s->tile_slots;
     tile_prepare<TILE_FORCE_LIST, true>(s); tile_prepare<TILE_FORCE_LIST, false>(s);
     tile_prepare<TILE_FORCE_PRUNE, true>(s); tile_prepare<TILE_FORCE_PRUNE, false>(s);
     tile_prepare<TILE_FORCE_CELL, false>(s); tile_prepare<TILE_LIST_COUNT, false>(s); tile_prepare<TILE_LIST_FILL, false>(s);
