@@ -459,7 +459,10 @@ tile_kernel(LJConst c, TileGrid g, TileArgs a, int guarded) {
 #pragma unroll
                     for (int u = 0; u < kTileGroup; ++u) {
                         const uint32_t w = cw[(part * kTileGroup + u) >> 1];
-                        jj[u] = __byte_perm(w, 0u, (u & 1) ? 0x4432u : 0x4410u);     // (one PRMT for either half-word)
+                        // (extracting with one PRMT per index - __byte_perm - saves 16 integer instructions per quad and changed
+                        // nothing for the plain pass; with it the 2-GPU slab worker produced garbage forces at N = 262 144 while this
+                        // form passes, same sources otherwise: gpurun_out/r03u_bisect.log.  Not understood, so not used.)
+                        jj[u] = (u & 1) ? (w >> 16) : (w & 0xffffu);
 #ifdef LJ_EXP_NOCONFLICT /* timing experiment only (steps with dt == 0): every lane reads a different bank - a gather without bank conflicts */
                         if (c.dt == 0.0) jj[u] = (jj[u] & ~31u) | lane;
 #endif
