@@ -7,8 +7,8 @@
 // Here:  kick_drift_kernel (the PREVIOUS step's wrap applied lazily, kick1 + scale + drift + displacement
 //                           accumulation and check: one pass over HBM)
 //        force_*_kernel    (on the drifted, not yet wrapped positions, as the reference)
-//        kick2_kernel      (kick2 + sum v^2 + the NEXT step's kick1 kinetic sum)
-//        step_finalize_kernel (fixed-order final reductions, energies, history, rebuild flag).
+//        kick2_kernel      (kick2 + sum v^2 + the NEXT step's kick1 kinetic sum; its last block - ticket - does the
+//                           fixed-order final reductions and publishes energies, history, rebuild flag).
 // Stored positions are the reference's positions BEFORE its wrap of the current step; the wrap
 // (x - L*floor(x/L), .cpp:431-433) is applied wherever the reference would read a wrapped value: at the
 // top of the next drift, in the re-binning, and in every query.  Values are bit-identical to wrapping

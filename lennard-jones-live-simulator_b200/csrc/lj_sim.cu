@@ -857,7 +857,7 @@ void ljgpu_sim::rebuild() {
 }
 
 // The persistent brick kernel (lj_tile.cuh): as many CTAs as stay resident (occupancy x SMs), each streaming bricks
-// through its two-slot ring of shared-memory tiles.
+// through its ring of two to four shared-memory tiles.
 static size_t tile_smem(const ljgpu_sim* s) { return (size_t)s->tcap * kTileRecBytes * s->tile_slots; }
 
 template <int MODE, bool UNIT_SIGMA>

@@ -8,14 +8,15 @@
 // walks its list as 16-bit indices into that tile.
 //
 // Why persistent and warp-specialised (round 2).  The list walk is latency-bound: nothing is saturated (FP64 pipe
-// 42 %, issue slots 48 %, shared-memory pipe 60-70 %), a warp inside the walk issues an instruction every ~6 cycles,
-// and the pass time is inversely proportional to the number of warps that are inside the walk at any moment
-// (profiles/r02b_*).  With one CTA per brick only ~11 of the 24 resident warps were: the rest read tables, waited at
-// barriers, staged, belonged to the 8 % of bricks with more home atoms than threads (a second, almost empty round)
-// or to the partial bricks at the box edge.  Now ONE CTA per SM stays resident and streams bricks through a ring of
-// up to four tiles: a staging warp fills the slots ahead (asynchronous global->shared copies, LDGSTS; full / empty
-// mbarriers per slot) and twenty computing warps pull work items - 32 consecutive home atoms of a brick - from a
-// CTA-wide counter, so every warp walks lists practically all the time, whatever the shapes of the bricks.
+// 45 %, issue slots 55 %, shared-memory pipe 63 %), a warp inside the walk issues an instruction every ~6 cycles, a work
+// item of 32 atoms takes ~10 us whatever the load, and the pass time follows the number of warps that are inside the
+// walk at any moment (profiles/r02b_*, r02t_*, r03c_*).  With one CTA per brick only ~11 of the 24 resident warps were:
+// the rest read tables, waited at barriers, staged, belonged to the 8 % of bricks with more home atoms than threads
+// (a second, almost empty round) or to the partial bricks at the box edge.  Now ONE CTA per SM stays resident and
+// streams bricks - handed out by a device-wide queue - through a ring of up to four tiles: four staging warps fill the
+// slots ahead (asynchronous global->shared copies, LDGSTS; release / acquire counters per ring) and sixteen computing
+// warps pull work items - 32 consecutive home atoms of a brick - from a CTA-wide counter, so every warp walks lists
+// practically all the time, whatever the shapes of the bricks.
 //
 // Reference code replaced: calculate_forces (.cpp:258-330) and build_neighbor_list (.cpp:441-551) of
 // /root/reference/src/simulator/lennardjonessimulation.cpp.
